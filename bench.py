@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- Jacobi GLUP/s of the effective-diffusivity hot path on B200 (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json configs[1] -- the bundled 00042.jpg (1002 x 2007,
+decoded by the reference's own decoder and committed as tests/golden/images.npz) with 4x mesh
+amplification = 4008 x 8028 = 32 176 224 cells, shipped input.txt defaults (3-phase, Ds 0,
+Df 1, Dg 1 237 500, CL 0, CR 1).  If the fixture is missing a synthetic three-tone image of the
+same shape is used and `data` says so.
+
+A "step" is one check interval of the reference loop (Deff2D.cuh:1232-1290): `check_every`
+(10 000) damped-Jacobi sweeps followed by the boundary-flux Deff evaluation and the stop-rule
+update, on the resident domain.  value = cells x sweeps / device time (CUDA events on the
+launching stream, max over ranks), counted per sweep.  The iterate (2 x 257 MB) is larger than
+L2 (126 MB), so no L2 flush is needed between steps.
+
+e2e: the same metric through the C ABI with HOST buffers: every step uploads the image
+(deff2d_domain_load: H2D, threshold + amplification, FloodFill, tables), runs the reference loop
+for check_every + 1 sweeps (deff2d_domain_solve: two checks) and reads Deff back.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                  [--sweeps-per-step S] [--kernel 0|1|2] [--tblock T]
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+AMP = 4
+ALG_BYTES_PER_LUP = 16.0       # one FP64 read + one FP64 write of x per lattice update
+
+
+def load_workload():
+    fx = os.path.join(ROOT, "tests", "golden", "images.npz")
+    if os.path.exists(fx):
+        return np.load(fx)["img00042"], "bundled 00042.jpg (decoded fixture), coefficients/iterate synthetic-free"
+    rng = np.random.default_rng(42)
+    z = rng.random((2007, 1002))
+    for _ in range(6):
+        z = (z + np.roll(z, 1, 0) + np.roll(z, -1, 0) + np.roll(z, 1, 1) + np.roll(z, -1, 1)) / 5
+    q1, q2 = np.quantile(z, [0.3, 0.7])
+    img = np.where(z < q1, 0, np.where(z < q2, 150, 255)).astype(np.uint8)
+    return img, "synthetic three-tone 1002x2007 (fixture missing)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                     nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:      # NVML missing: report what we know
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+# --------------------------------------------------------------------------------- reference arm
+
+def run_reference(args):
+    """The reference's own code on host cores (it ships GPU-only; oracle/_ref is its unmodified
+    host logic + kernel body run on OpenMP threads).  Each step = one call of its JacobiGPU on the
+    benchmark domain, bounded to `ref_sweeps` sweeps; GLUP/s from its own event timer."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import _oracle as O
+    img, data = load_workload()
+    three_phase = True
+    ref = O.reference("cpu")
+    nthreads = O.oracle().orc_num_threads()
+    if args.ref_crop:
+        img = img[:args.ref_crop, :]
+    Ds, Df, Dg = 0.0, 1.0, 1237500.0
+    D = O.fill_D(img, AMP, AMP, 3, Ds, Df, Dg)
+    Ny, Nx = D.shape
+    cells = Nx * Ny
+    G, _ = O.floodfill(O.grid_mask(img, AMP, AMP, 200))
+    x0 = O.init_x(Nx, Ny, 0.0, 1.0)
+    sweeps = args.ref_sweeps
+    if ref is not None:
+        kind = "reference"
+        A, b = O.ref_discretize(D, 0.0, 1.0, G if three_phase else None)
+
+        def step():
+            r = O.ref_jacobi(A, b, x0, D, 0.0, 1.0, 1e-30, sweeps)
+            return r["ms"] / 1000.0, r["iters"]
+    else:
+        kind = "port"
+        A, b = O.discretize(D, 0.0, 1.0, G if three_phase else None)
+
+        def step():
+            r = O.jacobi(A, b, x0, D, 0.0, 1.0, 1e-30, sweeps)
+            return r["seconds"], r["iters"]
+    for _ in range(args.warmup):
+        step()
+    tot_s, tot_it = 0.0, 0
+    for _ in range(args.steps):
+        s, it = step()
+        tot_s += s
+        tot_it += it
+    glups = cells * tot_it / tot_s / 1e9
+    sample = "%d sweeps per step of %s's JacobiGPU loop on %dx%d cells, %d OpenMP threads" % (
+        sweeps, "the reference" if kind == "reference" else "the oracle port", Nx, Ny, nthreads)
+    line = {"impl": "reference", "metric": "jacobi_glups", "value": glups, "unit": "GLUP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1000,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": data,
+            "config": {"workload": "configs[1]: 00042.jpg x4 mesh amplification (%dx%d cells), 3-phase shipped defaults; "
+                                   "bounded sample: %s" % (Nx, Ny, sample)},
+            "cpu_baseline": {"value": glups, "unit": "GLUP/s", "cores": nthreads, "kind": kind, "sample": sample},
+            "e2e": {"value": glups, "unit": "GLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------- our arm
+
+def cpu_baseline(img, sweeps, three_phase=True):
+    import _oracle as O
+    o = O.make_opts(Ds=0.0, Df=1.0, Dg=1237500.0, ampx=AMP, ampy=AMP, nphase=3 if three_phase else 2)
+    d = np.zeros(1)
+    img = np.ascontiguousarray(img)
+    secs = O.oracle().orc_time_sweeps(O._up(img), img.shape[1], img.shape[0], o, 1 if three_phase else 0, sweeps, O._dp(d))
+    cells = img.shape[0] * img.shape[1] * AMP * AMP
+    n = O.oracle().orc_num_threads()
+    return {"value": cells * sweeps / secs / 1e9, "unit": "GLUP/s", "cores": n, "kind": "port",
+            "sample": "%d sweeps of the oracle's restatement of updateX_SOR (A[n][5]+b, 80 B/LUP) on the full "
+                      "%dx%d domain, %d OpenMP threads, %.1f s" % (sweeps, img.shape[1] * AMP, img.shape[0] * AMP, n, secs)}
+
+
+def run_ours(args):
+    import torch
+    import effectivediffusivityfvm_b200 as E
+    rank, local_rank, world = dist_env()
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    img, data = load_workload()
+    H, W = img.shape
+    Nx, Ny = W * AMP, H * AMP
+    ctx = E.Deff2D(local_rank)
+    p = E.default_params(amp_x=AMP, amp_y=AMP)          # shipped defaults: 3-phase, Ds 0, Df 1, Dg 1237500
+    ctx.set_kernel(args.kernel, args.tblock)
+    S = args.sweeps_per_step
+    slab_mode = world > 1
+    if slab_mode:
+        from effectivediffusivityfvm_b200 import slab as slabmod
+        dom = slabmod.SlabDomain(ctx, img, p, rank, world, weak=True)
+        cells = dom.global_cells
+        launch_sweeps, flux = dom.sweeps, dom.flux
+    else:
+        ctx.domain_load(img, 3, p)
+        cells = Nx * Ny
+        launch_sweeps, flux = ctx.sweeps, lambda: ctx.flux()[0]
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        launch_sweeps(S)
+        return flux()            # K4 + stop-rule state; blocks for the 8-byte result like the reference's check
+
+    for _ in range(max(args.warmup, 3) if not args.allow_short_warmup else args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        deff = None
+        for _ in range(args.steps):
+            deff = step()
+        ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.kernel_launches - l0
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = cells * S * args.steps / (ms * 1e-3) / 1e9
+
+    # roofline of the dominant kernel (the sweep): live CUDA-event time of sweep launches only
+    sweep_ms = ctx.sweeps_timed(S) if not slab_mode else ms / args.steps
+    sweep_launches_per_step = (launches / args.steps) - 2 if not slab_mode else None
+    peak, peak_src = measured_peaks()
+    local_cells = cells // world
+    achieved = ALG_BYTES_PER_LUP * local_cells * S / (sweep_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "sweep (K%d, tblock %d)" % (args.kernel, args.tblock),
+                "alg_bytes_per_launch": ALG_BYTES_PER_LUP * local_cells * (S / max(sweep_launches_per_step or S, 1)),
+                "avg_launch_us": sweep_ms * 1e3 / max(sweep_launches_per_step or S, 1)}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            roofline["traffic"] = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    # end to end through the C ABI with host buffers
+    e2e = None
+    if not slab_mode:
+        Se = S + 1                                          # sweep 0 + check, S sweeps + check (cuh:1243)
+        e_steps = max(1, min(args.steps, 3))
+        ctx.domain_load(img, 3, p)
+        ctx.solve(1e-30, Se)
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            ctx.domain_load(img, 3, p)                      # H2D image + pinned mask, assembly, tables
+            r = ctx.solve(1e-30, Se)                        # 2 checks; Deff read back (D2H)
+        dt = time.perf_counter() - t0
+        e2e = {"value": cells * Se * e_steps / dt / 1e9, "unit": "GLUP/s",
+               # image + FloodFill mask (1 B/cell) + weight LUT and dead table
+               "h2d_bytes_per_step": int(img.size + Nx * Ny + 2048 * 32 + 2048),
+               # phase counts (48 B) + the convergence state read at each of the 2 checks
+               "d2h_bytes_per_step": int(48 + 2 * 2120), "steps": e_steps, "sweeps_per_step": Se,
+               "deff_raw": r["deff_raw"]}
+    else:
+        e2e = {"value": value, "unit": "GLUP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 16,
+               "note": "slab mode: domain resident, only {Q1,Q2} leave the device per step"}
+
+    line = {"metric": "jacobi_glups", "value": value, "unit": "GLUP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": data,
+            "config": {"workload": "configs[1]: 00042.jpg x4 mesh amplification (%dx%d cells%s), 3-phase shipped "
+                                   "input.txt defaults; step = %d sweeps + flux/Deff check" %
+                                   (Nx, Ny, "" if world == 1 else " per GPU, stacked into %d row slabs with NCCL halo exchange" % world, S),
+                       "cells": cells, "sweeps_per_step": S, "l2_policy": "working set 2x%.0f MB > 126 MB L2, no flush needed" % (Nx * Ny * 8 / 1e6),
+                       "kernel": args.kernel, "tblock": args.tblock},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "deff_raw": deff}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(img, args.cpu_sweeps)
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sweeps-per-step", type=int, default=10000)
+    ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--tblock", type=int, default=0)
+    ap.add_argument("--cpu-sweeps", type=int, default=40)
+    ap.add_argument("--ref-sweeps", type=int, default=20)
+    ap.add_argument("--ref-crop", type=int, default=0, help="use only the first N source rows for the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--allow-short-warmup", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

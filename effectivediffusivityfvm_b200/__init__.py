@@ -1,0 +1,15 @@
+"""effectivediffusivityfvm_b200 -- B200-native (sm_100a) effective-diffusivity solve.
+
+The hot path of adama-wzr/EffectiveDiffusivityFVM (image -> phases -> FVM coefficients ->
+damped-Jacobi sweeps -> boundary-flux Deff) as hand-written CUDA behind a C ABI
+(include/deff2d.h, libdeff2d.so), plus this thin host-side mirror of the reference's driver
+interface.  There is no CPU fallback: the API raises if the CUDA library is not built or no
+device is present.
+"""
+from ._lib import (LIB_PATH, MODE_2PH_BATCH, MODE_2PH_SINGLE, MODE_3PH, Input, Params, Result)
+from .api import (Deff2D, Deff2DError, build_tables, default_params, floodfill, load_image, nccl_unique_id,
+                  read_input_file)
+
+__all__ = ["Deff2D", "Deff2DError", "Params", "Result", "Input", "default_params", "read_input_file",
+           "build_tables", "floodfill", "load_image", "nccl_unique_id", "MODE_2PH_SINGLE", "MODE_2PH_BATCH",
+           "MODE_3PH", "LIB_PATH"]

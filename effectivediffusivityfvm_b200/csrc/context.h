@@ -1,0 +1,84 @@
+// context.h -- the opaque per-device context behind the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;     // elements
+};
+
+struct deff2d_ctx {
+    int device = 0;
+    cudaDeviceProp prop;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
+    std::string error;
+
+    // resident domain
+    bool loaded = false;
+    int64_t Nx = 0, Ny = 0;          // local interior (incl. slab halo rows)
+    int64_t NxG = 0, NyG = 0;        // global domain (dx = 1/NxG, dy = 1/NyG)
+    int64_t pitch = 0, rows = 0;
+    int64_t own_first = 0, own_rows = 0;     // rows this context owns (flux, counts)
+    int64_t halo_above = 0, halo_below = 0, grow0 = 0;
+    int nphase = 2;
+    double Dphase[3] = {1, 0, 0};    // fluid, solid, gas of the current stage
+    double CL = 0, CR = 1, omega = 2.0 / 3.0;
+    int check_every = 10000;
+    int cur = 0;                     // x[cur] holds the newest iterate
+    int pathflag = 0;
+    double porosity = 0;
+    int64_t src_pixels = 0;
+    bool in_batch = false;
+
+    DevBuf<double> x[2];
+    DevBuf<uint8_t> code, img, grid, dead, dense8;
+    DevBuf<double> lut, dense;
+    std::vector<uint8_t> h_grid;
+
+    deff2d::SolveState *d_state = nullptr, *h_state = nullptr;
+    deff2d::Counts *d_counts = nullptr, *h_counts = nullptr;
+    double *d_scalar = nullptr, *h_scalar = nullptr;
+
+    // kernel selection
+    int kernel = 0;                  // 0 default, 1 simple, 2 TMA tiled
+    int tblock = 1;
+    int64_t launches = 0;
+
+    // TMA tiled sweep state (sweep_tma.cu)
+    bool tma_ready = false;
+    void *tma = nullptr;
+
+    // multi-GPU slab state (slab.cu)
+    void *slab = nullptr;
+};
+
+namespace deff2d {
+
+void set_error(deff2d_ctx *c, const char *fmt, ...);
+DomainView view(const deff2d_ctx *c);
+int solve_loop(deff2d_ctx *c, double tol, int64_t max_iter, bool verbose_checks, double print_div,
+               int64_t *iters_out);
+int solve_image_impl(deff2d_ctx *c, const uint8_t *gray, int W, int H, const deff2d_params *p,
+                     deff2d_result *res, double *field, int image_number);
+
+// sweep_tma.cu: enqueue up to min(n, tblock) sweeps with the TMA tiled kernel; *done = sweeps
+// enqueued (0: this domain is not eligible, caller falls back to the streaming kernel).
+int launch_sweep_tma(deff2d_ctx *c, int64_t n, int64_t *done);
+void tma_destroy(deff2d_ctx *c);
+
+// slab.cu
+int slab_allreduce_q(deff2d_ctx *c);     // no-op unless the context is part of a slab group
+void slab_destroy(deff2d_ctx *c);
+
+// batch.cu: returns 1 when the resident small-image kernel does not cover the request
+int batch_resident_solve(deff2d_ctx *c, const uint8_t *gray, int count, int W, int H,
+                         const deff2d_params *p, deff2d_result *results, double *fields);
+
+}  // namespace deff2d

@@ -1,0 +1,131 @@
+// driver.cpp -- the reference program's dispatch and four drivers (Deff2D.cu:17-50,
+// cuh:1316-2419) on top of the C ABI: same input file, same CSV / CMAP files, same stdout
+// lines; the solve itself is the library's.
+#include "deff2d_internal.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <vector>
+
+// printOptions, cuh:121-175
+static int print_options(const deff2d_input *in)
+{
+    const deff2d_params &p = in->p;
+    if (in->batch == 0) {
+        std::printf("--------------------------------------\n\n");
+        std::printf("Current selected options:\n\n");
+        std::printf("--------------------------------------\n");
+        std::printf("Number of Phases = %d\n", in->nphase);
+        std::printf("DC Fluid = %1.3e\n", p.Df);
+        std::printf("DC Solid = %1.3e\n", p.Ds);
+        std::printf("DC Gas = %1.3e\n", p.Dg);
+        std::printf("Concentration Left = %.2f\n", p.CL);
+        std::printf("Concentration Right = %.2f\n", p.CR);
+        std::printf("Mesh Amp. X = %d\n", p.amp_x);
+        std::printf("Mesh Amp. Y = %d\n", p.amp_y);
+        std::printf("Maximum Iterations = %ld\n", (long)p.max_iter);
+        std::printf("Convergence = %.10f\n", p.tol);
+        std::printf("Name of input image: %s\n", in->input_name);
+        std::printf("Name of output file: %s\n", in->output_name);
+        if (in->print_cmap == 0) std::printf("Print Concentration Map = False\n");
+        else std::printf("Concentration Map Name = %s\n", in->cmap_name);
+        std::printf("--------------------------------------\n\n");
+    } else if (in->batch == 1) {
+        std::printf("--------------------------------------\n\n");
+        std::printf("Running Image Batch:\n\n");
+        std::printf("Number of Phases = %d\n", in->nphase);
+        std::printf("DC Fluid = %1.3e\n", p.Df);
+        std::printf("DC Solid = %1.3e\n", p.Ds);
+        std::printf("DC Gas = %1.3e\n", p.Dg);
+        std::printf("Concentration Left = %.2f\n", p.CL);
+        std::printf("Concentration Right = %.2f\n", p.CR);
+        std::printf("Mesh Amp. X = %d\n", p.amp_x);
+        std::printf("Mesh Amp. Y = %d\n", p.amp_y);
+        std::printf("Maximum Iterations = %ld\n", (long)p.max_iter);
+        std::printf("Convergence = %.10f\n", p.tol);
+        std::printf("Name of output file: %s\n", in->output_name);
+        std::printf("Number of files to run: %d\n", in->num_images);
+        if (in->print_cmap == 1) std::printf("Printing Concentration Distribution for all images.\n");
+        else std::printf("No Concentration maps will be printed.\n");
+        std::printf("--------------------------------------\n\n");
+    } else {
+        std::printf("Options entered are not valid, code will exit.\n");
+        return 1;
+    }
+    return 0;
+}
+
+DEFF2D_EXPORT int deff2d_run_input_file(deff2d_ctx *ctx, const char *path)
+{
+    if (!ctx || !path) return DEFF2D_ERR_ARG;
+    deff2d_input in;
+    int rc = deff2d_read_input_file(path, &in);
+    if (rc) return rc;
+    if (in.p.verbose == 1) print_options(&in);                      // cuh:318-322
+    else if (in.p.verbose != 0) std::printf("Please enter a value of 0 or 1 for 'verbose'. Default = 0.\n");
+    if (in.nphase != 2 && in.nphase != 3) {                         // cu:47-50
+        std::printf("Current option entered for Phases is not supported.\n Exiting now. \n");
+        return DEFF2D_OK;
+    }
+    if (in.batch != 0 && in.batch != 1) {                           // cu:27-30
+        std::cout << "Error: no valid BatchFlag option, check input file." << std::endl;
+        return DEFF2D_OK;
+    }
+    if (in.batch == 0) {
+        // SingleSim (cuh:1635-1841) / SingleSim3Phase (cuh:1316-1633)
+        uint8_t *gray = nullptr;
+        int W = 0, H = 0, ch = 0;
+        rc = deff2d_load_image(in.input_name, &gray, &W, &H, &ch);
+        if (rc) { std::printf("Error: could not read image %s\n", in.input_name); return rc; }   // reference: NULL deref (Q24)
+        if (ch != 1) {                                              // cuh:1665-1668
+            std::printf("Error: please enter a grascale image with 1 channel.\n Current number of channels = %d\n", ch);
+            deff2d_free(gray);
+            return DEFF2D_ERR_ARG;
+        }
+        deff2d_result res;
+        std::vector<double> field;
+        if (in.print_cmap == 1) field.resize((size_t)W * in.p.amp_x * (size_t)H * in.p.amp_y);
+        rc = deff2d_solve_image(ctx, gray, W, H, &in.p, &res, in.print_cmap == 1 ? field.data() : nullptr);
+        deff2d_free(gray);
+        if (rc) return rc;
+        if ((rc = deff2d_write_csv_single(&in, &res))) return rc;   // cuh:1821, cuh:1612
+        if (in.print_cmap == 1)                                     // cuh:1825-1827
+            rc = deff2d_write_cmap(in.cmap_name, field.data(), (int64_t)W * in.p.amp_x, (int64_t)H * in.p.amp_y);
+        return rc;
+    }
+    // BatchSim (cuh:1843-2054) / BatchSim3Phase (cuh:2056-2419): images "%05d.jpg" from 0;
+    // results are written once at the end (cuh:2051); only the 3-phase batch writes
+    // per-image CMAP_%05d.csv files (cuh:2395-2398, quirk Q17).
+    std::vector<deff2d_result> results((size_t)std::max(in.num_images, 0));
+    for (int k = 0; k < in.num_images; k++) {
+        char name[100];
+        std::snprintf(name, sizeof(name), "%05d.jpg", k);           // cuh:1876
+        uint8_t *gray = nullptr;
+        int W = 0, H = 0, ch = 0;
+        rc = deff2d_load_image(name, &gray, &W, &H, &ch);
+        if (rc) { std::printf("Error: could not read image %s\n", name); return rc; }
+        if (ch != 1) {
+            std::printf("Error: please enter a grascale image with 1 channel.\n Current number of channels = %d\n", ch);
+            deff2d_free(gray);
+            return DEFF2D_ERR_ARG;
+        }
+        std::vector<double> field;
+        const bool cmap = (in.nphase == 3 && in.print_cmap == 1);
+        if (cmap) field.resize((size_t)W * in.p.amp_x * (size_t)H * in.p.amp_y);
+        deff2d_params p = in.p;
+        // one image at a time keeps the reference's per-image stdout order; a packed
+        // same-size batch goes through deff2d_solve_batch
+        rc = deff2d_solve_batch(ctx, gray, 1, W, H, &p, &results[(size_t)k], cmap ? field.data() : nullptr);
+        deff2d_free(gray);
+        if (rc) return rc;
+        if (cmap) {
+            char cm[100];
+            std::snprintf(cm, sizeof(cm), "CMAP_%05d.csv", k);      // cuh:2396
+            if ((rc = deff2d_write_cmap(cm, field.data(), (int64_t)W * in.p.amp_x, (int64_t)H * in.p.amp_y))) return rc;
+        }
+    }
+    return deff2d_write_csv_batch(&in, results.data(), in.num_images);
+}

@@ -1,0 +1,204 @@
+// host.cpp -- host-side pieces of the path that need no GPU: FloodFill, the input.txt
+// parser and the CSV / CMAP writers, with the reference's formats and quirks.
+#include "deff2d_internal.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+
+namespace deff2d {
+
+// FloodFill, cuh:557-713.  grid: 1 = solid, anything else = open.  Reachability through
+// open cells from the open cells of the left column; 4-connected; periodic in y
+// (cuh:641-665) but not in x (cuh:675, cuh:687).  The reference's open list is an ordered
+// std::set; the set of reached cells does not depend on the visiting order, so a flat FIFO
+// gives the same result in O(n).  Reference quirk Q11 (cuh:601): the test
+// `Domain[indexR == -1]` reads Domain[0], so while cell (0,0) is marked solid every
+// right-column cell, solid or not, is seeded as well.  Unreached open cells become 2
+// (cuh:701-708).  PathFlag = some visited cell lies in the last column (cuh:619-621).
+int floodfill(uint8_t *grid, int64_t Nx, int64_t Ny)
+{
+    const int64_t n = Nx * Ny;
+    // state: 1 solid, 0 reached, 0xFF not reached yet   (Domain of cuh:573-587)
+    std::vector<uint8_t> dom((size_t)n);
+    for (int64_t k = 0; k < n; k++) dom[(size_t)k] = (grid[k] == 1) ? 1 : 0xFF;
+    std::vector<int64_t> queue;
+    queue.reserve((size_t)(n / 4 + Ny + 16));
+    for (int64_t row = 0; row < Ny; row++) {
+        const int64_t iL = row * Nx, iR = (row + 1) * Nx - 1;
+        if (dom[(size_t)iL] == 0xFF) { dom[(size_t)iL] = 0; queue.push_back(iL); }
+        if (dom[0] != 0) {                       // cuh:601
+            dom[(size_t)iR] = 0;
+            queue.push_back(iR);
+        }
+    }
+    int pathflag = 0;
+    size_t head = 0;
+    auto visit = [&](int64_t t) {
+        if (dom[(size_t)t] == 0xFF) { dom[(size_t)t] = 0; queue.push_back(t); }
+    };
+    while (head < queue.size()) {
+        const int64_t idx = queue[head++];
+        const int64_t row = idx / Nx, col = idx - row * Nx;
+        if (col == Nx - 1) pathflag = 1;
+        visit(((row == 0) ? Ny - 1 : row - 1) * Nx + col);      // north, periodic
+        visit(((row == Ny - 1) ? 0 : row + 1) * Nx + col);      // south, periodic
+        if (col != 0) visit(idx - 1);
+        if (col != Nx - 1) visit(idx + 1);
+    }
+    for (int64_t k = 0; k < n; k++)
+        if (dom[(size_t)k] == 0xFF) grid[k] = 2;
+    return pathflag;
+}
+
+// cuh:402 / cuh:437: the reference accumulates fractions as `+= 1.0/total` per cell, so
+// e.g. 0.3 prints as 0.299999999999983.  Reproduce the rounding, not the closed form.
+double accumulate_fraction(int64_t count, int64_t total)
+{
+    const double inc = 1.0 / (double)total;
+    double s = 0;
+    for (int64_t k = 0; k < count; k++) s += inc;
+    return s;
+}
+
+}  // namespace deff2d
+
+DEFF2D_EXPORT int deff2d_floodfill(uint8_t *grid, int64_t Nx, int64_t Ny)
+{
+    if (!grid || Nx < 1 || Ny < 1) return DEFF2D_ERR_ARG;
+    return deff2d::floodfill(grid, Nx, Ny);
+}
+
+DEFF2D_EXPORT int deff2d_version(void) { return DEFF2D_VERSION; }
+
+DEFF2D_EXPORT void deff2d_free(void *p) { std::free(p); }
+
+DEFF2D_EXPORT void deff2d_default_params(deff2d_params *p)
+{
+    // Deff2DGPU/input.txt:2-18
+    std::memset(p, 0, sizeof(*p));
+    p->Ds = 0; p->Df = 1; p->Dg = 1237500;
+    p->amp_x = 1; p->amp_y = 1;
+    p->CL = 0; p->CR = 1;
+    p->max_iter = 500000;
+    p->tol = 1e-5;
+    p->mode = DEFF2D_MODE_3PH;
+    p->check_every = 10000;
+    p->omega = 2.0 / 3.0;
+    p->tblock = 0;
+    p->verbose = 0;
+    p->strict_reference = 1;
+}
+
+// readInputFile, cuh:234-324.  `sscanf("%s %lf")` per line; keys are case-sensitive and
+// include the colon; numeric values go through a double (so "MaxIter: 5e5" works,
+// cuh:299-300); unknown lines are ignored.  Unlike the reference the struct starts from
+// the shipped defaults instead of uninitialised memory.
+DEFF2D_EXPORT int deff2d_read_input_file(const char *path, deff2d_input *in)
+{
+    if (!path || !in) return DEFF2D_ERR_ARG;
+    std::memset(in, 0, sizeof(*in));
+    deff2d_default_params(&in->p);
+    in->nphase = 3; in->batch = 0; in->num_images = 0; in->print_cmap = 0;
+    std::ifstream f(path);
+    if (!f.is_open()) return DEFF2D_ERR_IO;
+    std::string line;
+    char key[1000], name[1000];
+    while (std::getline(f, line)) {
+        if (line.size() >= sizeof(key)) continue;
+        double v = 0;
+        key[0] = 0;
+        const int got = std::sscanf(line.c_str(), "%999s %lf", key, &v);
+        if (got < 1) continue;
+        auto is = [&](const char *k) { return std::strcmp(key, k) == 0; };
+        auto str = [&](char *dst) {
+            if (std::sscanf(line.c_str(), "%999s %999s", key, name) == 2) std::strcpy(dst, name);
+        };
+        if (is("Ds:")) in->p.Ds = v;
+        else if (is("Df:")) in->p.Df = v;
+        else if (is("Dg:")) in->p.Dg = v;
+        else if (is("MeshAmpX:")) in->p.amp_x = (int)v;
+        else if (is("MeshAmpY:")) in->p.amp_y = (int)v;
+        else if (is("InputName:")) str(in->input_name);
+        else if (is("CR:")) in->p.CR = v;
+        else if (is("CL:")) in->p.CL = v;
+        else if (is("OutputName:")) str(in->output_name);
+        else if (is("printCMap:")) in->print_cmap = (int)v;
+        else if (is("CMapName:")) str(in->cmap_name);
+        else if (is("Convergence:")) in->p.tol = v;
+        else if (is("MaxIter:")) in->p.max_iter = (int64_t)v;
+        else if (is("Verbose:")) in->p.verbose = (int)v;
+        else if (is("RunBatch:")) in->batch = (int)v;
+        else if (is("NumImages:")) in->num_images = (int)v;
+        else if (is("Phases:")) in->nphase = (int)v;
+    }
+    if (in->nphase == 3) in->p.mode = DEFF2D_MODE_3PH;
+    else in->p.mode = in->batch ? DEFF2D_MODE_2PH_BATCH : DEFF2D_MODE_2PH_SINGLE;
+    return DEFF2D_OK;
+}
+
+// outputSingle (cuh:177-188) / outputSingle3Phase (cuh:191-202): append header + one row.
+DEFF2D_EXPORT int deff2d_write_csv_single(const deff2d_input *in, const deff2d_result *r)
+{
+    if (!in || !r) return DEFF2D_ERR_ARG;
+    FILE *o = std::fopen(in->output_name, "a+");
+    if (!o) return DEFF2D_ERR_IO;
+    if (in->nphase == 3) {
+        std::fprintf(o, "imgNum,SVF,LVF,PathFlag,Deff,Time,nElements,converge,ds,df,dg\n");
+        std::fprintf(o, "%s,%f,%f,%d,%1.3e,%f,%d,%1.3e,%1.3e,%1.3e,%1.3e\n", in->input_name, r->SVF, r->LVF,
+                     r->pathflag, r->deff, r->solve_ms / 1000, (int)r->n_cells, r->conv, in->p.Ds, in->p.Df,
+                     in->p.Dg);
+    } else {
+        std::fprintf(o, "imgNum,porosity,PathFlag,Deff,Time,nElements,converge,ds,df\n");
+        std::fprintf(o, "%s,%f,%d,%f,%f,%d,%f,%f,%f\n", in->input_name, r->porosity, r->pathflag, r->deff,
+                     r->solve_ms / 1000, (int)r->n_cells, r->conv, in->p.Ds, in->p.Df);
+    }
+    std::fclose(o);
+    return DEFF2D_OK;
+}
+
+// outputBatch (cuh:204-217) / outputBatch3Phase (cuh:219-232).
+DEFF2D_EXPORT int deff2d_write_csv_batch(const deff2d_input *in, const deff2d_result *r, int count)
+{
+    if (!in || (!r && count > 0)) return DEFF2D_ERR_ARG;
+    FILE *o = std::fopen(in->output_name, "a+");
+    if (!o) return DEFF2D_ERR_IO;
+    if (in->nphase == 3) {
+        std::fprintf(o, "imgNum,SVF,LVF,PathFlag,Deff,Time,nElements,converge,ds,df,dg\n");
+        for (int i = 0; i < count; i++)
+            std::fprintf(o, "%d,%f,%f,%d,%1.5e,%f,%d,%1.5e,%1.5e,%1.5e,%1.5e\n", i, r[i].SVF, r[i].LVF,
+                         r[i].pathflag, r[i].deff, r[i].solve_ms / 1000, (int)r[i].n_cells, r[i].conv,
+                         in->p.Ds, r[i].last_df, in->p.Dg);
+    } else {
+        std::fprintf(o, "imgNum,porosity,PathFlag,Deff,Time,nElements,converge,ds,df\n");
+        for (int i = 0; i < count; i++)
+            std::fprintf(o, "%d,%f,%d,%f,%f,%d,%f,%f,%f\n", i, r[i].porosity, r[i].pathflag, r[i].deff,
+                         r[i].solve_ms / 1000, (int)r[i].n_cells, r[i].conv, in->p.Ds, r[i].last_df);
+    }
+    std::fclose(o);
+    return DEFF2D_OK;
+}
+
+// createCMAP / createCMAPBatch, cuh:497-554: "X,Y,C" then "%d,%d,%1.3e" per cell, y outer,
+// x inner, file truncated.  Formatting goes through one large buffer per row block instead
+// of one fprintf per cell (the text is identical).
+DEFF2D_EXPORT int deff2d_write_cmap(const char *path, const double *field, int64_t Nx, int64_t Ny)
+{
+    if (!path || !field || Nx < 1 || Ny < 1) return DEFF2D_ERR_ARG;
+    FILE *o = std::fopen(path, "w+");
+    if (!o) return DEFF2D_ERR_IO;
+    std::fputs("X,Y,C\n", o);
+    std::vector<char> buf((size_t)Nx * 40 + 64);
+    for (int64_t i = 0; i < Ny; i++) {
+        size_t pos = 0;
+        for (int64_t j = 0; j < Nx; j++)
+            pos += (size_t)std::snprintf(buf.data() + pos, 40, "%d,%d,%1.3e\n", (int)j, (int)i,
+                                         field[i * Nx + j]);
+        std::fwrite(buf.data(), 1, pos, o);
+    }
+    std::fclose(o);
+    return DEFF2D_OK;
+}

@@ -1,0 +1,326 @@
+// image_io.cpp -- image ingest for the drop-in driver: decodes a file to 8-bit gray the way
+// the reference's `stbi_load(name, &W, &H, &nCh, 1)` call does (cuh:342, cuh:377): format is
+// sniffed from the content, not the extension; the channel count reported is the file's.
+// Own decoders, written from the format specifications: binary/ASCII PGM/PPM, PNG (all
+// colour types and bit depths, non-interlaced and Adam7) and baseline/progressive JPEG
+// (jpeg_decode.cpp).  Colour is reduced to luma with the integer weights 77/150/29 >> 8.
+#include "deff2d_internal.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace deff2d {
+
+int jpeg_decode_gray(const uint8_t *data, size_t len, std::vector<uint8_t> &out, int *W, int *H, int *ch,
+                     std::string &err);
+
+static inline uint8_t luma(int r, int g, int b) { return (uint8_t)(((r * 77) + (g * 150) + (29 * b)) >> 8); }
+
+// ---------------------------------------------------------------------------------- PNM
+
+static bool pnm_token(const uint8_t *d, size_t n, size_t &pos, int &val)
+{
+    for (;;) {
+        while (pos < n && (d[pos] == ' ' || d[pos] == '\t' || d[pos] == '\n' || d[pos] == '\r')) pos++;
+        if (pos < n && d[pos] == '#') { while (pos < n && d[pos] != '\n' && d[pos] != '\r') pos++; continue; }
+        break;
+    }
+    if (pos >= n || d[pos] < '0' || d[pos] > '9') return false;
+    long v = 0;
+    while (pos < n && d[pos] >= '0' && d[pos] <= '9') { v = v * 10 + (d[pos] - '0'); pos++; if (v > (1 << 30)) return false; }
+    val = (int)v;
+    return true;
+}
+
+static int pnm_decode(const uint8_t *d, size_t n, std::vector<uint8_t> &out, int *W, int *H, int *ch, std::string &err)
+{
+    const int kind = d[1] - '0';      // 2 ascii gray, 3 ascii rgb, 5 raw gray, 6 raw rgb
+    size_t pos = 2;
+    int w, h, maxv;
+    if (!pnm_token(d, n, pos, w) || !pnm_token(d, n, pos, h) || !pnm_token(d, n, pos, maxv) || w < 1 || h < 1 ||
+        maxv < 1 || maxv > 65535) { err = "bad PNM header"; return DEFF2D_ERR_IO; }
+    const int comp = (kind == 3 || kind == 6) ? 3 : 1;
+    const size_t count = (size_t)w * h * comp;
+    std::vector<int> v(count);
+    if (kind == 5 || kind == 6) {
+        pos++;   // single whitespace after maxval
+        const int bps = maxv > 255 ? 2 : 1;
+        if (pos + count * bps > n) { err = "truncated PNM"; return DEFF2D_ERR_IO; }
+        for (size_t k = 0; k < count; k++) v[k] = (bps == 1) ? d[pos + k] : d[pos + 2 * k];   // 16 bit: high byte
+    } else {
+        for (size_t k = 0; k < count; k++) {
+            int t;
+            if (!pnm_token(d, n, pos, t)) { err = "truncated PNM"; return DEFF2D_ERR_IO; }
+            v[k] = maxv > 255 ? (t >> 8) : t;
+        }
+    }
+    out.resize((size_t)w * h);
+    for (size_t k = 0; k < (size_t)w * h; k++)
+        out[k] = comp == 1 ? (uint8_t)v[k] : luma(v[3 * k], v[3 * k + 1], v[3 * k + 2]);
+    *W = w; *H = h; *ch = comp;
+    return DEFF2D_OK;
+}
+
+// ---------------------------------------------------------------------------------- inflate (RFC 1950/1951)
+
+struct BitReader {
+    const uint8_t *d; size_t n, pos = 0; uint32_t buf = 0; int cnt = 0;
+    BitReader(const uint8_t *dd, size_t nn) : d(dd), n(nn) {}
+    inline int bits(int k)
+    {
+        while (cnt < k) { buf |= (uint32_t)(pos < n ? d[pos] : 0) << cnt; pos++; cnt += 8; }
+        const int v = (int)(buf & ((1u << k) - 1));
+        buf >>= k; cnt -= k;
+        return v;
+    }
+    inline void align() { buf = 0; cnt = 0; }
+};
+
+struct Huff {
+    uint16_t count[16]; uint16_t symbol[288];
+    bool build(const uint8_t *len, int n)
+    {
+        std::memset(count, 0, sizeof(count));
+        for (int i = 0; i < n; i++) count[len[i]]++;
+        count[0] = 0;
+        uint16_t offs[16]; offs[1] = 0;
+        for (int i = 1; i < 15; i++) offs[i + 1] = offs[i] + count[i];
+        for (int i = 0; i < n; i++) if (len[i]) symbol[offs[len[i]]++] = (uint16_t)i;
+        return true;
+    }
+    inline int decode(BitReader &br) const
+    {
+        int code = 0, first = 0, index = 0;
+        for (int l = 1; l <= 15; l++) {
+            code |= br.bits(1);
+            const int c = count[l];
+            if (code - c < first) return symbol[index + (code - first)];
+            index += c; first += c; first <<= 1; code <<= 1;
+        }
+        return -1;
+    }
+};
+
+static bool inflate_zlib(const uint8_t *d, size_t n, std::vector<uint8_t> &out)
+{
+    if (n < 2) return false;
+    BitReader br(d + 2, n - 2);
+    static const uint16_t lbase[] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+    static const uint16_t lext[] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+    static const uint16_t dbase[] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+    static const uint16_t dext[] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+    int last;
+    do {
+        last = br.bits(1);
+        const int type = br.bits(2);
+        if (type == 0) {
+            br.align();
+            if (br.pos + 4 > br.n) return false;
+            const unsigned len = br.d[br.pos] | (br.d[br.pos + 1] << 8);
+            br.pos += 4;
+            if (br.pos + len > br.n) return false;
+            out.insert(out.end(), br.d + br.pos, br.d + br.pos + len);
+            br.pos += len;
+        } else if (type == 1 || type == 2) {
+            Huff hl, hd;
+            uint8_t lens[320];
+            if (type == 1) {
+                int i = 0;
+                for (; i < 144; i++) lens[i] = 8;
+                for (; i < 256; i++) lens[i] = 9;
+                for (; i < 280; i++) lens[i] = 7;
+                for (; i < 288; i++) lens[i] = 8;
+                hl.build(lens, 288);
+                for (i = 0; i < 30; i++) lens[i] = 5;
+                hd.build(lens, 30);
+            } else {
+                const int nlen = br.bits(5) + 257, ndist = br.bits(5) + 1, ncode = br.bits(4) + 4;
+                static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+                uint8_t cl[19] = {0};
+                for (int i = 0; i < ncode; i++) cl[order[i]] = (uint8_t)br.bits(3);
+                Huff hc; hc.build(cl, 19);
+                int idx = 0;
+                while (idx < nlen + ndist) {
+                    int sym = hc.decode(br);
+                    if (sym < 0) return false;
+                    if (sym < 16) lens[idx++] = (uint8_t)sym;
+                    else {
+                        int rep, val = 0;
+                        if (sym == 16) { if (!idx) return false; val = lens[idx - 1]; rep = 3 + br.bits(2); }
+                        else if (sym == 17) rep = 3 + br.bits(3);
+                        else rep = 11 + br.bits(7);
+                        if (idx + rep > nlen + ndist) return false;
+                        while (rep--) lens[idx++] = (uint8_t)val;
+                    }
+                }
+                hl.build(lens, nlen);
+                hd.build(lens + nlen, ndist);
+            }
+            for (;;) {
+                int sym = hl.decode(br);
+                if (sym < 0) return false;
+                if (sym < 256) out.push_back((uint8_t)sym);
+                else if (sym == 256) break;
+                else {
+                    sym -= 257;
+                    if (sym >= 29) return false;
+                    const int len = lbase[sym] + br.bits(lext[sym]);
+                    const int ds = hd.decode(br);
+                    if (ds < 0 || ds >= 30) return false;
+                    const size_t dist = dbase[ds] + (size_t)br.bits(dext[ds]);
+                    if (dist > out.size()) return false;
+                    const size_t start = out.size() - dist;
+                    for (int k = 0; k < len; k++) out.push_back(out[start + k]);
+                }
+                if (br.pos > br.n + 8) return false;
+            }
+        } else return false;
+    } while (!last);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------- PNG
+
+static inline uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; }
+
+static inline int paeth(int a, int b, int c)
+{
+    const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+// un-filter one pass of w x h pixels starting at raw[pos]; returns gray-convertible samples
+static bool png_unfilter(const std::vector<uint8_t> &raw, size_t &pos, int w, int h, int bpp_bits,
+                         std::vector<uint8_t> &img /* h * stride */, size_t &stride)
+{
+    stride = ((size_t)w * bpp_bits + 7) / 8;
+    const int bpp = bpp_bits >= 8 ? bpp_bits / 8 : 1;
+    img.assign(stride * h, 0);
+    for (int y = 0; y < h; y++) {
+        if (pos + 1 + stride > raw.size()) return false;
+        const int ft = raw[pos++];
+        uint8_t *cur = img.data() + (size_t)y * stride;
+        const uint8_t *up = y ? cur - stride : nullptr;
+        for (size_t x = 0; x < stride; x++) {
+            const int a = x >= (size_t)bpp ? cur[x - bpp] : 0;
+            const int b = up ? up[x] : 0;
+            const int c = (up && x >= (size_t)bpp) ? up[x - bpp] : 0;
+            int v = raw[pos + x];
+            switch (ft) {
+                case 0: break;
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) >> 1; break;
+                case 4: v += paeth(a, b, c); break;
+                default: return false;
+            }
+            cur[x] = (uint8_t)v;
+        }
+        pos += stride;
+    }
+    return true;
+}
+
+static int png_decode(const uint8_t *d, size_t n, std::vector<uint8_t> &out, int *W, int *H, int *ch, std::string &err)
+{
+    size_t pos = 8;
+    int w = 0, h = 0, depth = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, plte;
+    bool has_trns = false;
+    while (pos + 12 <= n) {
+        const uint32_t len = be32(d + pos);
+        const uint8_t *t = d + pos + 4;
+        if (pos + 12 + len > n) { err = "truncated PNG"; return DEFF2D_ERR_IO; }
+        const uint8_t *body = d + pos + 8;
+        if (!std::memcmp(t, "IHDR", 4)) {
+            w = (int)be32(body); h = (int)be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12];
+        } else if (!std::memcmp(t, "PLTE", 4)) plte.assign(body, body + len);
+        else if (!std::memcmp(t, "tRNS", 4)) has_trns = true;
+        else if (!std::memcmp(t, "IDAT", 4)) idat.insert(idat.end(), body, body + len);
+        else if (!std::memcmp(t, "IEND", 4)) break;
+        pos += 12 + len;
+    }
+    if (w < 1 || h < 1 || idat.empty()) { err = "bad PNG"; return DEFF2D_ERR_IO; }
+    int comp;
+    switch (ctype) { case 0: comp = 1; break; case 2: comp = 3; break; case 3: comp = 1; break; case 4: comp = 2; break; case 6: comp = 4; break; default: err = "bad PNG colour type"; return DEFF2D_ERR_IO; }
+    std::vector<uint8_t> raw;
+    raw.reserve(((size_t)w * comp * depth / 8 + 2) * h);
+    if (!inflate_zlib(idat.data(), idat.size(), raw)) { err = "PNG inflate failed"; return DEFF2D_ERR_IO; }
+    out.assign((size_t)w * h, 0);
+    const int bpp_bits = comp * depth;
+    auto sample_to_gray = [&](const uint8_t *row, int x) -> uint8_t {
+        if (depth == 8) {
+            const uint8_t *p = row + (size_t)x * comp;
+            if (ctype == 3) { const size_t k = p[0]; return k * 3 + 2 < plte.size() ? luma(plte[3 * k], plte[3 * k + 1], plte[3 * k + 2]) : 0; }
+            return comp >= 3 ? luma(p[0], p[1], p[2]) : p[0];
+        }
+        if (depth == 16) {
+            const uint8_t *p = row + (size_t)x * comp * 2;
+            return comp >= 3 ? luma(p[0], p[2], p[4]) : p[0];
+        }
+        const int per = 8 / depth;
+        const int v = (row[x / per] >> (8 - depth * (x % per + 1))) & ((1 << depth) - 1);
+        if (ctype == 3) { const size_t k = (size_t)v; return k * 3 + 2 < plte.size() ? luma(plte[3 * k], plte[3 * k + 1], plte[3 * k + 2]) : 0; }
+        static const int scale[5] = {0, 255, 85, 0, 17};
+        return (uint8_t)(v * scale[depth]);
+    };
+    size_t rp = 0, stride;
+    std::vector<uint8_t> pass;
+    if (!interlace) {
+        if (!png_unfilter(raw, rp, w, h, bpp_bits, pass, stride)) { err = "bad PNG data"; return DEFF2D_ERR_IO; }
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) out[(size_t)y * w + x] = sample_to_gray(pass.data() + (size_t)y * stride, x);
+    } else {
+        static const int xo[7] = {0, 4, 0, 2, 0, 1, 0}, yo[7] = {0, 0, 4, 0, 2, 0, 1}, xs[7] = {8, 8, 4, 4, 2, 2, 1}, ys[7] = {8, 8, 8, 4, 4, 2, 2};
+        for (int p = 0; p < 7; p++) {
+            const int pw = (w - xo[p] + xs[p] - 1) / xs[p], ph = (h - yo[p] + ys[p] - 1) / ys[p];
+            if (pw <= 0 || ph <= 0) continue;
+            if (!png_unfilter(raw, rp, pw, ph, bpp_bits, pass, stride)) { err = "bad PNG data"; return DEFF2D_ERR_IO; }
+            for (int y = 0; y < ph; y++)
+                for (int x = 0; x < pw; x++)
+                    out[(size_t)(y * ys[p] + yo[p]) * w + (x * xs[p] + xo[p])] = sample_to_gray(pass.data() + (size_t)y * stride, x);
+        }
+    }
+    // channel count as the reference's decoder reports it: palette images count as RGB(A)
+    *ch = (ctype == 3) ? (has_trns ? 4 : 3) : (comp + ((has_trns && (ctype == 0 || ctype == 2)) ? 1 : 0));
+    *W = w; *H = h;
+    return DEFF2D_OK;
+}
+
+int decode_image_memory(const uint8_t *d, size_t n, std::vector<uint8_t> &out, int *W, int *H, int *ch, std::string &err)
+{
+    static const uint8_t pngsig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (n >= 8 && !std::memcmp(d, pngsig, 8)) return png_decode(d, n, out, W, H, ch, err);
+    if (n >= 3 && d[0] == 0xFF && d[1] == 0xD8) return jpeg_decode_gray(d, n, out, W, H, ch, err);
+    if (n >= 7 && d[0] == 'P' && (d[1] == '2' || d[1] == '3' || d[1] == '5' || d[1] == '6')) return pnm_decode(d, n, out, W, H, ch, err);
+    err = "unknown image format (supported: PNG, JPEG, PGM/PPM)";
+    return DEFF2D_ERR_IO;
+}
+
+}  // namespace deff2d
+
+DEFF2D_EXPORT int deff2d_load_image(const char *path, uint8_t **gray, int *W, int *H, int *channels)
+{
+    if (!path || !gray || !W || !H) return DEFF2D_ERR_ARG;
+    *gray = nullptr;
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return DEFF2D_ERR_IO;
+    std::vector<uint8_t> data;
+    uint8_t buf[1 << 16];
+    size_t got;
+    while ((got = std::fread(buf, 1, sizeof(buf), f)) > 0) data.insert(data.end(), buf, buf + got);
+    std::fclose(f);
+    std::vector<uint8_t> out;
+    std::string err;
+    int ch = 0;
+    const int rc = deff2d::decode_image_memory(data.data(), data.size(), out, W, H, &ch, err);
+    if (rc) return rc;
+    if (channels) *channels = ch;
+    *gray = (uint8_t *)std::malloc(out.size() ? out.size() : 1);
+    if (!*gray) return DEFF2D_ERR_ALLOC;
+    std::memcpy(*gray, out.data(), out.size());
+    return DEFF2D_OK;
+}

@@ -1,0 +1,81 @@
+// kernels.cuh -- device-side data model and kernel launchers of libdeff2d (sm_100a).
+//
+// HBM layout of one resident domain (see DESIGN.md "Data layout"):
+//   x[2]   FP64 ping-pong iterate, (Ny+2) rows x pitch doubles.  Interior cell (i,j) lives at
+//          [(i+1)*pitch + j + XOFF]; column XOFF-1 and XOFF+Nx are the Dirichlet ghost
+//          columns (value 1.0, their weight carries CL / CR), rows 0 and Ny+1 are the no-flux
+//          ghost rows (weight 0).  pitch is a multiple of 16 doubles (128 B rows, TMA needs 16 B).
+//   code   one byte per cell in the same padded geometry (pitch bytes per row):
+//          bits 0-1 phase (0 fluid, 1 solid, 2 gas, 3 ghost), bit 2 pinned (3-phase Grid in {1,2}).
+//   lut    2048 x 4 doubles: sweep weights for every (p, pW, pE, pS, pN, pinned), per stage.
+// The reference's A[n][5] + b[n] (48 B/cell, cuh:1396-1397) are never materialised.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "deff2d_internal.h"
+
+namespace deff2d {
+
+struct DomainView {
+    double *x_in;            // iterate read by the sweep
+    double *x_out;           // iterate written by the sweep
+    const uint8_t *code;
+    const double *lut;       // [2048][4]
+    const uint8_t *dead;     // [2048]
+    int64_t Nx, Ny;          // local interior size
+    int64_t pitch;           // elements per padded row (x and code)
+    double om;               // 1 - omega
+};
+
+// Device-resident convergence state of the reference loop (cuh:1167-1176, 1243-1276).
+struct SolveState {
+    double q[2];             // Q1, Q2 of the last flux evaluation (cuh:1252-1260)
+    double deff_old;         // deffOld, seeded with 5 (cuh:1172)
+    double deff_new;         // deffNew (cuh:1171)
+    double change;           // percentChange, seeded with 100 (cuh:1173)
+    double conv;             // myImg->conv (cuh:1275)
+    double resid;            // optional residual diagnostic (cuh:451-494)
+    long long stop_iter;     // iterCount at which the stop rule fired (-1: not yet)
+    int stop;                // 1: sweeps already enqueued behind the check become no-ops
+    int nchecks;
+    double trace[256];       // deffNew at every check (diagnostics / parity tests)
+};
+
+struct Counts {
+    unsigned long long phase[4];   // cells per phase on the amplified grid (own rows only)
+    unsigned long long below150;   // source pixels < 150 (calcPorosity, cuh:401)
+    unsigned long long pinned;
+};
+
+// ---- launchers (all asynchronous on `s`) -------------------------------------------------
+
+// threshold + mesh amplification + ghost ring + x0 (cuh:1773-1785, 1557-1578, 1730-1734)
+void launch_init_domain(cudaStream_t s, const uint8_t *img, int W, int Hsrc, int amp_x, int amp_y,
+                        int nphase, int64_t grow0 /* global amplified row of local interior row 0 */,
+                        int64_t img_row0 /* global source row of the first row held in img */,
+                        const uint8_t *grid /* Ny*Nx: 0/1/2 from FloodFill, or NULL */,
+                        double *x0, double *x1, uint8_t *code, int64_t Nx, int64_t Ny, int64_t pitch,
+                        int64_t NxG, double CL, double CR, int64_t own_first, int64_t own_rows,
+                        Counts *counts);
+void launch_count_below(cudaStream_t s, const uint8_t *img, int64_t n, int thr, Counts *counts);
+
+// K3: plain streaming sweep, one sweep per HBM pass (cuh:69-92 matrix-free)
+void launch_sweep_simple(cudaStream_t s, const DomainView &d, const int *stop);
+
+// K4: boundary-flux sums over local rows [row_first, row_first+nrows) (cuh:1252-1260)
+void launch_flux(cudaStream_t s, const DomainView &d, const double Dphase[3], double CL, double CR,
+                 int64_t NxG, int64_t row_first, int64_t nrows, SolveState *st);
+// stop rule of cuh:1263-1276 + cuh:1232 on the (all-reduced) Q1, Q2
+void launch_check(cudaStream_t s, SolveState *st, int64_t NyG, double CL, double CR, double tol,
+                  long long iter_index);
+void launch_reset_state(cudaStream_t s, SolveState *st);
+
+// concentration map as the reference downloads it (cuh:1300), NaN in dead cells (Q13)
+void launch_extract_field(cudaStream_t s, const DomainView &d, double *dense);
+void launch_inject_field(cudaStream_t s, const DomainView &d, const double *dense);
+void launch_extract_codes(cudaStream_t s, const DomainView &d, uint8_t *dense);
+// K7: mean |qW - qE + qN - qS| (cuh:451-494)
+void launch_residual(cudaStream_t s, const DomainView &d, const double Dphase[3], double CL, double CR,
+                     int64_t NxG, int64_t NyG, double *partial /* 1 double, zeroed */);
+
+}  // namespace deff2d

@@ -1,0 +1,216 @@
+/*
+ * deff2d.h -- C ABI of libdeff2d, the B200-native (sm_100a) effective-diffusivity solve.
+ *
+ * Drop-in boundary for the hot path of adama-wzr/EffectiveDiffusivityFVM
+ * (image -> phases -> FVM coefficients -> damped-Jacobi sweeps -> boundary-flux Deff).
+ * Plain pointers and sizes only; no torch / CUDA types appear in any signature.
+ * Citations: cuh = Deff2DGPU/Deff2D.cuh, cu = Deff2DGPU/Deff2D.cu of the reference.
+ *
+ * Every function returns 0 on success or a negative deff2d_status; the message of the
+ * last error is available from deff2d_last_error().  Nothing here calls getchar() or
+ * resets the device (reference quirk Q16, cuh:914, cuh:1015).  A context is not
+ * thread-safe: one caller thread per context.  Calls block until their results are on
+ * the host unless stated otherwise.  There is NO CPU fallback: without a CUDA device
+ * deff2d_create() fails with DEFF2D_ERR_CUDA.
+ */
+#ifndef DEFF2D_H
+#define DEFF2D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEFF2D_VERSION 100
+
+typedef enum {
+    DEFF2D_OK = 0,
+    DEFF2D_ERR_CUDA = -1,     /* CUDA runtime / driver error, or no device */
+    DEFF2D_ERR_ARG = -2,      /* invalid argument */
+    DEFF2D_ERR_ALLOC = -3,    /* host or device allocation failed */
+    DEFF2D_ERR_STATE = -4,    /* call sequence error (e.g. sweeps before a domain is loaded) */
+    DEFF2D_ERR_IO = -5,       /* file could not be read / written / decoded */
+    DEFF2D_ERR_NCCL = -6
+} deff2d_status;
+
+/* Which reference driver's logic to follow (cu:17-50). */
+typedef enum {
+    DEFF2D_MODE_2PH_SINGLE = 0,   /* SingleSim        cuh:1635-1841  DCF = 100^k continuation  */
+    DEFF2D_MODE_2PH_BATCH = 1,    /* BatchSim body    cuh:1867-2049  one solve at Df           */
+    DEFF2D_MODE_3PH = 2           /* SingleSim3Phase  cuh:1316-1633  == BatchSim3Phase body    */
+} deff2d_mode;
+
+/* Replaces the numeric part of `options` (cuh:18-37). */
+typedef struct {
+    double Ds, Df, Dg;        /* DCsolid, DCfluid, DCgas                  cuh:20-22 */
+    int amp_x, amp_y;         /* MeshIncreaseX / MeshIncreaseY            cuh:23-24 */
+    double CL, CR;            /* CLeft, CRight                            cuh:25-26 */
+    int64_t max_iter;         /* MAX_ITER                                 cuh:27    */
+    double tol;               /* ConvergeCriteria                         cuh:28    */
+    int mode;                 /* deff2d_mode                                        */
+    int check_every;          /* 0 -> 10000, the reference's hard-coded cadence  cuh:1174 */
+    double omega;             /* 0 -> 2/3, the reference's damping               cuh:72   */
+    int tblock;               /* sweeps fused per HBM pass; 0 -> library default         */
+    int verbose;              /* 1: print the reference's per-check / per-stage stdout lines */
+    int strict_reference;     /* 1 (default semantics): keep reference quirks Q8/Q11; 0 reserved */
+} deff2d_params;
+
+#define DEFF2D_MAX_STAGES 16
+
+/* Replaces `simulationInfo` (cuh:39-52) + what the drivers print/write per image. */
+typedef struct {
+    double porosity;          /* calcPorosity, 2-phase only               cuh:383-408 */
+    double SVF, LVF;          /* calcFracts3D, 3-phase only               cuh:411-448 */
+    double deff;              /* normalised: deff_raw / DCF               cuh:1802, 1601, 2017 */
+    double deff_raw;          /* myImg->deff as JacobiGPU leaves it       cuh:1309 */
+    double conv;              /* signed relative change at the last check cuh:1275 */
+    int pathflag;             /* FloodFill                                cuh:619-621 */
+    int nstages;              /* continuation stages executed (incl. the final one) */
+    int64_t iters[DEFF2D_MAX_STAGES];          /* value JacobiGPU returns, per stage */
+    double stage_deff_raw[DEFF2D_MAX_STAGES];
+    double stage_D[DEFF2D_MAX_STAGES];         /* DCF (2-phase) or DCG_Temp (3-phase) of the stage */
+    int64_t total_iters;
+    int64_t n_cells;          /* mesh.nElements                           cuh:1681 */
+    double solve_ms;          /* device time of the non-PreCond solve loops = CSV `Time`*1000  cuh:1311 */
+    double total_ms;          /* device time of everything the call launched */
+    double last_df;           /* DCF used by the last stage (CSV `df` column of batch mode, cuh:2034) */
+} deff2d_result;
+
+typedef struct deff2d_ctx deff2d_ctx;
+
+/* ---- library / context --------------------------------------------------------------- */
+
+int deff2d_version(void);
+
+/* Replaces initializeGPU / unInitializeGPU (cuh:904-1021): one persistent context per
+ * device owns streams, arenas and lookup tables; no per-image allocation or reset. */
+int deff2d_create(deff2d_ctx **out, int device);
+void deff2d_destroy(deff2d_ctx *ctx);
+const char *deff2d_last_error(const deff2d_ctx *ctx);   /* ctx may be NULL: last create error */
+
+void deff2d_default_params(deff2d_params *p);            /* shipped input.txt defaults */
+
+/* ---- the whole path, host buffers in, Deff out ------------------------------------- */
+
+/* One image through the reference driver logic selected by p->mode, covering threshold +
+ * mesh amplification (cuh:1773-1785, 1557-1578), FloodFill (cuh:557-713), assembly
+ * (cuh:715-902, matrix-free here), the continuation stages (cuh:1759-1817, 1492-1597),
+ * the damped-Jacobi loop with the reference stop rule (cuh:1163-1314) and Deff
+ * (cuh:1252-1264).  gray: H*W row-major 8-bit pixels as stbi_load(...,1) returns them
+ * (cuh:342).  field: NULL or (H*amp_y)*(W*amp_x) doubles receiving the concentration
+ * map the reference would write to its CMAP file (cuh:497-524). */
+int deff2d_solve_image(deff2d_ctx *ctx, const uint8_t *gray, int W, int H,
+                       const deff2d_params *p, deff2d_result *res, double *field);
+
+/* `count` images of identical size packed back to back (count*H*W bytes): the body of
+ * BatchSim / BatchSim3Phase (cuh:1867-2049, 2056-2419) for every image.  results: count
+ * entries.  fields: NULL or count*(H*amp_y)*(W*amp_x) doubles. */
+int deff2d_solve_batch(deff2d_ctx *ctx, const uint8_t *gray, int count, int W, int H,
+                       const deff2d_params *p, deff2d_result *results, double *fields);
+
+/* ---- device-resident stepping (tests, benchmarks, multi-GPU slabs) ------------------- */
+
+/* Upload an image, threshold/amplify it into the per-cell phase codes, run FloodFill
+ * (3-phase: pinned mask; always: PathFlag), set x0 = j/Nx*(CR-CL)+CL (cuh:1730-1734) and
+ * build the coefficient tables for (Ds, Df, Dg).  nphase = 2 or 3. */
+int deff2d_domain_load(deff2d_ctx *ctx, const uint8_t *gray, int W, int H, int nphase,
+                       const deff2d_params *p);
+/* Same for a horizontal slab [row0, row0+rows) of a taller global domain of NyGlobal cell
+ * rows (multi-GPU row decomposition).  gray holds the slab's own source rows plus
+ * `halo_src` source rows above and below where they exist; pinned: NULL or the slab's
+ * pinned mask incl. halo rows. */
+int deff2d_domain_load_slab(deff2d_ctx *ctx, const uint8_t *gray, int W, int Hslab, int nphase,
+                            const deff2d_params *p, int64_t row0, int64_t NyGlobal, int halo_rows,
+                            const uint8_t *pinned);
+/* New continuation stage: only the 3 diffusivities change (cuh:1762, 1524); the phase
+ * codes and the iterate stay resident (warm start, cuh:1793). */
+int deff2d_domain_set_D(deff2d_ctx *ctx, double Ds, double Df, double Dg);
+/* Enqueue `n` damped-Jacobi sweeps (cuh:69-92 + the D2D copy of cuh:1281 as a pointer
+ * swap) on the context's stream; returns without synchronising. */
+int deff2d_domain_sweeps(deff2d_ctx *ctx, int64_t n);
+/* Same, bracketed by CUDA events on the launching stream; blocks; *ms = device time. */
+int deff2d_domain_sweeps_timed(deff2d_ctx *ctx, int64_t n, float *ms);
+/* Boundary-flux Deff of the current iterate (cuh:1252-1264), un-normalised; blocks.
+ * q (optional): {Q1, Q2} partial sums of this domain/slab. */
+int deff2d_domain_flux(deff2d_ctx *ctx, double *deff_raw, double *q);
+/* Mean |flux imbalance| per cell, the reference's (dead) Residual (cuh:451-494); blocks. */
+int deff2d_domain_residual(deff2d_ctx *ctx, double *res);
+/* The reference solve loop on the resident domain: sweeps + checks every `check_every`
+ * + stop rule (cuh:1232-1290).  Returns the reference's iterCount in *iters. */
+int deff2d_domain_solve(deff2d_ctx *ctx, double tol, int64_t max_iter, int64_t *iters,
+                        double *deff_raw, double *conv, double *trace, int trace_cap, int *ntrace);
+int deff2d_domain_get_field(deff2d_ctx *ctx, double *field);        /* Ny*Nx doubles out */
+int deff2d_domain_set_field(deff2d_ctx *ctx, const double *field);  /* Ny*Nx doubles in  */
+int deff2d_domain_get_codes(deff2d_ctx *ctx, uint8_t *codes);       /* Ny*Nx bytes out: bits 0-1 phase, bit 2 pinned */
+int deff2d_domain_info(deff2d_ctx *ctx, int64_t *Nx, int64_t *Ny, int *pathflag, double *porosity,
+                       double *SVF, double *LVF);
+int deff2d_sync(deff2d_ctx *ctx);
+
+/* Select the sweep kernel: 0 = library default, 1 = plain streaming kernel (one sweep per
+ * HBM pass), 2 = TMA-staged tiled kernel with `tblock` sweeps per pass. */
+int deff2d_set_kernel(deff2d_ctx *ctx, int kernel, int tblock);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t deff2d_kernel_launches(const deff2d_ctx *ctx);
+/* The CUDA stream (cudaStream_t as an opaque pointer) all work of the context is enqueued on. */
+void *deff2d_stream(deff2d_ctx *ctx);
+/* Device pointers of the resident iterate buffers and row pitch in doubles (for peer /
+ * NCCL halo exchange by the host layer); rows include one ghost row above and below. */
+int deff2d_domain_buffers(deff2d_ctx *ctx, void **x_cur, void **x_next, int64_t *pitch, int64_t *rows);
+
+/* ---- multi-GPU row-slab decomposition over NCCL --------------------------------------- */
+
+/* size of the opaque NCCL unique id the ranks must share */
+#define DEFF2D_NCCL_ID_BYTES 128
+int deff2d_nccl_unique_id(uint8_t id[DEFF2D_NCCL_ID_BYTES]);       /* call on rank 0, broadcast by the host layer */
+int deff2d_nccl_init(deff2d_ctx *ctx, const uint8_t id[DEFF2D_NCCL_ID_BYTES], int rank, int nranks);
+/* Sweeps on a slab with halo exchange every `tblock` sweeps (ncclSend/ncclRecv of the
+ * boundary rows to the two neighbours) -- enqueue only. */
+int deff2d_slab_sweeps(deff2d_ctx *ctx, int64_t n);
+/* Global Deff: local {Q1,Q2} -> ncclAllReduce(sum) -> same value on every rank; blocks. */
+int deff2d_slab_flux(deff2d_ctx *ctx, double *deff_raw);
+
+/* ---- host-side pieces of the path (no GPU needed; CPU-testable) ---------------------- */
+
+/* Coefficient tables for one stage, exactly as the library uploads them: lut is
+ * 2048*4 doubles -- for the 11-bit index  p | pW<<2 | pE<<4 | pS<<6 | pN<<8 | pinned<<10
+ * the four sweep weights (w/A0)*c_f in order W,E,S,N following cuh:815-902 and cuh:89;
+ * dead is 2048 bytes (1 where A0 == 0, reference quirk Q13).  Phases: 0 fluid, 1 solid,
+ * 2 gas, 3 ghost (Dirichlet face for W/E, no-flux wall for S/N). */
+int deff2d_build_tables(double Ds, double Df, double Dg, int64_t Nx, int64_t Ny, double CL, double CR,
+                        double omega, double *lut, uint8_t *dead);
+/* FloodFill (cuh:557-713) on a solid mask (1 = solid), incl. the y-periodic wrap and the
+ * right-column seeding quirk (cuh:601).  grid: Ny*Nx bytes in/out (unreached non-solid
+ * cells become 2).  Returns PathFlag (0/1) or a negative status. */
+int deff2d_floodfill(uint8_t *grid, int64_t Nx, int64_t Ny);
+
+/* input.txt parser with the reference's quirks (cuh:234-324): case-sensitive "Key: value"
+ * lines, numerics parsed as double then cast, unknown keys ignored. */
+typedef struct {
+    deff2d_params p;
+    int nphase;               /* Phases:    cuh:309-310 */
+    int batch;                /* RunBatch:  cuh:305-306 */
+    int num_images;           /* NumImages: cuh:307-308 */
+    int print_cmap;           /* printCMap: cuh:289-290 */
+    char input_name[1000];    /* InputName: cuh:275-277 */
+    char output_name[1000];   /* OutputName:cuh:285-287 */
+    char cmap_name[1000];     /* CMapName:  cuh:292-294 */
+} deff2d_input;
+int deff2d_read_input_file(const char *path, deff2d_input *in);
+/* CSV / CMAP writers with the reference's exact formats (cuh:177-232, 497-554). */
+int deff2d_write_csv_single(const deff2d_input *in, const deff2d_result *r);
+int deff2d_write_csv_batch(const deff2d_input *in, const deff2d_result *r, int count);
+int deff2d_write_cmap(const char *path, const double *field, int64_t Nx, int64_t Ny);
+/* The reference program: read ./input.txt-style file, run the selected driver (cu:17-50),
+ * write the same files.  Images are decoded by the library's own readers (PGM/PNG content
+ * under any file name; baseline JPEG). */
+int deff2d_run_input_file(deff2d_ctx *ctx, const char *path);
+/* Decode an image file to 8-bit gray.  *gray is malloc'd (free with deff2d_free). */
+int deff2d_load_image(const char *path, uint8_t **gray, int *W, int *H, int *channels);
+void deff2d_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEFF2D_H */

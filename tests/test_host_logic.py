@@ -1,0 +1,196 @@
+"""CPU tests of the host-side half of libdeff2d (no GPU compute): the coefficient LUT against
+the oracle's materialised A/b, FloodFill and input parsing against the reference goldens, the
+CSV/CMAP writers' formats, the image readers, and the C-ABI symbol table."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import _emulate as EM
+import _oracle as O
+import effectivediffusivityfvm_b200 as E
+from effectivediffusivityfvm_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "deff2d.h")).read()
+    declared = set(re.findall(r"\b(deff2d_[A-Za-z0-9_]+)\s*\(", hdr))
+    L = _lib.lib()
+    assert declared == set(L._declared), declared ^ set(L._declared)
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH]).decode()
+    exported = set(re.findall(r" T (deff2d_[A-Za-z0-9_]+)", out))
+    assert declared <= exported, declared - exported
+    assert L.deff2d_version() == 100
+
+
+def test_no_device_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(E.Deff2DError):
+        E.Deff2D(0)
+
+
+@pytest.mark.parametrize("nphase,Ds,Dg", [(2, 1e-3, 0.0), (2, 0.0, 0.0), (3, 0.0, 50.0), (3, 0.01, 1237500.0)])
+@pytest.mark.parametrize("shape,CL,CR", [((12, 20), 0.0, 1.0), ((9, 17), 0.25, 1.5), ((1, 7), 0.0, 1.0), ((6, 2), 0.0, 1.0)])
+def test_lut_matches_reference_matrix(nphase, Ds, Dg, shape, CL, CR):
+    """Every weight the kernels will use equals (w/A0) * coefficient of the reference's A, b."""
+    rng = np.random.default_rng(hash((nphase, shape)) % 2**32)
+    Ny, Nx = shape
+    if Ny == 1 or Nx == 1:
+        pytest.skip("the reference reads out of bounds on 1-wide domains")
+    img = np.choose(rng.integers(0, 3, size=shape), [0, 150, 255]).astype(np.uint8)
+    omega = 2.0 / 3.0
+    grid = None
+    if nphase == 3:
+        grid, _ = O.floodfill((img > 200).astype(np.uint32))
+    D = O.fill_D(img, 1, 1, nphase, Ds, 1.0, Dg)
+    A, b = O.discretize(D, CL, CR, grid)
+    A = A.reshape(Ny, Nx, 5)
+    b = b.reshape(Ny, Nx)
+    lut, dead = E.build_tables(Ds, 1.0, Dg, Nx, Ny, CL, CR, omega)
+    codes = EM.phase_codes(img, nphase, grid=grid)
+    idx = EM.lut_index(EM.pad_codes(codes), Nx, Ny)
+    w = lut[idx]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dinv = omega / A[..., 0]
+        exp = np.stack([dinv * -A[..., 1], dinv * -A[..., 2], dinv * -A[..., 3], dinv * -A[..., 4]], axis=-1)
+        exp[:, 0, 0] = dinv[:, 0] * b[:, 0]          # Dirichlet faces ride on the ghost value 1.0
+        exp[:, -1, 1] = dinv[:, -1] * b[:, -1]
+    isdead = A[..., 0] == 0
+    assert np.array_equal(dead[idx].astype(bool), isdead)
+    exp[isdead] = 0.0
+    pinned = (codes & 4) != 0
+    assert np.all(w[pinned] == 0)
+    exp[pinned] = 0.0                                  # identity row: x' = (1-w) x
+    exp = exp + 0.0                                    # -0.0 -> +0.0
+    assert np.array_equal(w + 0.0, exp)
+
+
+@pytest.mark.parametrize("nphase,Ds,Dg", [(2, 1e-3, 0.0), (3, 0.0, 50.0)])
+def test_matrix_free_sweeps_match_oracle(nphase, Ds, Dg):
+    """The LUT formulation run in numpy tracks the oracle's A/b sweeps to rounding."""
+    rng = np.random.default_rng(5)
+    Ny, Nx = 23, 37
+    img = np.choose(rng.integers(0, 3, size=(Ny, Nx)), [0, 150, 255]).astype(np.uint8)
+    grid = O.floodfill((img > 200).astype(np.uint32))[0] if nphase == 3 else None
+    D = O.fill_D(img, 1, 1, nphase, Ds, 1.0, Dg)
+    A, b = O.discretize(D, 0.0, 1.0, grid)
+    x0 = O.init_x(Nx, Ny, 0.0, 1.0)
+    ref = O.sweeps(A, b, x0, 200)
+    lut, dead = E.build_tables(Ds, 1.0, Dg, Nx, Ny, 0.0, 1.0, 2.0 / 3.0)
+    pc = EM.pad_codes(EM.phase_codes(img, nphase, grid=grid))
+    got = EM.sweep(EM.pad_field(x0), pc, lut, Nx, Ny, nsweeps=200)[1:Ny + 1, EM.XOFF:EM.XOFF + Nx]
+    assert np.max(np.abs(got - ref)) < 1e-13
+
+
+@pytest.mark.parametrize("k", range(6))
+@pytest.mark.parametrize("nphase", [2, 3])
+def test_floodfill_matches_reference(golden_prims, k, nphase):
+    img = golden_prims["img%d" % k]
+    thr = 150 if nphase == 2 else 200
+    g, pf = E.floodfill((img > thr).astype(np.uint8))
+    assert np.array_equal(g, golden_prims["flood%d_p%d" % (k, nphase)])
+    assert pf == int(golden_prims["pathflag%d_p%d" % (k, nphase)])
+
+
+def test_floodfill_large_random_vs_oracle():
+    rng = np.random.default_rng(11)
+    for p in (0.35, 0.45, 0.6):
+        m = (rng.random((150, 190)) < p).astype(np.uint8)
+        g, pf = E.floodfill(m)
+        go, pfo = O.floodfill(m.astype(np.uint32))
+        assert np.array_equal(g, go.astype(np.uint8)) and pf == pfo
+
+
+def test_read_input_file_shipped_defaults(tmp_path):
+    txt = ("Input File:\nPhases: 3\nDs: 0\nDf: 1\nDg: 1237500\nMeshAmpX: 1\nMeshAmpY: 1\nInputName: 00042.jpg\n"
+           "CR: 1\nCL: 0\nOutputName: singleTest.csv\nprintCMap: 1\nCMapName: CMAP_00042.csv\nConvergence: 1e-5\n"
+           "MaxIter: 5e5\nVerbose: 1\nRunBatch: 0\nNumImages: 500")      # Deff2DGPU/input.txt verbatim
+    f = tmp_path / "input.txt"
+    f.write_text(txt)
+    inp = E.read_input_file(f)
+    assert (inp.nphase, inp.batch, inp.num_images, inp.print_cmap) == (3, 0, 500, 1)
+    assert (inp.p.Ds, inp.p.Df, inp.p.Dg) == (0.0, 1.0, 1237500.0)
+    assert inp.p.max_iter == 500000 and inp.p.tol == 1e-5 and inp.p.verbose == 1       # "5e5" via double (cuh:299-300)
+    assert inp.input_name == b"00042.jpg" and inp.output_name == b"singleTest.csv" and inp.cmap_name == b"CMAP_00042.csv"
+    assert inp.p.mode == E.MODE_3PH
+    # case-sensitive keys, unknown keys ignored (cuh:258-312)
+    f.write_text("phases: 2\nPhases: 2\nSolver: fancy\nRunBatch: 1\nDf: 7\n")
+    inp = E.read_input_file(f)
+    assert inp.nphase == 2 and inp.p.mode == E.MODE_2PH_BATCH and inp.p.Df == 7.0
+    with pytest.raises(E.Deff2DError):
+        E.read_input_file(tmp_path / "missing.txt")
+
+
+def test_csv_and_cmap_writers_match_reference_format(tmp_path, golden_drivers):
+    L = _lib.lib()
+    g = golden_drivers["bundled00000_3ph_single"]
+    ref_row = g["csv"].strip().splitlines()
+    inp = _lib.Input()
+    inp.p = E.default_params()
+    inp.nphase = 3
+    inp.input_name = b"00000.jpg"
+    out = tmp_path / "o.csv"
+    inp.output_name = str(out).encode()
+    r = _lib.Result()
+    r.SVF, r.LVF, r.pathflag, r.deff, r.n_cells, r.conv = 0.653931, 0.0, 1, 224673.610442892, 16384, 1.368e-08
+    r.solve_ms = float(ref_row[1].split(",")[5]) * 1000
+    assert L.deff2d_write_csv_single(C.byref(inp), C.byref(r)) == 0
+    assert L.deff2d_write_csv_single(C.byref(inp), C.byref(r)) == 0        # "a+": header repeats (Q18)
+    lines = out.read_text().splitlines()
+    assert lines[0] == ref_row[0] and lines[2] == ref_row[0]
+    assert lines[1].split(",")[:5] == ref_row[1].split(",")[:5]
+    assert lines[1].split(",")[6:] == ref_row[1].split(",")[6:]
+    # 2-phase batch rows
+    g2 = golden_drivers["bundled00000_2ph_batch"]["csv"].strip().splitlines()
+    inp.nphase = 2
+    inp.p.Ds, inp.p.Df = 1e-4, 1.0
+    out2 = tmp_path / "b.csv"
+    inp.output_name = str(out2).encode()
+    rs = (_lib.Result * 1)()
+    rs[0].porosity, rs[0].pathflag, rs[0].deff, rs[0].n_cells, rs[0].conv, rs[0].last_df = \
+        0.3460693359375, 1, 0.18169102773720014, 16384, 6.546346763587775e-06, 1.0
+    rs[0].solve_ms = float(g2[1].split(",")[4]) * 1000
+    assert L.deff2d_write_csv_batch(C.byref(inp), rs, 1) == 0
+    lines = out2.read_text().splitlines()
+    assert lines[0] == g2[0]
+    assert lines[1].split(",")[:4] == g2[1].split(",")[:4] and lines[1].split(",")[5:] == g2[1].split(",")[5:]
+    # CMAP
+    gc = golden_drivers["kat_parallel_3ph_single"]
+    field = np.linspace(0, 1, 12).reshape(3, 4)
+    cm = tmp_path / "c.csv"
+    assert L.deff2d_write_cmap(str(cm).encode(), field.ctypes.data_as(_lib.c_double_p), 4, 3) == 0
+    lines = cm.read_text().splitlines()
+    assert lines[0] == gc["cmap_head"][0] == "X,Y,C"
+    assert lines[1] == "0,0,0.000e+00" and lines[2].startswith("1,0,") and lines[5].startswith("0,1,")   # x inner, y outer
+    assert len(lines) == 13
+    assert re.fullmatch(r"\d+,\d+,-?\d\.\d{3}e[+-]\d\d", gc["cmap_head"][1])
+
+
+def test_image_readers(tmp_path, golden_images):
+    img = golden_images["00000"]
+    p = tmp_path / "a.jpg"           # content sniffing: PGM bytes under a .jpg name
+    with open(p, "wb") as f:
+        f.write(b"P5\n# comment\n%d %d\n255\n" % (img.shape[1], img.shape[0]) + img.tobytes())
+    got, ch = E.load_image(p)
+    assert ch == 1 and np.array_equal(got, img)
+    import cv2
+    for params in ([], [cv2.IMWRITE_PNG_COMPRESSION, 9]):
+        q = tmp_path / "b.png"
+        cv2.imwrite(str(q), img, params)
+        got, ch = E.load_image(q)
+        assert ch == 1 and np.array_equal(got, img)
+    rgb = np.stack([img, img // 2, 255 - img], axis=-1)
+    cv2.imwrite(str(tmp_path / "c.png"), rgb[..., ::-1])
+    got, ch = E.load_image(tmp_path / "c.png")
+    assert ch == 3
+    exp = ((rgb[..., 0].astype(int) * 77 + rgb[..., 1].astype(int) * 150 + rgb[..., 2].astype(int) * 29) >> 8).astype(np.uint8)
+    assert np.array_equal(got, exp)
+    with pytest.raises(E.Deff2DError):
+        E.load_image(tmp_path / "nope.png")
