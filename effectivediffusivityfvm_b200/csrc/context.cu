@@ -647,7 +647,9 @@ DEFF2D_EXPORT int deff2d_sync(deff2d_ctx *c)
 
 DEFF2D_EXPORT int deff2d_set_kernel(deff2d_ctx *c, int kernel, int tblock)
 {
-    if (!c || kernel < 0 || kernel > 2 || tblock < 0 || tblock > 16) return DEFF2D_ERR_ARG;
+    if (!c || kernel < 0 || kernel > 3 || tblock < 0 || tblock > 16) return DEFF2D_ERR_ARG;
+    c->tile_family = (kernel == 3) ? 1 : 0;     // 3: alternative tile geometry of the TMA kernel (tuning)
+    if (kernel == 3) kernel = 2;
     c->kernel = kernel;
     c->tblock = tblock > 0 ? tblock : 1;
     return DEFF2D_OK;

@@ -49,6 +49,7 @@ struct deff2d_ctx {
     // kernel selection
     int kernel = 0;                  // 0 default, 1 simple, 2 TMA tiled
     int tblock = 1;
+    int tile_family = 0;             // sweep_tma.cu tile geometry (tuning)
     int64_t launches = 0;
 
     // TMA tiled sweep state (sweep_tma.cu)

@@ -1,16 +1,473 @@
-// sweep_tma.cu -- K2: TMA-staged, temporally blocked damped-Jacobi sweep (placeholder until
-// the tiled kernel lands; the streaming kernel K3 is used meanwhile).
+// sweep_tma.cu -- K2: TMA-staged, temporally blocked damped-Jacobi sweep (sm_100a).
+//
+// Replaces T launches of the reference's updateX_SOR (Deff2D.cuh:69-92) plus its per-sweep
+// device-to-device copy (cuh:1281) by ONE pass over HBM:
+//
+//   * persistent CTAs walk a static list of (TW x TH) tiles; every tile, halo included, is
+//     brought into shared memory by two bulk tensor copies (FP64 iterate + u8 phase codes,
+//     cp.async.bulk.tensor.2d, mbarrier complete_tx), double buffered so the next tile's
+//     copy overlaps the current tile's sweeps; out-of-range boxes are zero filled by TMA;
+//   * each thread owns a PX x PY patch of cells for the whole tile visit: the patch values
+//     and its 4 x PX x PY sweep weights (looked up once per tile from the per-stage LUT with
+//     the 11-bit phase-neighbourhood index) live in registers;
+//   * T sweeps run on chip; per sweep a thread publishes only its patch boundary to a planar
+//     exchange buffer (column-phase planes -> conflict-free LDS/STS) and reads its 2(PX+PY)
+//     halo values back; one __syncthreads per sweep;
+//   * after T sweeps the (TW-2T) x (TH-2T) interior is written back with one bulk tensor
+//     store through a tensor map that covers only the interior of the domain (so ghost
+//     columns/rows are never overwritten and edge tiles are clipped by the hardware).
+//
+// Overlapped tiling is algebraically identical to T plain sweeps: a cell at distance >= T
+// from the tile edge only ever sees values that are exact at each intermediate level.
+// Ghost columns (Dirichlet value 1.0) keep their value because their weights are zero and
+// their (1-omega) factor is replaced by 1 (per thread column, no per-cell branch).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
 #include "context.h"
 
 namespace deff2d {
 
-int launch_sweep_tma(deff2d_ctx *c, int64_t n, int64_t *done)
+// ------------------------------------------------------------------------------------------ PTX helpers
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-    (void)c; (void)n;
-    *done = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, int c0, int c1, const void *src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+
+struct TmaMaps {
+    CUtensorMap x_load[2];     // padded iterate buffers, box TW x TH
+    CUtensorMap x_store[2];    // interior of the iterate buffers, box OW x OH
+    CUtensorMap code;          // padded codes, box TW x TH (u8)
+};
+
+template <int T_, int PX_, int PY_, int NWX_, int NWY_>
+struct Cfg {
+    static constexpr int T = T_, PX = PX_, PY = PY_, NWX = NWX_, NWY = NWY_;
+    static constexpr int TW = 32 * PX * NWX, TH = PY * NWY;
+    static constexpr int NT = 32 * NWX * NWY;
+    // TMA needs the innermost box coordinate 16-byte aligned (measured on B200: an odd FP64
+    // column or a u8 column that is not a multiple of 16 raises "illegal instruction").  The x
+    // halo is therefore rounded up to an even number of columns, and the code box is 16 bytes
+    // wider than the tile and starts at the previous multiple of 16.
+    static constexpr int TE = (T + 1) & ~1;
+    static constexpr int OW = TW - 2 * TE, OH = TH - 2 * T;
+    static constexpr int CELLS = TW * TH;
+    static constexpr int CW = TW + 16;                           // code box width
+    static constexpr int PLANE_W = TW / PX;                      // columns per phase plane
+    // shared memory map (bytes)
+    static constexpr size_t IN_BYTES = (size_t)CELLS * 8;
+    static constexpr size_t CODE_BYTES = ((size_t)CW * TH + 127) / 128 * 128;
+    static constexpr size_t OFF_IN = 0;                           // IN[2]
+    static constexpr size_t OFF_P = OFF_IN + 2 * IN_BYTES;        // P[2] planar exchange
+    static constexpr size_t OFF_OUT = OFF_P + 2 * IN_BYTES;       // OUT: dense OW x OH box for the bulk store
+    static constexpr size_t OUT_BYTES = ((size_t)OW * OH * 8 + 127) / 128 * 128;
+    static constexpr size_t OFF_CODE = OFF_OUT + OUT_BYTES;       // CODE[2]
+    static constexpr size_t OFF_BAR = OFF_CODE + 2 * CODE_BYTES;  // 2 mbarriers
+    static constexpr size_t SMEM = OFF_BAR + 64 + 128;            // + alignment slack
+    static_assert(OW > 0 && OH > 0, "tile too small for this temporal depth");
+    static_assert(TW <= 256 && TH <= 256, "TMA box dimension limit");
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, 1)
+k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, double om,
+            int Nx, int tiles_x, int ntiles, const int *__restrict__ stop)
+{
+    constexpr int T = C::T, TE = C::TE, PX = C::PX, PY = C::PY, TW = C::TW, TH = C::TH, OW = C::OW, OH = C::OH;
+    constexpr int PW = C::PLANE_W, CW = C::CW;
+    if (stop && *stop) return;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+    double *IN[2] = {reinterpret_cast<double *>(smem + C::OFF_IN), reinterpret_cast<double *>(smem + C::OFF_IN + C::IN_BYTES)};
+    double *P[2] = {reinterpret_cast<double *>(smem + C::OFF_P), reinterpret_cast<double *>(smem + C::OFF_P + C::IN_BYTES)};
+    double *OUT = reinterpret_cast<double *>(smem + C::OFF_OUT);
+    uint8_t *CODE[2] = {smem + C::OFF_CODE, smem + C::OFF_CODE + C::CODE_BYTES};
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wx = warp % C::NWX, wy = warp / C::NWX;
+    const int g = wx * 32 + lane;            // column group of this thread (plane column index)
+    const int c0 = g * PX;                   // first tile column of the patch
+    const int r0 = wy * PY;                  // first tile row of the patch
+
+    const CUtensorMap *map_in = &maps.x_load[src];
+    const CUtensorMap *map_out = &maps.x_store[src ^ 1];
+    constexpr uint32_t TX_BYTES = (uint32_t)(C::IN_BYTES + (size_t)CW * TH);
+
+    auto tile_origin = [&](int t, int &ox, int &oy) {
+        const int ty = t / tiles_x, tx = t - ty * tiles_x;
+        ox = tx * OW; oy = ty * OH;          // interior-coordinate origin of the OUTPUT box
+    };
+    auto issue_load = [&](int t, int b) {
+        int ox, oy;
+        tile_origin(t, ox, oy);
+        mbar_expect_tx(&bar[b], TX_BYTES);
+        // padded coordinates of the input box: interior (ox-TE, oy-T) -> (+XOFF, +1); even
+        const int xs = ox - TE + DEFF2D_XOFF;
+        tma_load_2d(IN[b], map_in, xs, oy - T + 1, &bar[b]);
+        tma_load_2d(CODE[b], &maps.code, xs & ~15, oy - T + 1, &bar[b]);
+    };
+
+    if (tid == 0) {
+        prefetch_tmap(map_in); prefetch_tmap(map_out); prefetch_tmap(&maps.code);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    int tile = blockIdx.x;
+    if (tid == 0) {
+        if (tile < ntiles) issue_load(tile, 0);
+        if (tile + (int)gridDim.x < ntiles) issue_load(tile + gridDim.x, 1);
+    }
+
+    // clamped neighbour positions (tile-edge patches produce halo garbage that is never stored)
+    const int gW = (g > 0) ? g - 1 : g;                       // plane PX-1, column gW
+    const int gE = (g < PW - 1) ? g + 1 : g;                  // plane 0,    column gE
+    const int rN = (r0 > 0) ? r0 - 1 : r0;
+    const int rS = (r0 + PY < TH) ? r0 + PY : r0 + PY - 1;
+
+    int k = 0;
+    for (; tile < ntiles; tile += gridDim.x, k++) {
+        const int b = k & 1;
+        mbar_wait(&bar[b], (uint32_t)((k >> 1) & 1));
+
+        // ---- patch values and weights into registers --------------------------------------
+        double x[PY][PX];
+        double w[PY][PX][4];
+        double omc[PX];
+        {
+            int ox, oy;
+            tile_origin(tile, ox, oy);
+            const double *in = IN[b];
+            const uint8_t *cd = CODE[b] + ((ox - TE + DEFF2D_XOFF) & 15);
+#pragma unroll
+            for (int py = 0; py < PY; py++) {
+                if constexpr (PX % 2 == 0) {       // 16-byte loads: conflict-free for PX == 2
+#pragma unroll
+                    for (int px = 0; px < PX; px += 2) {
+                        const double2 v = *reinterpret_cast<const double2 *>(in + (r0 + py) * TW + c0 + px);
+                        x[py][px] = v.x; x[py][px + 1] = v.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int px = 0; px < PX; px++) x[py][px] = in[(r0 + py) * TW + c0 + px];
+                }
+            }
+            // phase codes of the (PY+2) x (PX+2) neighbourhood, clamped at the tile edge
+            unsigned cc[PY + 2][PX + 2];
+#pragma unroll
+            for (int py = 0; py < PY + 2; py++) {
+                int r = r0 + py - 1;
+                r = r < 0 ? 0 : (r > TH - 1 ? TH - 1 : r);
+#pragma unroll
+                for (int px = 0; px < PX + 2; px++) {
+                    int c = c0 + px - 1;
+                    c = c < 0 ? 0 : (c > TW - 1 ? TW - 1 : c);
+                    cc[py][px] = cd[r * CW + c];
+                }
+            }
+            {
+                // a Dirichlet ghost column (global column -1 or Nx) keeps its value: its weights
+                // are 0 (LUT, p == 3) and its (1-omega) factor is 1
+#pragma unroll
+                for (int px = 0; px < PX; px++) {
+                    const int jg = ox - TE + c0 + px;
+                    omc[px] = (jg == -1 || jg == Nx) ? 1.0 : om;
+                }
+            }
+#pragma unroll
+            for (int py = 0; py < PY; py++)
+#pragma unroll
+                for (int px = 0; px < PX; px++) {
+                    const unsigned c = cc[py + 1][px + 1];
+                    const unsigned idx = (c & 3u) | ((cc[py + 1][px] & 3u) << 2) | ((cc[py + 1][px + 2] & 3u) << 4) |
+                                         ((cc[py + 2][px + 1] & 3u) << 6) | ((cc[py][px + 1] & 3u) << 8) | ((c & 4u) << 8);
+                    const double2 *lp = reinterpret_cast<const double2 *>(lut + (size_t)idx * 4);
+                    const double2 a = __ldg(lp), bb = __ldg(lp + 1);
+                    w[py][px][0] = a.x; w[py][px][1] = a.y; w[py][px][2] = bb.x; w[py][px][3] = bb.y;
+                }
+        }
+
+        // ---- publish the patch boundary of level 0 ----------------------------------------
+        auto publish = [&](double *pb) {
+#pragma unroll
+            for (int py = 0; py < PY; py++)
+#pragma unroll
+                for (int px = 0; px < PX; px++) {
+                    const bool edge = (px == 0) || (px == PX - 1) || (py == 0) || (py == PY - 1);
+                    if (edge) pb[(px * TH + r0 + py) * PW + g] = x[py][px];
+                }
+        };
+        publish(P[0]);
+        // the OUT box of the previous tile must have been read by its bulk store before this
+        // tile's last sweep overwrites it (the wait is ordered before the writes by S1)
+        if (tid == 0) tma_wait_read0();
+        __syncthreads();                       // S1: IN[b], CODE[b] fully consumed; P[0] visible
+
+        // prefetch the tile after next into the buffer just consumed: loads run two tiles ahead
+        if (tid == 0) {
+            const int nt = tile + 2 * (int)gridDim.x;
+            if (nt < ntiles) issue_load(nt, b);
+        }
+
+        // ---- T sweeps on chip --------------------------------------------------------------
+#pragma unroll
+        for (int s = 1; s <= T; s++) {
+            const double *pr = P[(s - 1) & 1];
+            double hW[PY], hE[PY], hN[PX], hS[PX];
+#pragma unroll
+            for (int py = 0; py < PY; py++) {
+                hW[py] = pr[((PX - 1) * TH + r0 + py) * PW + gW];
+                hE[py] = pr[(0 * TH + r0 + py) * PW + gE];
+            }
+#pragma unroll
+            for (int px = 0; px < PX; px++) {
+                hN[px] = pr[(px * TH + rN) * PW + g];
+                hS[px] = pr[(px * TH + rS) * PW + g];
+            }
+            // in-place update; `up[px]` carries the old value of the row above
+            double up[PX];
+#pragma unroll
+            for (int px = 0; px < PX; px++) up[px] = hN[px];
+#pragma unroll
+            for (int py = 0; py < PY; py++) {
+                double left = hW[py];
+#pragma unroll
+                for (int px = 0; px < PX; px++) {
+                    const double c = x[py][px];
+                    const double right = (px == PX - 1) ? hE[py] : x[py][px + 1];
+                    const double down = (py == PY - 1) ? hS[px] : x[py + 1][px];
+                    // x' = (1-w) x + wW xW + wE xE + wS xS + wN xN   (cuh:76-89, A and b folded into w)
+                    double r = omc[px] * c;
+                    r = fma(w[py][px][0], left, r);
+                    r = fma(w[py][px][1], right, r);
+                    r = fma(w[py][px][2], down, r);
+                    r = fma(w[py][px][3], up[px], r);
+                    x[py][px] = r;
+                    left = c;
+                    up[px] = c;
+                }
+            }
+            if (s < T) {
+                publish(P[s & 1]);
+                __syncthreads();
+            }
+        }
+
+        // ---- interior back to HBM through one bulk tensor store ---------------------------
+        {
+            double *out = OUT;                 // dense OW x OH box
+#pragma unroll
+            for (int py = 0; py < PY; py++) {
+                const int r = r0 + py - T;
+                if (r >= 0 && r < OH) {
+                    if constexpr (PX % 2 == 0) {   // c0, TE and OW are even: pairs never straddle the box edge
+#pragma unroll
+                        for (int px = 0; px < PX; px += 2) {
+                            const int c = c0 + px - TE;
+                            if (c >= 0 && c < OW)
+                                *reinterpret_cast<double2 *>(out + r * OW + c) = make_double2(x[py][px], x[py][px + 1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int px = 0; px < PX; px++) {
+                            const int c = c0 + px - TE;
+                            if (c >= 0 && c < OW) out[r * OW + c] = x[py][px];
+                        }
+                    }
+                }
+            }
+        }
+        fence_proxy_async();                   // generic-proxy writes -> visible to the TMA engine
+        __syncthreads();
+        if (tid == 0) {
+            int ox, oy;
+            tile_origin(tile, ox, oy);
+            tma_store_2d(map_out, ox, oy, OUT);
+            tma_commit();
+        }
+    }
+    if (tid == 0) tma_wait_all0();             // stores complete before the CTA's smem goes away
+}
+
+// ------------------------------------------------------------------------------------------ host side
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TmaState {
+    EncodeTiledFn encode = nullptr;
+    TmaMaps maps;
+    int cfg_T = 0;               // temporal depth the maps were encoded for
+    int ow = 0, oh = 0, tiles_x = 0, tiles_y = 0;
+    void *key_x0 = nullptr, *key_x1 = nullptr, *key_code = nullptr;
+    int64_t key_Nx = 0, key_Ny = 0, key_pitch = 0;
+    bool attr_set[2][17] = {{false}};
+    int cfg_F = -1;
+    int max_smem_optin = 0;
+};
+
+static int encode_2d(deff2d_ctx *c, TmaState *ts, CUtensorMap *m, CUtensorMapDataType dt, int esize, void *base,
+                     uint64_t d0, uint64_t d1, uint64_t pitch_bytes, uint32_t b0, uint32_t b1)
+{
+    cuuint64_t dims[2] = {d0, d1};
+    cuuint64_t strides[1] = {pitch_bytes};
+    cuuint32_t box[2] = {b0, b1};
+    cuuint32_t estr[2] = {1, 1};
+    (void)esize;
+    CUresult r = ts->encode(m, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error(c, "cuTensorMapEncodeTiled failed (CUresult %d) dims %llu x %llu pitch %llu box %u x %u", (int)r,
+                  (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)pitch_bytes, b0, b1);
+        return DEFF2D_ERR_CUDA;
+    }
     return DEFF2D_OK;
 }
 
-void tma_destroy(deff2d_ctx *c) { (void)c; }
+// tile geometries (all 128 x 32 cells, 256 threads, 16 cells per thread):
+//   family 0: 2 x 8 cells per thread, 2 x 4 warps   (16-byte patch rows: conflict-free staging)
+//   family 1: 4 x 4 cells per thread, 1 x 8 warps   (fewest exchange operations per sweep)
+template <int T, int F> struct Family;
+template <int T> struct Family<T, 0> { using type = Cfg<T, 2, 8, 2, 4>; };
+template <int T> struct Family<T, 1> { using type = Cfg<T, 4, 4, 1, 8>; };
+
+template <int T, int F>
+static int launch_T(deff2d_ctx *c, TmaState *ts, int src)
+{
+    using C = typename Family<T, F>::type;
+    auto kern = k_sweep_tma<C>;
+    if (!ts->attr_set[F][T]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) { set_error(c, "cudaFuncSetAttribute(smem %zu) failed: %s", C::SMEM, cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
+        ts->attr_set[F][T] = true;
+    }
+    const int ntiles = ts->tiles_x * ts->tiles_y;
+    int grid = c->prop.multiProcessorCount;
+    if (grid > ntiles) grid = ntiles;
+    kern<<<grid, C::NT, C::SMEM, c->stream>>>(ts->maps, src, c->lut.p, 1.0 - c->omega, (int)c->Nx, ts->tiles_x, ntiles, nullptr);
+    return DEFF2D_OK;
+}
+
+template <int T, int F>
+static int prepare_T(deff2d_ctx *c, TmaState *ts)
+{
+    using C = typename Family<T, F>::type;
+    if ((int)C::SMEM > ts->max_smem_optin) { set_error(c, "tile needs %zu B smem > %d", C::SMEM, ts->max_smem_optin); return DEFF2D_ERR_STATE; }
+    const bool same = ts->cfg_T == T && ts->cfg_F == F && ts->key_x0 == c->x[0].p && ts->key_x1 == c->x[1].p && ts->key_code == c->code.p &&
+                      ts->key_Nx == c->Nx && ts->key_Ny == c->Ny && ts->key_pitch == c->pitch;
+    if (same) return DEFF2D_OK;
+    int rc;
+    for (int b = 0; b < 2; b++) {
+        if ((rc = encode_2d(c, ts, &ts->maps.x_load[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, c->x[b].p, (uint64_t)c->pitch,
+                            (uint64_t)c->rows, (uint64_t)c->pitch * 8, C::TW, C::TH))) return rc;
+        if ((rc = encode_2d(c, ts, &ts->maps.x_store[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8,
+                            c->x[b].p + c->pitch + DEFF2D_XOFF, (uint64_t)c->Nx, (uint64_t)c->Ny, (uint64_t)c->pitch * 8,
+                            C::OW, C::OH))) return rc;
+    }
+    if ((rc = encode_2d(c, ts, &ts->maps.code, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c->code.p, (uint64_t)c->pitch,
+                        (uint64_t)c->rows, (uint64_t)c->pitch, C::CW, C::TH))) return rc;
+    ts->cfg_T = T;
+    ts->cfg_F = F;
+    ts->ow = C::OW; ts->oh = C::OH;
+    ts->tiles_x = (int)((c->Nx + C::OW - 1) / C::OW);
+    ts->tiles_y = (int)((c->Ny + C::OH - 1) / C::OH);
+    ts->key_x0 = c->x[0].p; ts->key_x1 = c->x[1].p; ts->key_code = c->code.p;
+    ts->key_Nx = c->Nx; ts->key_Ny = c->Ny; ts->key_pitch = c->pitch;
+    return DEFF2D_OK;
+}
+
+int launch_sweep_tma(deff2d_ctx *c, int64_t n, int64_t *done)
+{
+    *done = 0;
+    TmaState *ts = static_cast<TmaState *>(c->tma);
+    if (!ts) {
+        ts = new TmaState();
+        c->tma = ts;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+            (void)cudaGetLastError();
+            ts->encode = nullptr;
+        } else ts->encode = (EncodeTiledFn)fn;
+        cudaDeviceGetAttribute(&ts->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+    }
+    if (!ts->encode) { set_error(c, "cuTensorMapEncodeTiled is not available from this driver"); return DEFF2D_ERR_CUDA; }
+    int T = (int)std::min<int64_t>(n, c->tblock);
+    if (T < 1) T = 1;
+    // halo exchange of slab mode limits the depth to the halo rows held
+    int rc = DEFF2D_OK;
+    if (T > 8) T = 8;
+    const int fam = c->tile_family;
+#define DEFF2D_CASE(TT)                                                         \
+    case TT:                                                                    \
+        if (fam == 1) {                                                         \
+            if ((rc = prepare_T<TT, 1>(c, ts))) return rc;                      \
+            if ((rc = launch_T<TT, 1>(c, ts, c->cur))) return rc;               \
+        } else {                                                                \
+            if ((rc = prepare_T<TT, 0>(c, ts))) return rc;                      \
+            if ((rc = launch_T<TT, 0>(c, ts, c->cur))) return rc;               \
+        }                                                                       \
+        break;
+    switch (T) {
+        DEFF2D_CASE(1) DEFF2D_CASE(2) DEFF2D_CASE(3) DEFF2D_CASE(4) DEFF2D_CASE(5) DEFF2D_CASE(6) DEFF2D_CASE(7) DEFF2D_CASE(8)
+    }
+#undef DEFF2D_CASE
+    c->launches++;
+    c->cur ^= 1;
+    *done = T;
+    return DEFF2D_OK;
+}
+
+void tma_destroy(deff2d_ctx *c)
+{
+    delete static_cast<TmaState *>(c->tma);
+    c->tma = nullptr;
+}
 
 }  // namespace deff2d
