@@ -117,13 +117,14 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     constexpr int PW = C::PLANE_W, CW = C::CW;
     if (stop && *stop) return;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-    double *IN[2] = {reinterpret_cast<double *>(smem + C::OFF_IN), reinterpret_cast<double *>(smem + C::OFF_IN + C::IN_BYTES)};
-    double *P[2] = {reinterpret_cast<double *>(smem + C::OFF_P), reinterpret_cast<double *>(smem + C::OFF_P + C::IN_BYTES)};
-    double *OUT = reinterpret_cast<double *>(smem + C::OFF_OUT);
-    uint8_t *CODE[2] = {smem + C::OFF_CODE, smem + C::OFF_CODE + C::CODE_BYTES};
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+    // No integer round trip on the base pointer: the compiler must keep seeing the shared
+    // address space (a generic pointer turns every LDS/STS below into a slow generic LD/ST).
+    extern __shared__ __align__(1024) uint8_t smem[];
+    double *const IN0 = reinterpret_cast<double *>(smem + C::OFF_IN);
+    double *const P0 = reinterpret_cast<double *>(smem + C::OFF_P);
+    double *const OUT = reinterpret_cast<double *>(smem + C::OFF_OUT);
+    uint8_t *const CODE0 = smem + C::OFF_CODE;
+    uint64_t *const bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wx = warp % C::NWX, wy = warp / C::NWX;
@@ -145,8 +146,8 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         mbar_expect_tx(&bar[b], TX_BYTES);
         // padded coordinates of the input box: interior (ox-TE, oy-T) -> (+XOFF, +1); even
         const int xs = ox - TE + DEFF2D_XOFF;
-        tma_load_2d(IN[b], map_in, xs, oy - T + 1, &bar[b]);
-        tma_load_2d(CODE[b], &maps.code, xs & ~15, oy - T + 1, &bar[b]);
+        tma_load_2d(IN0 + b * C::CELLS, map_in, xs, oy - T + 1, &bar[b]);
+        tma_load_2d(CODE0 + b * C::CODE_BYTES, &maps.code, xs & ~15, oy - T + 1, &bar[b]);
     };
 
     if (tid == 0) {
@@ -180,8 +181,8 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         {
             int ox, oy;
             tile_origin(tile, ox, oy);
-            const double *in = IN[b];
-            const uint8_t *cd = CODE[b] + ((ox - TE + DEFF2D_XOFF) & 15);
+            const double *in = IN0 + b * C::CELLS;
+            const uint8_t *cd = CODE0 + b * C::CODE_BYTES + ((ox - TE + DEFF2D_XOFF) & 15);
 #pragma unroll
             for (int py = 0; py < PY; py++) {
                 if constexpr (PX % 2 == 0) {       // 16-byte loads: conflict-free for PX == 2
@@ -240,7 +241,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
                     if (edge) pb[(px * TH + r0 + py) * PW + g] = x[py][px];
                 }
         };
-        publish(P[0]);
+        publish(P0);
         // the OUT box of the previous tile must have been read by its bulk store before this
         // tile's last sweep overwrites it (the wait is ordered before the writes by S1)
         if (tid == 0) tma_wait_read0();
@@ -255,7 +256,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         // ---- T sweeps on chip --------------------------------------------------------------
 #pragma unroll
         for (int s = 1; s <= T; s++) {
-            const double *pr = P[(s - 1) & 1];
+            const double *pr = P0 + ((s - 1) & 1) * C::CELLS;
             double hW[PY], hE[PY], hN[PX], hS[PX];
 #pragma unroll
             for (int py = 0; py < PY; py++) {
@@ -291,7 +292,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
                 }
             }
             if (s < T) {
-                publish(P[s & 1]);
+                publish(P0 + (s & 1) * C::CELLS);
                 __syncthreads();
             }
         }
