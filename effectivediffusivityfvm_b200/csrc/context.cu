@@ -93,7 +93,12 @@ static int enqueue_sweeps(deff2d_ctx *c, int64_t n)
 {
     while (n > 0) {
         int64_t done = 0;
-        if (c->kernel == 2) {
+        // kernel 0 (default): the TMA tiled kernel (4x4 patches, 4 sweeps per HBM pass -- the
+        // fastest measured configuration, profiles/) once the domain fills the machine with
+        // tiles; the streaming kernel for small domains.
+        const bool big = c->Nx >= 512 && c->Ny >= 128 && c->Nx * c->Ny >= (int64_t)1 << 21;
+        if (c->kernel == 2 || (c->kernel == 0 && big)) {
+            if (c->kernel == 0) { c->tile_family = 1; c->tblock = 4; }
             int rc = launch_sweep_tma(c, n, &done);
             if (rc) return rc;
         }
@@ -647,9 +652,9 @@ DEFF2D_EXPORT int deff2d_sync(deff2d_ctx *c)
 
 DEFF2D_EXPORT int deff2d_set_kernel(deff2d_ctx *c, int kernel, int tblock)
 {
-    if (!c || kernel < 0 || kernel > 3 || tblock < 0 || tblock > 16) return DEFF2D_ERR_ARG;
-    c->tile_family = (kernel == 3) ? 1 : 0;     // 3: alternative tile geometry of the TMA kernel (tuning)
-    if (kernel == 3) kernel = 2;
+    if (!c || kernel < 0 || kernel > 4 || tblock < 0 || tblock > 16) return DEFF2D_ERR_ARG;
+    c->tile_family = (kernel >= 3) ? kernel - 2 : 0;   // 3, 4: alternative tile geometries of the TMA kernel (tuning)
+    if (kernel >= 3) kernel = 2;
     c->kernel = kernel;
     c->tblock = tblock > 0 ? tblock : 1;
     return DEFF2D_OK;

@@ -18,7 +18,7 @@ p = E.default_params(amp_x=4, amp_y=4)
 ctx.domain_load(img, 3, p)
 cells = 4008 * 8028
 out = {}
-for kernel, T in [(1, 1)] + [(2, t) for t in range(1, 9)] + [(3, t) for t in range(1, 9)]:
+for kernel, T in [(1, 1)] + [(2, t) for t in range(1, 9)] + [(3, t) for t in (4, 6)] + [(4, t) for t in range(1, 9)]:
     ctx.set_kernel(kernel, T)
     ctx.sweeps_timed(max(T * 4, 8))
     ms = min(ctx.sweeps_timed(sweeps) for _ in range(3))
