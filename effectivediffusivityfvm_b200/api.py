@@ -242,6 +242,10 @@ class Deff2D:
     def set_kernel(self, kernel, tblock=0):
         self._ck(self._L.deff2d_set_kernel(self._h, int(kernel), int(tblock)))
 
+    def set_batch_slots(self, max_slots):
+        """Cap the images resident at a time in packed batch mode (0 = library default)."""
+        self._ck(self._L.deff2d_set_batch_slots(self._h, int(max_slots)))
+
     @property
     def kernel_launches(self):
         return int(self._L.deff2d_kernel_launches(self._h))

@@ -1,11 +1,688 @@
-// batch.cu -- K5: resident small-image batch solve (placeholder: falls back to per-image solves).
+// batch.cu -- K5: packed batch mode.  Many small images are solved per launch by packing them
+// into one resident "stack" that the tiled sweep kernel (sweep_tma.cu) walks like a single
+// large domain:
+//
+//   * the stack is a GX x GY grid of slots; slot (gx, gy) holds one image with its interior
+//     origin at column gx*(Nx+1), row gy*(Ny+1).  Neighbouring slots share one ghost column
+//     (Dirichlet value 1.0, the CL / CR factor lives in the face weight, tables.cpp) and one
+//     ghost row (no-flux wall, weight 0), so images never interact: the packed sweep is
+//     exactly the reference's per-image sweep (BatchSim / BatchSim3Phase bodies,
+//     Deff2D.cuh:1867-2049, 2056-2419), image by image.
+//   * every image follows its own copy of the reference loop (cuh:1232-1290): its own sweep
+//     counter, checks at its own sweeps 1, 10 001, ..., its own stop rule and its own
+//     continuation stage (3-phase pre-conditioning, cuh:1492-1597).  The stage is carried in
+//     bits 3-7 of the cell code and selects one of the per-stage weight tables, so images in
+//     different stages share a launch.
+//   * the host enqueues sweeps up to the next event of any active image (a check or MaxIter),
+//     then one k_batch_check launch evaluates boundary flux + stop rule for all images at once
+//     and the host reads back 40 bytes per slot.  Tiles whose output touches no active image
+//     are dropped from the tile list, finished slots are refilled from the queue.
+//
+// Nothing here allocates per image: the stack, tables and staging buffers live in the
+// context's grow-only arenas.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <thread>
+#include <vector>
+
 #include "context.h"
 
 namespace deff2d {
+
+#define XOFF DEFF2D_XOFF
+#define BATCH_MAX_STAGES DEFF2D_MAX_STAGES
+
+struct BatchStage {
+    double D[3];            // fluid, solid, gas of the stage
+    double tol;
+    long long max_iter;
+    int precond;            // JacobiGPUPreCond stage: result not recorded as Deff (cuh:1144-1159)
+    int pad;
+};
+
+struct BatchSlot {
+    double deff_old, deff_new, change, conv;   // cuh:1171-1173, 1275
+    long long iter;         // iterCount of the current stage
+    int stage;
+    int status;             // 0 empty, 1 active, 2 finished
+    int image;
+    int nchecks;
+};
+
+struct BatchOut {
+    long long iters[BATCH_MAX_STAGES];
+    double stage_deff_raw[BATCH_MAX_STAGES];
+    double deff_raw, conv;
+    unsigned long long phase[3], below150;
+    int nstages, pad;
+};
+
+struct BatchJob { int slot, image; };
+
+struct BatchGeom {
+    int W, H, amp_x, amp_y, Nx, Ny, GX, nphase;
+    long long pitch;
+    double CL, CR;
+    int ce, nstages;
+};
+
+struct BatchStages { BatchStage s[BATCH_MAX_STAGES]; };
+
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_ull(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Threshold + mesh amplification + ghost ring + x0 of every (slot, image) job: the packed
+// counterpart of k_init_domain (cuh:1773-1785, 1557-1578, 1730-1734, 750).
+__global__ void __launch_bounds__(256)
+k_batch_init(BatchGeom g, const BatchJob *__restrict__ jobs, const uint8_t *__restrict__ img_base,
+             const uint8_t *__restrict__ grid_base, double *__restrict__ xc, double *__restrict__ xo,
+             uint8_t *__restrict__ code, BatchSlot *slots, BatchOut *outs)
+{
+    const BatchJob job = jobs[blockIdx.y];
+    const int gx = job.slot % g.GX, gy = job.slot / g.GX;
+    const long long col0 = (long long)gx * (g.Nx + 1), row0 = (long long)gy * (g.Ny + 1);
+    const uint8_t *img = img_base + (size_t)job.image * g.W * g.H;
+    const uint8_t *grid = grid_base ? grid_base + (size_t)job.image * g.Nx * g.Ny : nullptr;
+    const long long wp = g.Nx + 2, total = (long long)(g.Ny + 2) * wp;
+    unsigned long long cnt[3] = {0, 0, 0}, below = 0;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const long long r = k / wp;
+        const long long i = r - 1, j = (k - r * wp) - 1;
+        const long long idx = (row0 + r) * g.pitch + col0 + j + XOFF;
+        unsigned cd = DEFF2D_PHASE_GHOST;
+        double v0 = 0.0, v1 = 0.0;
+        if (j == -1 || j == g.Nx) { v0 = 1.0; v1 = 1.0; }                 // Dirichlet ghost column
+        else if (i >= 0 && i < g.Ny) {
+            const unsigned char p = img[(i / g.amp_y) * g.W + (int)(j / g.amp_x)];      // cuh:1778
+            if (g.nphase == 2) cd = (p < 150) ? DEFF2D_PHASE_FLUID : DEFF2D_PHASE_SOLID;   // cuh:1779
+            else cd = (p > 200) ? DEFF2D_PHASE_SOLID : ((p < 50) ? DEFF2D_PHASE_GAS : DEFF2D_PHASE_FLUID);   // cuh:1565-1576
+            cnt[cd]++;
+            if (grid) {
+                const unsigned char gv = grid[i * g.Nx + j];
+                if (gv == 1 || gv == 2) cd |= DEFF2D_CODE_PINNED;                      // cuh:750
+            }
+            v0 = __dadd_rn(__dmul_rn(__ddiv_rn((double)j, (double)g.Nx), __dsub_rn(g.CR, g.CL)), g.CL);   // cuh:1732
+        }
+        code[idx] = (uint8_t)cd;
+        xc[idx] = v0;
+        xo[idx] = v1;
+    }
+    // calcPorosity's count (cuh:399-405) over the source pixels
+    const long long npix = (long long)g.W * g.H;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < npix; k += (long long)gridDim.x * blockDim.x)
+        below += (img[k] < 150) ? 1u : 0u;
+    BatchOut *o = outs + job.image;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const unsigned long long s = warp_sum_ull(cnt[k]);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(&o->phase[k], s);
+    }
+    const unsigned long long sb = warp_sum_ull(below);
+    if ((threadIdx.x & 31) == 0 && sb) atomicAdd(&o->below150, sb);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        BatchSlot s;
+        s.deff_old = 5; s.deff_new = 1; s.change = 100.0; s.conv = 0;          // cuh:1171-1173
+        s.iter = 0; s.stage = 0; s.status = 1; s.image = job.image; s.nchecks = 0;
+        slots[job.slot] = s;
+    }
+}
+
+// After `nsweeps` more sweeps of every active slot: the reference's check (boundary flux,
+// Deff, signed change, cuh:1243-1276), its loop condition (cuh:1232) and the drivers' stage
+// sequence (cuh:1492-1597), for all slots of `active` in one launch.  The flux sums use the same
+// thread-to-row assignment and reduction order as k_flux (kernels.cu), so a packed image gets
+// bit-identical Deff values to a single-image solve.
+__global__ void __launch_bounds__(1024)
+k_batch_check(BatchGeom g, BatchStages stages, BatchSlot *slots, BatchOut *outs, const int *__restrict__ active,
+              long long nsweeps, const double *__restrict__ x, uint8_t *code)
+{
+    __shared__ double s1[32], s2[32];
+    __shared__ int sh_restage;
+    const int slot = active[blockIdx.x];
+    BatchSlot S = slots[slot];
+    if (S.status != 1) return;
+    const long long it = S.iter + nsweeps;
+    const BatchStage st = stages.s[S.stage];
+    const bool do_check = ((it - 1) % g.ce == 0);                   // cuh:1243 on the pre-increment counter
+    const int gx = slot % g.GX, gy = slot / g.GX;
+    const long long col0 = (long long)gx * (g.Nx + 1), row0 = (long long)gy * (g.Ny + 1);
+    if (threadIdx.x == 0) sh_restage = -1;
+    double q1 = 0, q2 = 0;
+    if (do_check) {
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        const double half_dx = (1.0 / (double)g.Nx) / 2.0;          // dx / 2.0, cuh:1256
+        for (long long r = threadIdx.x; r < g.Ny; r += blockDim.x) {
+            const long long base = (row0 + r + 1) * g.pitch + col0 + XOFF;
+            const unsigned cl = code[base], cr = code[base + g.Nx - 1];
+            const double Dl = st.D[cl & 3u], Dr = st.D[cr & 3u];
+            double tl = Dl * (x[base] - g.CL) / half_dx;
+            double tr = Dr * (g.CR - x[base + g.Nx - 1]) / half_dx;
+            if (Dl == 0.0 && !(cl & 4u)) tl = nan;                  // quirk Q13, see k_flux
+            if (Dr == 0.0 && !(cr & 4u)) tr = nan;
+            q1 += tl;
+            q2 += tr;
+        }
+        q1 = warp_sum_d(q1);
+        q2 = warp_sum_d(q2);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) { s1[wid] = q1; s2[wid] = q2; }
+        __syncthreads();
+        if (wid == 0) {
+            const int nw = (blockDim.x + 31) >> 5;
+            q1 = lane < nw ? s1[lane] : 0.0;
+            q2 = lane < nw ? s2[lane] : 0.0;
+            q1 = warp_sum_d(q1);
+            q2 = warp_sum_d(q2);
+        }
+    }
+    if (threadIdx.x == 0) {
+        bool stop = false;
+        if (do_check) {
+            const double qAvg = (q1 + q2) / (2.0 * (double)g.Ny);           // cuh:1263
+            const double deffNew = qAvg / (g.CR - g.CL);                    // cuh:1264
+            const double change = (S.deff_old - deffNew) / (S.deff_old);    // cuh:1265
+            S.deff_new = deffNew;
+            S.change = change;
+            S.conv = change;                                                // cuh:1275
+            S.deff_old = deffNew;                                           // cuh:1273
+            S.nchecks++;
+            stop = !(st.tol < fabs(change));                                // cuh:1232 (NaN ends the loop)
+        }
+        S.iter = it;
+        if (stop || it >= st.max_iter) {
+            BatchOut *o = outs + S.image;
+            o->iters[S.stage] = it;
+            o->stage_deff_raw[S.stage] = S.deff_new;
+            if (!st.precond) { o->deff_raw = S.deff_new; o->conv = S.conv; }   // cuh:1309-1311 vs cuh:1144-1159
+            o->nstages = S.stage + 1;
+            if (S.stage + 1 < g.nstages) {
+                S.stage++;
+                S.iter = 0; S.deff_old = 5; S.deff_new = 1; S.change = 100.0; S.nchecks = 0;
+                sh_restage = S.stage;
+            } else {
+                S.status = 2;
+            }
+        }
+        slots[slot] = S;
+    }
+    __syncthreads();
+    const int rs = sh_restage;
+    if (rs >= 0) {      // next continuation stage: only the weight table changes (cuh:1524), selected by code bits 3-7
+        const long long total = (long long)g.Ny * g.Nx;
+        for (long long k = threadIdx.x; k < total; k += blockDim.x) {
+            const long long i = k / g.Nx, j = k - i * g.Nx;
+            const long long idx = (row0 + i + 1) * g.pitch + col0 + j + XOFF;
+            code[idx] = (uint8_t)((code[idx] & 7u) | ((unsigned)rs << 3));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+
+struct BatchState {
+    DevBuf<BatchSlot> slots;
+    DevBuf<BatchOut> outs;
+    DevBuf<BatchJob> jobs;
+    DevBuf<int> active;
+    DevBuf<uint32_t> tiles;
+    BatchSlot *h_slots = nullptr;
+    BatchJob *h_jobs = nullptr;
+    int *h_active = nullptr;
+    uint32_t *h_tiles = nullptr;
+    size_t h_slots_cap = 0, h_jobs_cap = 0, h_active_cap = 0, h_tiles_cap = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+};
+
+template <typename T>
+static int dev_ensure(deff2d_ctx *c, DevBuf<T> &b, size_t n)
+{
+    if (b.cap >= n && b.p) return DEFF2D_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+    const size_t want = n + n / 8 + 64;
+    if (cudaMalloc((void **)&b.p, want * sizeof(T)) != cudaSuccess) {
+        b.p = nullptr;
+        (void)cudaGetLastError();
+        set_error(c, "cudaMalloc of %zu bytes failed", want * sizeof(T));
+        return DEFF2D_ERR_ALLOC;
+    }
+    b.cap = want;
+    return DEFF2D_OK;
+}
+
+template <typename T>
+static int host_ensure(deff2d_ctx *c, T *&p, size_t &cap, size_t n)
+{
+    if (cap >= n && p) return DEFF2D_OK;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = n + n / 8 + 64;
+    if (cudaMallocHost((void **)&p, want * sizeof(T)) != cudaSuccess) {
+        p = nullptr;
+        (void)cudaGetLastError();
+        set_error(c, "cudaMallocHost of %zu bytes failed", want * sizeof(T));
+        return DEFF2D_ERR_ALLOC;
+    }
+    cap = want;
+    return DEFF2D_OK;
+}
+
+void batch_destroy(deff2d_ctx *c)
+{
+    BatchState *b = static_cast<BatchState *>(c->batch);
+    if (!b) return;
+    if (b->slots.p) cudaFree(b->slots.p);
+    if (b->outs.p) cudaFree(b->outs.p);
+    if (b->jobs.p) cudaFree(b->jobs.p);
+    if (b->active.p) cudaFree(b->active.p);
+    if (b->tiles.p) cudaFree(b->tiles.p);
+    if (b->h_slots) cudaFreeHost(b->h_slots);
+    if (b->h_jobs) cudaFreeHost(b->h_jobs);
+    if (b->h_active) cudaFreeHost(b->h_active);
+    if (b->h_tiles) cudaFreeHost(b->h_tiles);
+    if (b->e0) cudaEventDestroy(b->e0);
+    if (b->e1) cudaEventDestroy(b->e1);
+    delete b;
+    c->batch = nullptr;
+}
+
+#define CUB(call)                                                                            \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            set_error(c, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return DEFF2D_ERR_CUDA;                                                          \
+        }                                                                                    \
+    } while (0)
+
+// The stage sequence of the reference drivers for one image (context.cu: solve_image_impl).
+static int build_stages(const deff2d_params *p, BatchStages *st, double *stageD, int *nst)
+{
+    int n = 0;
+    auto add = [&](double Df, double Ds, double Dg, double tol, long long mi, int pre, double sd) {
+        if (n >= BATCH_MAX_STAGES) return false;
+        st->s[n].D[0] = Df; st->s[n].D[1] = Ds; st->s[n].D[2] = Dg;
+        st->s[n].tol = tol; st->s[n].max_iter = mi; st->s[n].precond = pre; st->s[n].pad = 0;
+        stageD[n] = sd;
+        n++;
+        return true;
+    };
+    if (p->mode == DEFF2D_MODE_2PH_BATCH) {
+        if (!add(p->Df, p->Ds, 0.0, p->tol, p->max_iter, 0, p->Df)) return 1;          // cuh:2004-2009
+    } else if (p->mode == DEFF2D_MODE_3PH) {
+        double DCG_Temp = 10;                                                         // cuh:1492
+        while (DCG_Temp < p->Dg) {                                                    // cuh:1504; tol*10, MAX_ITER 1e6: cuh:1501-1502
+            if (!add(p->Df, p->Ds, DCG_Temp, p->tol * 10, 1000000, 1, DCG_Temp)) return 1;
+            DCG_Temp = DCG_Temp * 10;                                                 // cuh:1547
+        }
+        if (!add(p->Df, p->Ds, p->Dg, p->tol, p->max_iter, 0, p->Dg)) return 1;       // cuh:1557-1591
+    } else {
+        return 1;
+    }
+    for (int k = 0; k < n; k++)     // the packed loop needs at least one sweep per stage (cuh:1232)
+        if (!(st->s[k].tol < 100.0) || st->s[k].max_iter < 1) return 1;
+    *nst = n;
+    return 0;
+}
+
+// Slot grid for `count` images of Nx x Ny cells: rows of slots about 4096 cells wide, at most
+// ~48 M cells resident (2 x 8 + 1 bytes per cell).
+void batch_plan(int64_t Nx, int64_t Ny, int count, int limit, int *GX, int *GY)
+{
+    int gx = (int)std::max<int64_t>(1, 4096 / (Nx + 1));
+    int64_t max_slots = std::max<int64_t>(1, ((int64_t)48 << 20) / (Nx * Ny));
+    if (limit > 0 && limit < max_slots) max_slots = limit;
+    int slots = (int)std::min<int64_t>(count, max_slots);
+    if (gx > slots) gx = slots;
+    int gy = (slots + gx - 1) / gx;
+    *GX = gx;
+    *GY = gy;
+}
+
+// Tiles (output box ow x oh) whose output intersects the interior of an active slot.
+void batch_tile_list(int64_t Nx, int64_t Ny, int GX, const int *active, int nactive, int ow, int oh, int tiles_x,
+                     int tiles_y, std::vector<uint8_t> &mark, std::vector<uint32_t> &out)
+{
+    mark.assign((size_t)tiles_x * tiles_y, 0);
+    for (int a = 0; a < nactive; a++) {
+        const int gx = active[a] % GX, gy = active[a] / GX;
+        const int64_t c0 = (int64_t)gx * (Nx + 1), r0 = (int64_t)gy * (Ny + 1);
+        const int tx0 = (int)(c0 / ow), tx1 = (int)((c0 + Nx - 1) / ow);
+        const int ty0 = (int)(r0 / oh), ty1 = (int)((r0 + Ny - 1) / oh);
+        for (int ty = ty0; ty <= ty1 && ty < tiles_y; ty++)
+            for (int tx = tx0; tx <= tx1 && tx < tiles_x; tx++) mark[(size_t)ty * tiles_x + tx] = 1;
+    }
+    out.clear();
+    for (int ty = 0; ty < tiles_y; ty++)
+        for (int tx = 0; tx < tiles_x; tx++)
+            if (mark[(size_t)ty * tiles_x + tx]) out.push_back(((uint32_t)ty << 16) | (uint32_t)tx);
+}
+
+static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int H, const deff2d_params *p,
+                       deff2d_result *results, double *fields, const BatchStages &stages, const double *stageD,
+                       int nstages)
+{
+    BatchState *b = static_cast<BatchState *>(c->batch);
+    if (!b) {
+        b = new BatchState();
+        c->batch = b;
+        CUB(cudaEventCreate(&b->e0));
+        CUB(cudaEventCreate(&b->e1));
+    }
+    const int nphase = (p->mode == DEFF2D_MODE_3PH) ? 3 : 2;
+    const int64_t Nx = (int64_t)W * p->amp_x, Ny = (int64_t)H * p->amp_y;
+    const int64_t cells = Nx * Ny;
+    const size_t npix = (size_t)W * H;
+    int GX, GY;
+    batch_plan(Nx, Ny, count, c->batch_max_slots, &GX, &GY);
+    const int nslots = GX * GY;
+    const int T = 4;                                     // sweeps per HBM pass (profiles/: best measured depth)
+
+    // ---- FloodFill on host threads (cuh:557-713): PathFlag always, pinned mask in 3-phase -----------
+    std::vector<int> pathflag((size_t)count, 0);
+    std::vector<uint8_t> masks;
+    if (nphase == 3) masks.resize((size_t)count * cells);
+    {
+        const int thr = (nphase == 3) ? 200 : 150;       // cuh:1368, cuh:1695
+        std::atomic<int> next(0);
+        const int nthreads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+        auto work = [&]() {
+            std::vector<uint8_t> local;
+            for (;;) {
+                const int k = next.fetch_add(1);
+                if (k >= count) break;
+                uint8_t *g = nullptr;
+                if (nphase == 3) g = masks.data() + (size_t)k * cells;
+                else { local.resize((size_t)cells); g = local.data(); }
+                const uint8_t *src = gray + npix * k;
+                for (int64_t i = 0; i < Ny; i++) {
+                    const uint8_t *srow = src + (size_t)(i / p->amp_y) * W;
+                    uint8_t *gr = g + (size_t)i * Nx;
+                    for (int64_t j = 0; j < Nx; j++) gr[j] = srow[j / p->amp_x] > thr;
+                }
+                pathflag[(size_t)k] = floodfill(g, Nx, Ny);
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nthreads && t < count; t++) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+    }
+
+    // ---- resident stack -----------------------------------------------------------------------
+    CUB(cudaSetDevice(c->device));
+    c->loaded = false;
+    c->Nx = (int64_t)GX * (Nx + 1) - 1;
+    c->Ny = (int64_t)GY * (Ny + 1) - 1;
+    c->NxG = Nx; c->NyG = Ny;
+    c->pitch = ((c->Nx + 2 * XOFF) + 15) / 16 * 16;
+    c->rows = c->Ny + 2;
+    c->ghost_period = Nx + 1;
+    c->own_first = 0; c->own_rows = c->Ny;
+    c->nphase = nphase;
+    c->CL = p->CL; c->CR = p->CR;
+    c->omega = (p->omega > 0) ? p->omega : 2.0 / 3.0;
+    c->check_every = (p->check_every > 0) ? p->check_every : 10000;
+    c->cur = 0;
+    const size_t stack_cells = (size_t)c->rows * (size_t)c->pitch;
+    int rc;
+    auto grow = [&](auto &buf, size_t n) -> int {
+        if (buf.cap >= n && buf.p) return DEFF2D_OK;
+        if (buf.p) { cudaFree(buf.p); buf.p = nullptr; buf.cap = 0; }
+        using E = std::remove_reference_t<decltype(*buf.p)>;
+        if (cudaMalloc((void **)&buf.p, n * sizeof(E)) != cudaSuccess) {
+            buf.p = nullptr;
+            (void)cudaGetLastError();
+            set_error(c, "cudaMalloc of %zu bytes failed", n * sizeof(E));
+            return DEFF2D_ERR_ALLOC;
+        }
+        buf.cap = n;
+        return DEFF2D_OK;
+    };
+    if ((rc = grow(c->x[0], stack_cells)) || (rc = grow(c->x[1], stack_cells)) || (rc = grow(c->code, stack_cells))) return rc;
+    if ((rc = grow(c->img, npix * count))) return rc;
+    if (nphase == 3 && (rc = grow(c->grid, (size_t)cells * count))) return rc;
+    if ((rc = grow(c->lut, (size_t)nstages * DEFF2D_LUT_ENTRIES * 4)) || (rc = grow(c->dead, (size_t)nstages * DEFF2D_LUT_ENTRIES))) return rc;
+    if (fields && (rc = grow(c->dense, (size_t)cells))) return rc;
+    if ((rc = dev_ensure(c, b->slots, (size_t)nslots)) || (rc = dev_ensure(c, b->outs, (size_t)count)) ||
+        (rc = dev_ensure(c, b->jobs, (size_t)nslots)) || (rc = dev_ensure(c, b->active, (size_t)nslots))) return rc;
+    if ((rc = host_ensure(c, b->h_slots, b->h_slots_cap, (size_t)nslots)) || (rc = host_ensure(c, b->h_jobs, b->h_jobs_cap, (size_t)nslots)) ||
+        (rc = host_ensure(c, b->h_active, b->h_active_cap, (size_t)nslots))) return rc;
+
+    cudaStream_t s = c->stream;
+    CUB(cudaMemsetAsync(c->x[0].p, 0, stack_cells * sizeof(double), s));
+    CUB(cudaMemsetAsync(c->x[1].p, 0, stack_cells * sizeof(double), s));
+    CUB(cudaMemsetAsync(c->code.p, DEFF2D_PHASE_GHOST, stack_cells, s));
+    CUB(cudaMemsetAsync(b->slots.p, 0, (size_t)nslots * sizeof(BatchSlot), s));
+    CUB(cudaMemsetAsync(b->outs.p, 0, (size_t)count * sizeof(BatchOut), s));
+    CUB(cudaMemcpyAsync(c->img.p, gray, npix * count, cudaMemcpyHostToDevice, s));
+    if (nphase == 3) CUB(cudaMemcpyAsync(c->grid.p, masks.data(), (size_t)cells * count, cudaMemcpyHostToDevice, s));
+    {
+        std::vector<double> lut((size_t)nstages * DEFF2D_LUT_ENTRIES * 4);
+        std::vector<uint8_t> dead((size_t)nstages * DEFF2D_LUT_ENTRIES);
+        for (int k = 0; k < nstages; k++)
+            build_tables(stages.s[k].D, Nx, Ny, c->CL, c->CR, c->omega, lut.data() + (size_t)k * DEFF2D_LUT_ENTRIES * 4,
+                         dead.data() + (size_t)k * DEFF2D_LUT_ENTRIES);
+        CUB(cudaMemcpyAsync(c->lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        CUB(cudaMemcpyAsync(c->dead.p, dead.data(), dead.size(), cudaMemcpyHostToDevice, s));
+        CUB(cudaStreamSynchronize(s));
+    }
+
+    BatchGeom g;
+    g.W = W; g.H = H; g.amp_x = p->amp_x; g.amp_y = p->amp_y; g.Nx = (int)Nx; g.Ny = (int)Ny; g.GX = GX; g.nphase = nphase;
+    g.pitch = c->pitch; g.CL = c->CL; g.CR = c->CR; g.ce = c->check_every; g.nstages = nstages;
+
+    // tile grids of the pass depths in use (T and the remainders 1..T-1)
+    int ow[9], oh[9], tx_n[9], ty_n[9];
+    size_t tiles_cap = 0;
+    for (int t = 1; t <= T; t++) {
+        tma_tile_geometry(c, t, &ow[t], &oh[t]);
+        tx_n[t] = (int)((c->Nx + ow[t] - 1) / ow[t]);
+        ty_n[t] = (int)((c->Ny + oh[t] - 1) / oh[t]);
+        if (ty_n[t] > 0xffff || tx_n[t] > 0xffff) { set_error(c, "packed batch: tile grid too large"); return DEFF2D_ERR_ARG; }
+        tiles_cap += (size_t)tx_n[t] * ty_n[t];
+    }
+    if ((rc = dev_ensure(c, b->tiles, tiles_cap)) || (rc = host_ensure(c, b->h_tiles, b->h_tiles_cap, tiles_cap))) return rc;
+    size_t tile_off[9] = {0};
+    int tile_cnt[9] = {0};
+
+    std::vector<int> slot_image((size_t)nslots, -1);     // host mirror: image in each slot (-1 empty)
+    std::vector<long long> slot_iter((size_t)nslots, 0);
+    std::vector<int> slot_stage((size_t)nslots, 0);
+    std::vector<double> solve_ms((size_t)count, 0.0), total_ms((size_t)count, 0.0);
+    std::vector<uint8_t> mark;
+    std::vector<uint32_t> tl;
+    int next_image = 0, nactive = 0, done_images = 0;
+    bool active_changed = true;
+    const int old_family = c->tile_family, old_tblock = c->tblock;
+    c->tile_family = 1;
+    c->tblock = T;
+    auto restore = [&]() {
+        c->tile_family = old_family; c->tblock = old_tblock;
+        c->tile_list = nullptr; c->tile_count = 0;
+    };
+
+    while (done_images < count) {
+        // ---- refill empty slots from the queue ------------------------------------------------
+        int njobs = 0;
+        for (int sl = 0; sl < nslots && next_image < count; sl++)
+            if (slot_image[(size_t)sl] < 0) {
+                b->h_jobs[njobs].slot = sl;
+                b->h_jobs[njobs].image = next_image;
+                slot_image[(size_t)sl] = next_image;
+                slot_iter[(size_t)sl] = 0;
+                slot_stage[(size_t)sl] = 0;
+                next_image++;
+                njobs++;
+                active_changed = true;
+            }
+        if (njobs) {
+            CUB(cudaMemcpyAsync(b->jobs.p, b->h_jobs, (size_t)njobs * sizeof(BatchJob), cudaMemcpyHostToDevice, s));
+            int bx = (int)std::min<int64_t>(((Ny + 2) * (Nx + 2) + 255) / 256, 64);
+            k_batch_init<<<dim3((unsigned)bx, (unsigned)njobs), 256, 0, s>>>(g, b->jobs.p, c->img.p, nphase == 3 ? c->grid.p : nullptr,
+                                                                            c->x[c->cur].p, c->x[c->cur ^ 1].p, c->code.p,
+                                                                            b->slots.p, b->outs.p);
+            c->launches++;
+        }
+        if (active_changed) {
+            nactive = 0;
+            for (int sl = 0; sl < nslots; sl++)
+                if (slot_image[(size_t)sl] >= 0) b->h_active[nactive++] = sl;
+            CUB(cudaMemcpyAsync(b->active.p, b->h_active, (size_t)nactive * sizeof(int), cudaMemcpyHostToDevice, s));
+            size_t off = 0;
+            for (int t = 1; t <= T; t++) {
+                batch_tile_list(Nx, Ny, GX, b->h_active, nactive, ow[t], oh[t], tx_n[t], ty_n[t], mark, tl);
+                tile_off[t] = off;
+                tile_cnt[t] = (int)tl.size();
+                std::memcpy(b->h_tiles + off, tl.data(), tl.size() * sizeof(uint32_t));
+                off += tl.size();
+            }
+            CUB(cudaMemcpyAsync(b->tiles.p, b->h_tiles, off * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+            active_changed = false;
+        }
+        // ---- sweeps up to the next event of any active image (check or MaxIter) ---------------
+        long long n = -1;
+        const long long ce = c->check_every;
+        int npre = 0;
+        for (int a = 0; a < nactive; a++) {
+            const int sl = b->h_active[a];
+            const long long it = slot_iter[(size_t)sl];
+            const BatchStage &st = stages.s[slot_stage[(size_t)sl]];
+            const long long to_check = ((it % ce == 0) ? it : (it / ce + 1) * ce) + 1 - it;
+            const long long to_max = st.max_iter - it;
+            const long long m = std::min(to_check, to_max);
+            if (n < 0 || m < n) n = m;
+            if (st.precond) npre++;
+        }
+        if (n < 1) { restore(); set_error(c, "packed batch: internal scheduling error"); return DEFF2D_ERR_STATE; }
+        CUB(cudaEventRecord(b->e0, s));
+        for (long long left = n; left > 0;) {
+            const int t = (int)std::min<long long>(left, T);
+            if ((rc = tma_pass(c, t, b->tiles.p + tile_off[t], tile_cnt[t], s))) { restore(); return rc; }
+            c->cur ^= 1;
+            left -= t;
+        }
+        k_batch_check<<<nactive, 1024, 0, s>>>(g, stages, b->slots.p, b->outs.p, b->active.p, n, c->x[c->cur].p, c->code.p);
+        c->launches++;
+        CUB(cudaEventRecord(b->e1, s));
+        CUB(cudaMemcpyAsync(b->h_slots, b->slots.p, (size_t)nslots * sizeof(BatchSlot), cudaMemcpyDeviceToHost, s));
+        CUB(cudaStreamSynchronize(s));
+        {
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) { restore(); set_error(c, "packed batch launch failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
+        }
+        float ms = 0;
+        CUB(cudaEventElapsedTime(&ms, b->e0, b->e1));
+        // the window's device time is shared equally by the images that were swept in it; like the
+        // reference's `Time` only the non-PreCond stages count towards solve_ms (cuh:1311)
+        for (int a = 0; a < nactive; a++) {
+            const int sl = b->h_active[a];
+            const int im = slot_image[(size_t)sl];
+            total_ms[(size_t)im] += ms / nactive;
+            if (!stages.s[slot_stage[(size_t)sl]].precond) solve_ms[(size_t)im] += ms / nactive;
+        }
+        // ---- adopt the device's decisions -------------------------------------------------------
+        for (int a = 0; a < nactive; a++) {
+            const int sl = b->h_active[a];
+            const BatchSlot &S = b->h_slots[sl];
+            slot_iter[(size_t)sl] = S.iter;
+            slot_stage[(size_t)sl] = S.stage;
+            if (S.status == 2) {
+                const int im = slot_image[(size_t)sl];
+                if (fields) {
+                    DomainView v = view(c);
+                    const int gx = sl % GX, gy = sl / GX;
+                    const int64_t off = ((int64_t)gy * (Ny + 1)) * c->pitch + (int64_t)gx * (Nx + 1);
+                    v.x_in += off; v.code += off;
+                    v.Nx = Nx; v.Ny = Ny;
+                    launch_extract_field(s, v, c->dense.p);
+                    c->launches++;
+                    CUB(cudaMemcpyAsync(fields + (size_t)im * cells, c->dense.p, (size_t)cells * sizeof(double), cudaMemcpyDeviceToHost, s));
+                    CUB(cudaStreamSynchronize(s));
+                }
+                slot_image[(size_t)sl] = -1;
+                done_images++;
+                active_changed = true;
+            }
+        }
+    }
+    restore();
+
+    // ---- results -----------------------------------------------------------------------------------
+    std::vector<BatchOut> outs((size_t)count);
+    CUB(cudaMemcpyAsync(outs.data(), b->outs.p, (size_t)count * sizeof(BatchOut), cudaMemcpyDeviceToHost, s));
+    CUB(cudaStreamSynchronize(s));
+    for (int k = 0; k < count; k++) {
+        deff2d_result *r = results + k;
+        const BatchOut &o = outs[(size_t)k];
+        std::memset(r, 0, sizeof(*r));
+        r->n_cells = cells;
+        r->pathflag = pathflag[(size_t)k];
+        if (nphase == 2) r->porosity = accumulate_fraction((int64_t)o.below150, (int64_t)npix);     // cuh:397-405
+        else {                                                                                      // calcFracts3D, cuh:411-448 (quirk Q21)
+            int64_t ns = 0, nl = 0;
+            const double Dfin[3] = {p->Df, p->Ds, p->Dg};
+            for (int ph = 0; ph < 3; ph++) {
+                if (Dfin[ph] == p->Ds) ns += (int64_t)o.phase[ph];
+                else if (Dfin[ph] == p->Df) nl += (int64_t)o.phase[ph];
+            }
+            r->SVF = accumulate_fraction(ns, cells);
+            r->LVF = accumulate_fraction(nl, cells);
+        }
+        r->nstages = o.nstages;
+        for (int st = 0; st < o.nstages && st < DEFF2D_MAX_STAGES; st++) {
+            r->iters[st] = o.iters[st];
+            r->stage_deff_raw[st] = o.stage_deff_raw[st];
+            r->stage_D[st] = stageD[st];
+            r->total_iters += o.iters[st];
+        }
+        r->deff_raw = o.deff_raw;
+        r->conv = o.conv;
+        r->deff = o.deff_raw / p->Df;                        // cuh:2017, cuh:2370
+        r->last_df = p->Df;
+        r->solve_ms = solve_ms[(size_t)k];
+        r->total_ms = total_ms[(size_t)k];
+    }
+    return DEFF2D_OK;
+}
+
+// Returns 1 when the packed path does not cover the request (the caller then solves image by
+// image), 0 on success, a negative status on error.
 int batch_resident_solve(deff2d_ctx *c, const uint8_t *gray, int count, int W, int H, const deff2d_params *p,
                          deff2d_result *results, double *fields)
 {
-    (void)c; (void)gray; (void)count; (void)W; (void)H; (void)p; (void)results; (void)fields;
-    return 1;
+    if (count < 2 || W < 1 || H < 1 || p->amp_x < 1 || p->amp_y < 1) return 1;
+    if (p->verbose == 1) return 1;                  // keep the reference's per-image stdout order
+    if (c->slab) return 1;
+    BatchStages stages;
+    double stageD[BATCH_MAX_STAGES];
+    int nstages = 0;
+    std::memset(&stages, 0, sizeof(stages));
+    if (build_stages(p, &stages, stageD, &nstages)) return 1;
+    const int64_t Nx = (int64_t)W * p->amp_x, Ny = (int64_t)H * p->amp_y;
+    if (Nx * Ny > ((int64_t)16 << 20)) return 1;    // large images fill the machine on their own
+    // host staging (images, 3-phase masks) is bounded to ~1 GiB per chunk
+    const int64_t per_image = std::max<int64_t>((int64_t)W * H, (p->mode == DEFF2D_MODE_3PH) ? Nx * Ny : 0);
+    int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(count, ((int64_t)1 << 30) / per_image));
+    for (int k0 = 0; k0 < count; k0 += chunk) {
+        const int n = std::min(chunk, count - k0);
+        int rc = batch_chunk(c, gray + (size_t)k0 * W * H, n, W, H, p, results + k0,
+                             fields ? fields + (size_t)k0 * Nx * Ny : nullptr, stages, stageD, nstages);
+        if (rc) return rc;
+    }
+    return DEFF2D_OK;
 }
+
 }  // namespace deff2d

@@ -179,6 +179,8 @@ static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc,
     c->Nx = Nx; c->Ny = Ny; c->NxG = Nx; c->NyG = NyG;
     c->pitch = ((Nx + 2 * DEFF2D_XOFF) + 15) / 16 * 16;
     c->rows = Ny + 2;
+    c->ghost_period = Nx + 1;
+    c->tile_list = nullptr; c->tile_count = 0;
     c->own_first = own_first; c->own_rows = own_rows;
     c->nphase = nphase;
     c->CL = p->CL; c->CR = p->CR;
@@ -420,6 +422,7 @@ DEFF2D_EXPORT void deff2d_destroy(deff2d_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     slab_destroy(c);
+    batch_destroy(c);
     tma_destroy(c);
     for (int k = 0; k < 2; k++) if (c->x[k].p) cudaFree(c->x[k].p);
     if (c->code.p) cudaFree(c->code.p);
@@ -657,6 +660,13 @@ DEFF2D_EXPORT int deff2d_set_kernel(deff2d_ctx *c, int kernel, int tblock)
     if (kernel >= 3) kernel = 2;
     c->kernel = kernel;
     c->tblock = tblock > 0 ? tblock : 1;
+    return DEFF2D_OK;
+}
+
+DEFF2D_EXPORT int deff2d_set_batch_slots(deff2d_ctx *c, int max_slots)
+{
+    if (!c || max_slots < 0) return DEFF2D_ERR_ARG;
+    c->batch_max_slots = max_slots;
     return DEFF2D_OK;
 }
 

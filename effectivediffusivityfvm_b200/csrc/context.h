@@ -55,6 +55,14 @@ struct deff2d_ctx {
     // TMA tiled sweep state (sweep_tma.cu)
     bool tma_ready = false;
     void *tma = nullptr;
+    int64_t ghost_period = 0;        // every ghost_period-th column (from -1) is a Dirichlet ghost column: Nx + 1
+                                     // for one domain, image width + 1 in a packed batch
+    const uint32_t *tile_list = nullptr;   // device: ty << 16 | tx of the tiles to sweep (NULL: the whole tile grid)
+    int tile_count = 0;
+
+    // packed-batch state (batch.cu)
+    void *batch = nullptr;
+    int batch_max_slots = 0;         // 0: library default
 
     // multi-GPU slab state (slab.cu)
     void *slab = nullptr;
@@ -72,11 +80,15 @@ int solve_image_impl(deff2d_ctx *c, const uint8_t *gray, int W, int H, const def
 // sweep_tma.cu: enqueue up to min(n, tblock) sweeps with the TMA tiled kernel; *done = sweeps
 // enqueued (0: this domain is not eligible, caller falls back to the streaming kernel).
 int launch_sweep_tma(deff2d_ctx *c, int64_t n, int64_t *done);
+// one pass of depth T over an explicit tile list on `stream`, without flipping c->cur
+int tma_pass(deff2d_ctx *c, int T, const uint32_t *list, int count, cudaStream_t stream);
+void tma_tile_geometry(const deff2d_ctx *c, int T, int *ow, int *oh);
 void tma_destroy(deff2d_ctx *c);
 
 // slab.cu
 int slab_allreduce_q(deff2d_ctx *c);     // no-op unless the context is part of a slab group
 void slab_destroy(deff2d_ctx *c);
+void batch_destroy(deff2d_ctx *c);
 
 // batch.cu: returns 1 when the resident small-image kernel does not cover the request
 int batch_resident_solve(deff2d_ctx *c, const uint8_t *gray, int count, int W, int H,

@@ -171,8 +171,8 @@ k_sweep_simple(DomainView d, const int *__restrict__ stop)
         const unsigned cW = cc[-1] & 3u, c0 = cc[0], c1 = cc[1], cE = cc[2] & 3u;
         const unsigned n0 = cc[-d.pitch] & 3u, n1 = cc[-d.pitch + 1] & 3u;
         const unsigned s0 = cc[d.pitch] & 3u, s1 = cc[d.pitch + 1] & 3u;
-        const unsigned idx0 = (c0 & 3u) | (cW << 2) | ((c1 & 3u) << 4) | (s0 << 6) | (n0 << 8) | ((c0 & 4u) << 8);
-        const unsigned idx1 = (c1 & 3u) | ((c0 & 3u) << 2) | (cE << 4) | (s1 << 6) | (n1 << 8) | ((c1 & 4u) << 8);
+        const unsigned idx0 = (c0 & 3u) | (cW << 2) | ((c1 & 3u) << 4) | (s0 << 6) | (n0 << 8) | ((c0 & 4u) << 8) | ((c0 >> 3) << 11);
+        const unsigned idx1 = (c1 & 3u) | ((c0 & 3u) << 2) | (cE << 4) | (s1 << 6) | (n1 << 8) | ((c1 & 4u) << 8) | ((c1 >> 3) << 11);
         double w0[4], w1[4];
         lut_load(d.lut, idx0, w0);
         lut_load(d.lut, idx1, w1);
@@ -302,7 +302,8 @@ __device__ __forceinline__ unsigned cell_index(const uint8_t *__restrict__ code,
 {
     const unsigned c = code[base];
     return (c & 3u) | ((code[base - 1] & 3u) << 2) | ((code[base + 1] & 3u) << 4) |
-           ((code[base + pitch] & 3u) << 6) | ((code[base - pitch] & 3u) << 8) | ((c & 4u) << 8);
+           ((code[base + pitch] & 3u) << 6) | ((code[base - pitch] & 3u) << 8) | ((c & 4u) << 8) |
+           ((c >> 3) << 11);       // bits 3-7: continuation stage (packed batches, batch.cu)
 }
 
 __global__ void __launch_bounds__(256) k_extract_field(DomainView d, double *__restrict__ dense)

@@ -111,7 +111,8 @@ struct Cfg {
 template <class C>
 __global__ void __launch_bounds__(C::NT, 1)
 k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, double om,
-            int Nx, int tiles_x, int ntiles, const int *__restrict__ stop)
+            int ghost_period, int tiles_x, int ntiles, const uint32_t *__restrict__ tile_list,
+            const int *__restrict__ stop)
 {
     constexpr int T = C::T, TE = C::TE, PX = C::PX, PY = C::PY, TW = C::TW, TH = C::TH, OW = C::OW, OH = C::OH;
     constexpr int PW = C::PLANE_W, CW = C::CW;
@@ -125,6 +126,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     double *const OUT = reinterpret_cast<double *>(smem + C::OFF_OUT);
     uint8_t *const CODE0 = smem + C::OFF_CODE;
     uint64_t *const bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+    int *const org = reinterpret_cast<int *>(smem + C::OFF_BAR + 16);   // output-box origin of the tile in buffer b: org[2b], org[2b+1]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wx = warp % C::NWX, wy = warp / C::NWX;
@@ -136,13 +138,18 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     const CUtensorMap *map_out = &maps.x_store[src ^ 1];
     constexpr uint32_t TX_BYTES = (uint32_t)(C::IN_BYTES + (size_t)CW * TH);
 
+    // interior-coordinate origin of the OUTPUT box of tile t: the whole tile grid, or -- packed
+    // batches and slab boundary/interior splits -- the entries of an explicit tile list
     auto tile_origin = [&](int t, int &ox, int &oy) {
-        const int ty = t / tiles_x, tx = t - ty * tiles_x;
-        ox = tx * OW; oy = ty * OH;          // interior-coordinate origin of the OUTPUT box
+        int tx, ty;
+        if (tile_list) { const uint32_t v = __ldg(tile_list + t); tx = (int)(v & 0xffffu); ty = (int)(v >> 16); }
+        else { ty = t / tiles_x; tx = t - ty * tiles_x; }
+        ox = tx * OW; oy = ty * OH;
     };
     auto issue_load = [&](int t, int b) {
         int ox, oy;
         tile_origin(t, ox, oy);
+        org[2 * b] = ox; org[2 * b + 1] = oy;            // released to the consumers by the arrive below
         mbar_expect_tx(&bar[b], TX_BYTES);
         // padded coordinates of the input box: interior (ox-TE, oy-T) -> (+XOFF, +1); even
         const int xs = ox - TE + DEFF2D_XOFF;
@@ -178,9 +185,8 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         double x[PY][PX];
         double w[PY][PX][4];
         double omc[PX];
+        const int ox = org[2 * b], oy = org[2 * b + 1];
         {
-            int ox, oy;
-            tile_origin(tile, ox, oy);
             const double *in = IN0 + b * C::CELLS;
             const uint8_t *cd = CODE0 + b * C::CODE_BYTES + ((ox - TE + DEFF2D_XOFF) & 15);
 #pragma unroll
@@ -210,12 +216,13 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
                 }
             }
             {
-                // a Dirichlet ghost column (global column -1 or Nx) keeps its value: its weights
-                // are 0 (LUT, p == 3) and its (1-omega) factor is 1
+                // a Dirichlet ghost column (column -1 or Nx of the domain; in a packed batch every
+                // (Nx+1)-th column separates two images) keeps its value: its weights are 0
+                // (LUT, p == 3) and its (1-omega) factor is 1
 #pragma unroll
                 for (int px = 0; px < PX; px++) {
                     const int jg = ox - TE + c0 + px;
-                    omc[px] = (jg == -1 || jg == Nx) ? 1.0 : om;
+                    omc[px] = ((jg + 1) % ghost_period == 0) ? 1.0 : om;
                 }
             }
             unsigned idx[PY][PX];
@@ -226,7 +233,8 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
                 for (int px = 0; px < PX; px++) {
                     const unsigned c = cc[py + 1][px + 1];
                     idx[py][px] = (c & 3u) | ((cc[py + 1][px] & 3u) << 2) | ((cc[py + 1][px + 2] & 3u) << 4) |
-                                  ((cc[py + 2][px + 1] & 3u) << 6) | ((cc[py][px + 1] & 3u) << 8) | ((c & 4u) << 8);
+                                  ((cc[py + 2][px + 1] & 3u) << 6) | ((cc[py][px + 1] & 3u) << 8) | ((c & 4u) << 8) |
+                                  ((c >> 3) << 11);          // bits 3-7: continuation stage of the image (packed batches)
                     uniform = uniform && (idx[py][px] == idx[0][0]);
                 }
             // Most patches lie inside one phase (every cell has the same neighbourhood index):
@@ -346,8 +354,6 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         fence_proxy_async();                   // generic-proxy writes -> visible to the TMA engine
         __syncthreads();
         if (tid == 0) {
-            int ox, oy;
-            tile_origin(tile, ox, oy);
             tma_store_2d(map_out, ox, oy, OUT);
             tma_commit();
         }
@@ -402,7 +408,7 @@ template <int T> struct Family<T, 1> { using type = Cfg<T, 4, 4, 1, 8>; };
 template <int T> struct Family<T, 2> { using type = Cfg<T, 2, 4, 2, 8>; };
 
 template <int T, int F>
-static int launch_T(deff2d_ctx *c, TmaState *ts, int src)
+static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, int count, cudaStream_t stream)
 {
     using C = typename Family<T, F>::type;
     auto kern = k_sweep_tma<C>;
@@ -411,10 +417,12 @@ static int launch_T(deff2d_ctx *c, TmaState *ts, int src)
         if (e != cudaSuccess) { set_error(c, "cudaFuncSetAttribute(smem %zu) failed: %s", C::SMEM, cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
         ts->attr_set[F][T] = true;
     }
-    const int ntiles = ts->tiles_x * ts->tiles_y;
+    const int ntiles = list ? count : ts->tiles_x * ts->tiles_y;
+    if (ntiles < 1) return DEFF2D_OK;
     int grid = c->prop.multiProcessorCount;
     if (grid > ntiles) grid = ntiles;
-    kern<<<grid, C::NT, C::SMEM, c->stream>>>(ts->maps, src, c->lut.p, 1.0 - c->omega, (int)c->Nx, ts->tiles_x, ntiles, nullptr);
+    kern<<<grid, C::NT, C::SMEM, stream>>>(ts->maps, src, c->lut.p, 1.0 - c->omega, (int)c->ghost_period, ts->tiles_x, ntiles,
+                                           list, nullptr);
     return DEFF2D_OK;
 }
 
@@ -446,9 +454,8 @@ static int prepare_T(deff2d_ctx *c, TmaState *ts)
     return DEFF2D_OK;
 }
 
-int launch_sweep_tma(deff2d_ctx *c, int64_t n, int64_t *done)
+static TmaState *tma_state(deff2d_ctx *c)
 {
-    *done = 0;
     TmaState *ts = static_cast<TmaState *>(c->tma);
     if (!ts) {
         ts = new TmaState();
@@ -462,31 +469,57 @@ int launch_sweep_tma(deff2d_ctx *c, int64_t n, int64_t *done)
         } else ts->encode = (EncodeTiledFn)fn;
         cudaDeviceGetAttribute(&ts->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
     }
+    return ts;
+}
+
+// Output-box size of the tiles of temporal depth T in the context's tile family.
+void tma_tile_geometry(const deff2d_ctx *c, int T, int *ow, int *oh)
+{
+    const int te = (T + 1) & ~1;
+    int tw = 128, th = 32;                  // all three families are 128 x 32 cells (Family<> below)
+    (void)c;
+    *ow = tw - 2 * te;
+    *oh = th - 2 * T;
+}
+
+// One pass of depth T (1..8) from x[c->cur] into x[c->cur ^ 1] over the tiles of `list` (NULL: the
+// whole tile grid) on `stream`; does not flip c->cur.
+int tma_pass(deff2d_ctx *c, int T, const uint32_t *list, int count, cudaStream_t stream)
+{
+    TmaState *ts = tma_state(c);
     if (!ts->encode) { set_error(c, "cuTensorMapEncodeTiled is not available from this driver"); return DEFF2D_ERR_CUDA; }
-    int T = (int)std::min<int64_t>(n, c->tblock);
-    if (T < 1) T = 1;
-    // halo exchange of slab mode limits the depth to the halo rows held
+    if (T < 1 || T > 8) { set_error(c, "temporal depth %d out of range", T); return DEFF2D_ERR_ARG; }
     int rc = DEFF2D_OK;
-    if (T > 8) T = 8;
     const int fam = c->tile_family;
-#define DEFF2D_CASE(TT)                                                         \
-    case TT:                                                                    \
-        if (fam == 1) {                                                         \
-            if ((rc = prepare_T<TT, 1>(c, ts))) return rc;                      \
-            if ((rc = launch_T<TT, 1>(c, ts, c->cur))) return rc;               \
-        } else if (fam == 2) {                                                  \
-            if ((rc = prepare_T<TT, 2>(c, ts))) return rc;                      \
-            if ((rc = launch_T<TT, 2>(c, ts, c->cur))) return rc;               \
-        } else {                                                                \
-            if ((rc = prepare_T<TT, 0>(c, ts))) return rc;                      \
-            if ((rc = launch_T<TT, 0>(c, ts, c->cur))) return rc;               \
-        }                                                                       \
+#define DEFF2D_CASE(TT)                                                                   \
+    case TT:                                                                              \
+        if (fam == 1) {                                                                   \
+            if ((rc = prepare_T<TT, 1>(c, ts))) return rc;                                \
+            if ((rc = launch_T<TT, 1>(c, ts, c->cur, list, count, stream))) return rc;    \
+        } else if (fam == 2) {                                                            \
+            if ((rc = prepare_T<TT, 2>(c, ts))) return rc;                                \
+            if ((rc = launch_T<TT, 2>(c, ts, c->cur, list, count, stream))) return rc;    \
+        } else {                                                                          \
+            if ((rc = prepare_T<TT, 0>(c, ts))) return rc;                                \
+            if ((rc = launch_T<TT, 0>(c, ts, c->cur, list, count, stream))) return rc;    \
+        }                                                                                 \
         break;
     switch (T) {
         DEFF2D_CASE(1) DEFF2D_CASE(2) DEFF2D_CASE(3) DEFF2D_CASE(4) DEFF2D_CASE(5) DEFF2D_CASE(6) DEFF2D_CASE(7) DEFF2D_CASE(8)
     }
 #undef DEFF2D_CASE
     c->launches++;
+    return DEFF2D_OK;
+}
+
+int launch_sweep_tma(deff2d_ctx *c, int64_t n, int64_t *done)
+{
+    *done = 0;
+    int T = (int)std::min<int64_t>(n, c->tblock);
+    if (T < 1) T = 1;
+    if (T > 8) T = 8;
+    int rc = tma_pass(c, T, c->tile_list, c->tile_count, c->stream);
+    if (rc) return rc;
     c->cur ^= 1;
     *done = T;
     return DEFF2D_OK;

@@ -151,6 +151,10 @@ int deff2d_sync(deff2d_ctx *ctx);
 /* Select the sweep kernel: 0 = library default, 1 = plain streaming kernel (one sweep per
  * HBM pass), 2 = TMA-staged tiled kernel with `tblock` sweeps per pass. */
 int deff2d_set_kernel(deff2d_ctx *ctx, int kernel, int tblock);
+/* Packed batch mode (deff2d_solve_batch): at most `max_slots` images resident at a time
+ * (0 = library default, sized from the image size); finished images are replaced from the
+ * queue.  Tuning / test hook. */
+int deff2d_set_batch_slots(deff2d_ctx *ctx, int max_slots);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t deff2d_kernel_launches(const deff2d_ctx *ctx);
 /* The CUDA stream (cudaStream_t as an opaque pointer) all work of the context is enqueued on. */

@@ -240,6 +240,71 @@ def test_batch_equals_serial(ctx):
         check_against_oracle(got[k], ref)
 
 
+def _same_result(a, b):
+    """Packed and single-image solves use the same kernels and reduction order: bit-identical."""
+    for k in ("iters", "nstages", "pathflag", "porosity", "SVF", "LVF", "total_iters", "n_cells", "stage_D"):
+        assert a[k] == b[k], (k, a[k], b[k])
+    for k in ("deff", "deff_raw", "conv"):
+        assert a[k] == b[k] or (np.isnan(a[k]) and np.isnan(b[k])), (k, a[k], b[k])
+    assert np.array_equal(np.array(a["stage_deff_raw"]), np.array(b["stage_deff_raw"]), equal_nan=True)
+
+
+@pytest.mark.parametrize("slots", [0, 3])
+def test_packed_batch_2phase_matches_single_image_and_oracle(ctx, slots):
+    """K5: images of different porosity (different sweep counts) packed into one stack; with
+    slots=3 finished images are replaced from the queue while the others keep iterating."""
+    imgs = np.stack([blobs(200 + k, (40, 56), fracs=(0.45 + 0.04 * k,)) for k in range(9)])
+    p = E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH, check_every=500, max_iter=9000, tol=1e-3)
+    ctx.set_batch_slots(slots)
+    try:
+        got = ctx.solve_batch(imgs, p, want_fields=True)
+    finally:
+        ctx.set_batch_slots(0)
+    assert len({tuple(g["iters"]) for g in got}) > 1          # the images really stop at different checks
+    for k in range(len(imgs)):
+        one = ctx.solve_image(imgs[k], p, want_field=True)
+        _same_result(got[k], one)
+        assert np.array_equal(got[k]["field"], one["field"], equal_nan=True)
+        ref = O.solve_image(imgs[k], O.make_opts(Ds=1e-3, Df=1.0, nphase=2, check_every=500, max_iter=9000, tol=1e-3), O.MODE_2PH_BATCH)
+        check_against_oracle(got[k], ref)
+
+
+@pytest.mark.parametrize("slots", [0, 2])
+def test_packed_batch_3phase_stages_match_single_image(ctx, slots):
+    """Every packed image walks its own pre-conditioning stages (cuh:1492-1597): images in
+    different stages share the launches, the stage lives in the cell code."""
+    imgs = np.stack([blobs(300 + k, (36, 44), levels=(0, 150, 255), fracs=(0.25 + 0.03 * k, 0.4)) for k in range(6)])
+    p = E.default_params(Ds=0.0, Df=1.0, Dg=300.0, mode=E.MODE_3PH, check_every=300, max_iter=20000, amp_x=2, amp_y=1, tol=1e-4)
+    ctx.set_batch_slots(slots)
+    try:
+        got = ctx.solve_batch(imgs, p, want_fields=True)
+    finally:
+        ctx.set_batch_slots(0)
+    for k in range(len(imgs)):
+        assert got[k]["nstages"] == 3 and got[k]["stage_D"] == [10.0, 100.0, 300.0]
+        one = ctx.solve_image(imgs[k], p, want_field=True)
+        _same_result(got[k], one)
+        assert np.array_equal(got[k]["field"], one["field"], equal_nan=True)
+    ref = O.solve_image(imgs[2], O.make_opts(Ds=0.0, Df=1.0, Dg=300.0, check_every=300, max_iter=20000, ampx=2, ampy=1, tol=1e-4), O.MODE_3PH)
+    check_against_oracle(got[2], ref)
+
+
+def test_packed_batch_quirks(ctx, golden_images):
+    """Q13 (Ds = 0 in 2-phase: NaN after the first check) and MaxIter exits inside a packed batch."""
+    img = golden_images["00000"]
+    imgs = np.stack([img, img[::-1].copy(), img[:, ::-1].copy()])
+    got = ctx.solve_batch(imgs, E.default_params(Ds=0.0, Df=1.0, mode=E.MODE_2PH_BATCH))
+    for g in got:
+        assert g["iters"] == [1] and np.isnan(g["deff"]) and np.isnan(g["conv"])
+    p = E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH, max_iter=12345, tol=1e-12)
+    got = ctx.solve_batch(imgs, p, want_fields=True)
+    for k in range(3):
+        one = ctx.solve_image(imgs[k], p, want_field=True)
+        assert got[k]["iters"] == [12345]
+        _same_result(got[k], one)
+        assert np.array_equal(got[k]["field"], one["field"], equal_nan=True)
+
+
 def test_drop_in_program(ctx, tmp_path, golden_drivers):
     """input.txt in, CSV + CMAP out, through deff2d_run_input_file; compared with the files the
     reference program wrote for the same inputs (Time column excluded)."""
