@@ -7,9 +7,9 @@ interface.  There is no CPU fallback: the API raises if the CUDA library is not 
 device is present.
 """
 from ._lib import (LIB_PATH, MODE_2PH_BATCH, MODE_2PH_SINGLE, MODE_3PH, Input, Params, Result)
-from .api import (Deff2D, Deff2DError, build_tables, default_params, floodfill, load_image, nccl_unique_id,
-                  read_input_file)
+from .api import (Deff2D, Deff2DError, batch_plan, batch_tile_list, build_tables, default_params, floodfill, load_image,
+                  nccl_unique_id, read_input_file, slab_split_tiles, tile_geometry)
 
 __all__ = ["Deff2D", "Deff2DError", "Params", "Result", "Input", "default_params", "read_input_file",
-           "build_tables", "floodfill", "load_image", "nccl_unique_id", "MODE_2PH_SINGLE", "MODE_2PH_BATCH",
+           "build_tables", "floodfill", "tile_geometry", "slab_split_tiles", "batch_plan", "batch_tile_list", "load_image", "nccl_unique_id", "MODE_2PH_SINGLE", "MODE_2PH_BATCH",
            "MODE_3PH", "LIB_PATH"]

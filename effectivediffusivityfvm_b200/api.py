@@ -61,6 +61,50 @@ def floodfill(grid):
     return g, pf
 
 
+def tile_geometry(T):
+    """(ow, oh, tw, th): output box and input tile of a tiled pass of depth T."""
+    v = [C.c_int(0) for _ in range(4)]
+    rc = _lib.lib().deff2d_tile_geometry(int(T), *[C.byref(x) for x in v])
+    if rc:
+        raise Deff2DError("tile_geometry failed (%d)" % rc)
+    return tuple(x.value for x in v)
+
+
+def slab_split_tiles(Nx, Ny, above, own, below, halo, T):
+    """(boundary, interior) tile ids (ty << 16 | tx) of one slab, as csrc/slab.cu schedules them."""
+    cap = 1 << 20
+    b = np.zeros(cap, dtype=np.uint32)
+    i = np.zeros(cap, dtype=np.uint32)
+    nb = C.c_int(0)
+    u32p = C.POINTER(C.c_uint32)
+    ni = _lib.lib().deff2d_slab_split_tiles(Nx, Ny, above, own, below, halo, T, b.ctypes.data_as(u32p), C.byref(nb),
+                                            i.ctypes.data_as(u32p), cap)
+    if ni < 0:
+        raise Deff2DError("slab_split_tiles failed (%d)" % ni)
+    return b[:nb.value].copy(), i[:ni].copy()
+
+
+def batch_plan(Nx, Ny, count, limit=0):
+    """(GX, GY) slot grid of the packed batch mode."""
+    gx, gy = C.c_int(0), C.c_int(0)
+    rc = _lib.lib().deff2d_batch_plan(Nx, Ny, count, limit, C.byref(gx), C.byref(gy))
+    if rc:
+        raise Deff2DError("batch_plan failed (%d)" % rc)
+    return gx.value, gy.value
+
+
+def batch_tile_list(Nx, Ny, GX, GY, active, T):
+    """Tile ids whose output box touches an active slot of the packed stack."""
+    cap = 1 << 20
+    t = np.zeros(cap, dtype=np.uint32)
+    a = np.ascontiguousarray(active, dtype=np.int32)
+    n = _lib.lib().deff2d_batch_tile_list(Nx, Ny, GX, GY, a.ctypes.data_as(C.POINTER(C.c_int)), len(a), T,
+                                          t.ctypes.data_as(C.POINTER(C.c_uint32)), cap)
+    if n < 0:
+        raise Deff2DError("batch_tile_list failed (%d)" % n)
+    return t[:n].copy()
+
+
 def load_image(path):
     """Decode an image file to (H, W) uint8 gray + the file's channel count (cuh:342)."""
     L = _lib.lib()

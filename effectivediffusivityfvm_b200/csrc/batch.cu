@@ -424,6 +424,8 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     // ---- resident stack -----------------------------------------------------------------------
     CUB(cudaSetDevice(c->device));
     c->loaded = false;
+    c->slab_domain = false;
+    c->halo_above = c->halo_below = 0;
     c->Nx = (int64_t)GX * (Nx + 1) - 1;
     c->Ny = (int64_t)GY * (Ny + 1) - 1;
     c->NxG = Nx; c->NyG = Ny;
@@ -665,7 +667,6 @@ int batch_resident_solve(deff2d_ctx *c, const uint8_t *gray, int count, int W, i
 {
     if (count < 2 || W < 1 || H < 1 || p->amp_x < 1 || p->amp_y < 1) return 1;
     if (p->verbose == 1) return 1;                  // keep the reference's per-image stdout order
-    if (c->slab) return 1;
     BatchStages stages;
     double stageD[BATCH_MAX_STAGES];
     int nstages = 0;
@@ -686,3 +687,27 @@ int batch_resident_solve(deff2d_ctx *c, const uint8_t *gray, int count, int W, i
 }
 
 }  // namespace deff2d
+
+DEFF2D_EXPORT int deff2d_batch_plan(int64_t Nx, int64_t Ny, int count, int limit, int *GX, int *GY)
+{
+    if (Nx < 1 || Ny < 1 || count < 1 || !GX || !GY) return DEFF2D_ERR_ARG;
+    deff2d::batch_plan(Nx, Ny, count, limit, GX, GY);
+    return DEFF2D_OK;
+}
+
+DEFF2D_EXPORT int deff2d_batch_tile_list(int64_t Nx, int64_t Ny, int GX, int GY, const int *active, int nactive, int T,
+                                         uint32_t *tiles, int cap)
+{
+    if (Nx < 1 || Ny < 1 || GX < 1 || GY < 1 || T < 1 || T > 8 || nactive < 0 || (nactive && !active)) return DEFF2D_ERR_ARG;
+    int ow, oh;
+    deff2d::tma_tile_geometry(nullptr, T, &ow, &oh);
+    const int64_t NxS = (int64_t)GX * (Nx + 1) - 1, NyS = (int64_t)GY * (Ny + 1) - 1;
+    const int tx = (int)((NxS + ow - 1) / ow), ty = (int)((NyS + oh - 1) / oh);
+    std::vector<uint8_t> mark;
+    std::vector<uint32_t> out;
+    deff2d::batch_tile_list(Nx, Ny, GX, active, nactive, ow, oh, tx, ty, mark, out);
+    if ((int)out.size() > cap) return DEFF2D_ERR_ARG;
+    if (tiles) std::memcpy(tiles, out.data(), out.size() * sizeof(uint32_t));
+    return (int)out.size();
+}
+

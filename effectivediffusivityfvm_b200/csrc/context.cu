@@ -91,6 +91,7 @@ static int upload_tables(deff2d_ctx *c)
 // One sweep (or, with the tiled kernel, up to tblock sweeps) -- enqueue only.
 static int enqueue_sweeps(deff2d_ctx *c, int64_t n)
 {
+    if (c->slab && c->slab_domain) return slab_enqueue_sweeps(c, n);
     while (n > 0) {
         int64_t done = 0;
         // kernel 0 (default): the TMA tiled kernel (4x4 patches, 4 sweeps per HBM pass -- the
@@ -307,6 +308,8 @@ int solve_image_impl(deff2d_ctx *c, const uint8_t *gray, int W, int H, const def
     }
     const int nphase = (p->mode == DEFF2D_MODE_3PH) ? 3 : 2;
     const int64_t Ny = (int64_t)H * p->amp_y;
+    c->halo_above = c->halo_below = 0; c->grow0 = 0;
+    c->slab_domain = false;
     int rc = domain_load_impl(c, gray, W, H, nphase, p, 0, 0, Ny, Ny, 0, Ny, nullptr, true);
     if (rc) return rc;
     res->n_cells = c->NxG * c->NyG;
@@ -475,6 +478,8 @@ DEFF2D_EXPORT int deff2d_domain_load(deff2d_ctx *c, const uint8_t *gray, int W, 
 {
     if (!c || !p) return DEFF2D_ERR_ARG;
     const int64_t Ny = (int64_t)H * p->amp_y;
+    c->halo_above = c->halo_below = 0; c->grow0 = 0;
+    c->slab_domain = false;
     return domain_load_impl(c, gray, W, H, nphase, p, 0, 0, Ny, Ny, 0, Ny, nullptr, true);
 }
 
@@ -496,6 +501,7 @@ DEFF2D_EXPORT int deff2d_domain_load_slab(deff2d_ctx *c, const uint8_t *gray, in
     const int64_t NyLocal = above + own_rows + below;
     const int Hsrc = (int)(NyLocal / p->amp_y);
     c->halo_above = above; c->halo_below = below; c->grow0 = row0 - above;
+    c->slab_domain = true;
     return domain_load_impl(c, gray, W, Hsrc, nphase, p, row0 - above, (row0 - above) / p->amp_y, NyLocal,
                             NyGlobal, above, own_rows, pinned, false);
 }

@@ -64,8 +64,11 @@ struct deff2d_ctx {
     void *batch = nullptr;
     int batch_max_slots = 0;         // 0: library default
 
+    int grid_limit = 0;              // > 0: cap on the CTAs of a tiled pass (slab mode leaves SMs to NCCL)
+
     // multi-GPU slab state (slab.cu)
     void *slab = nullptr;
+    bool slab_domain = false;        // the resident domain is one slab of a decomposed global domain
 };
 
 namespace deff2d {
@@ -86,7 +89,8 @@ void tma_tile_geometry(const deff2d_ctx *c, int T, int *ow, int *oh);
 void tma_destroy(deff2d_ctx *c);
 
 // slab.cu
-int slab_allreduce_q(deff2d_ctx *c);     // no-op unless the context is part of a slab group
+int slab_allreduce_q(deff2d_ctx *c);     // no-op unless the resident domain is a slab of a multi-rank group
+int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n);
 void slab_destroy(deff2d_ctx *c);
 void batch_destroy(deff2d_ctx *c);
 

@@ -1,17 +1,318 @@
-// slab.cu -- multi-GPU row-slab decomposition (placeholder: single-GPU contexts only).
+// slab.cu -- multi-GPU row-slab decomposition of one large domain over NCCL (K6).
+//
+// The reference is single-GPU (cudaSetDevice(0), Deff2D.cuh:908); a 5-point stencil shards
+// naturally into horizontal slabs.  One process (or thread) per GPU owns a contiguous band of
+// rows plus H halo rows of each neighbour (deff2d_domain_load_slab).  One temporally blocked
+// pass of depth T <= H (sweep_tma.cu) leaves the own rows exact and the halo rows stale, so
+// after every pass the H boundary rows travel to the neighbours:
+//
+//     main stream:  [pass over BOUNDARY tiles] --evA--> [pass over INTERIOR tiles] --wait evC--> next pass
+//     comm stream:            wait evA -> ncclGroup{Send/Recv up, Send/Recv down} -> evC
+//
+// Rows are contiguous (pitch doubles each), so the halo is sent straight from the iterate
+// buffer: no pack kernel.  The interior launch leaves a few SMs free so that the NCCL
+// send/recv kernel can run beside it.  Once per check the two boundary-flux partial sums are
+// all-reduced (ncclAllReduce, 2 doubles) and every rank applies the identical stop rule
+// (cuh:1263-1276 via k_check).
+//
+// NCCL is bound at run time (dlopen of libnccl.so.2): a process that already loaded NCCL (e.g.
+// through torch) shares that copy, and single-GPU users need no NCCL at all.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
 #include "context.h"
 
 namespace deff2d {
-int slab_allreduce_q(deff2d_ctx *c) { (void)c; return DEFF2D_OK; }
-void slab_destroy(deff2d_ctx *c) { (void)c; }
+
+struct NcclApi {
+    void *handle = nullptr;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclSend) Send = nullptr;
+    decltype(&ncclRecv) Recv = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclAllReduce) AllReduce = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    std::string error;
+};
+
+static NcclApi *nccl_api()
+{
+    static NcclApi api;
+    if (api.handle || !api.error.empty()) return &api;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) { api.error = std::string("cannot load libnccl.so.2: ") + dlerror(); return &api; }
+    bool ok = true;
+    auto sym = [&](const char *name) { void *p = dlsym(api.handle, name); if (!p) ok = false; return p; };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.Send = (decltype(api.Send))sym("ncclSend");
+    api.Recv = (decltype(api.Recv))sym("ncclRecv");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) { api.error = "libnccl.so.2 lacks a required symbol"; api.handle = nullptr; }
+    return &api;
+}
+
+struct SlabState {
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    cudaEvent_t evA = nullptr, evC = nullptr;
+    // per pass depth T (1..8): boundary and interior tile lists (device), built lazily per domain
+    DevBuf<uint32_t> tiles;
+    size_t off_b[9] = {0}, off_i[9] = {0};
+    int cnt_b[9] = {0}, cnt_i[9] = {0};
+    bool lists_ready = false;
+    int64_t key_Nx = 0, key_Ny = 0, key_above = -1, key_below = -1, key_own = -1;
+    int key_family = -1;
+    int reserve_sms = 4;          // SMs the interior launch leaves to the NCCL kernel
+};
+
+#define NCCLCHECK(call)                                                                      \
+    do {                                                                                     \
+        ncclResult_t r_ = (call);                                                            \
+        if (r_ != ncclSuccess) {                                                             \
+            set_error(c, "%s failed: %s", #call, api->GetErrorString(r_));                   \
+            return DEFF2D_ERR_NCCL;                                                          \
+        }                                                                                    \
+    } while (0)
+
+#define CUS(call)                                                                            \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            set_error(c, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return DEFF2D_ERR_CUDA;                                                          \
+        }                                                                                    \
+    } while (0)
+
+// Split the tile grid of output boxes ow x oh into the tiles that write a halo row or one of
+// the `H` own rows next to a neighbour (BOUNDARY: must finish before the exchange) and the rest.
+void slab_split_tiles(int64_t Nx, int64_t Ny, int64_t above, int64_t own, int64_t below, int64_t H, int ow, int oh,
+                      std::vector<uint32_t> &boundary, std::vector<uint32_t> &interior)
+{
+    const int tiles_x = (int)((Nx + ow - 1) / ow), tiles_y = (int)((Ny + oh - 1) / oh);
+    boundary.clear();
+    interior.clear();
+    const int64_t top_end = above > 0 ? above + H : 0;                       // rows [0, top_end)
+    const int64_t bot_begin = below > 0 ? above + own - H : Ny;              // rows [bot_begin, Ny)
+    for (int ty = 0; ty < tiles_y; ty++) {
+        const int64_t r0 = (int64_t)ty * oh, r1 = std::min<int64_t>(r0 + oh, Ny);
+        const bool b = (r0 < top_end) || (r1 > bot_begin);
+        for (int tx = 0; tx < tiles_x; tx++) (b ? boundary : interior).push_back(((uint32_t)ty << 16) | (uint32_t)tx);
+    }
+}
+
+static int build_lists(deff2d_ctx *c, SlabState *s)
+{
+    const bool same = s->lists_ready && s->key_Nx == c->Nx && s->key_Ny == c->Ny && s->key_above == c->halo_above &&
+                      s->key_below == c->halo_below && s->key_own == c->own_rows && s->key_family == c->tile_family;
+    if (same) return DEFF2D_OK;
+    const int64_t H = std::max(c->halo_above, c->halo_below);
+    std::vector<uint32_t> all, bd, in;
+    for (int T = 1; T <= 8; T++) {
+        int ow, oh;
+        tma_tile_geometry(c, T, &ow, &oh);
+        slab_split_tiles(c->Nx, c->Ny, c->halo_above, c->own_rows, c->halo_below, H, ow, oh, bd, in);
+        s->off_b[T] = all.size(); s->cnt_b[T] = (int)bd.size();
+        all.insert(all.end(), bd.begin(), bd.end());
+        s->off_i[T] = all.size(); s->cnt_i[T] = (int)in.size();
+        all.insert(all.end(), in.begin(), in.end());
+    }
+    if (s->tiles.cap < all.size() || !s->tiles.p) {
+        if (s->tiles.p) cudaFree(s->tiles.p);
+        s->tiles.p = nullptr;
+        CUS(cudaMalloc((void **)&s->tiles.p, all.size() * sizeof(uint32_t)));
+        s->tiles.cap = all.size();
+    }
+    CUS(cudaMemcpyAsync(s->tiles.p, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CUS(cudaStreamSynchronize(c->stream));
+    s->key_Nx = c->Nx; s->key_Ny = c->Ny; s->key_above = c->halo_above; s->key_below = c->halo_below;
+    s->key_own = c->own_rows; s->key_family = c->tile_family;
+    s->lists_ready = true;
+    return DEFF2D_OK;
+}
+
+// n sweeps on a slab: passes of depth T = min(tblock, halo rows) with a halo exchange after
+// each.  Enqueue only.
+int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
+{
+    SlabState *s = static_cast<SlabState *>(c->slab);
+    NcclApi *api = nccl_api();
+    if (!s || !s->comm) { set_error(c, "slab sweeps before deff2d_nccl_init"); return DEFF2D_ERR_STATE; }
+    const int64_t H = std::max(c->halo_above, c->halo_below);
+    if (s->nranks > 1 && (H < 1 || c->own_rows < H)) { set_error(c, "slab needs halo rows >= 1 and own rows >= halo rows"); return DEFF2D_ERR_STATE; }
+    const int old_family = c->tile_family;
+    c->tile_family = 1;
+    int rc = build_lists(c, s);
+    if (rc) { c->tile_family = old_family; return rc; }
+    int Tmax = c->tblock > 0 ? c->tblock : 4;
+    if (c->kernel == 0) Tmax = 4;
+    if (Tmax > 8) Tmax = 8;
+    if (s->nranks > 1 && Tmax > H) Tmax = (int)H;
+    const bool up = c->halo_above > 0, down = c->halo_below > 0;
+    const size_t count = (size_t)H * (size_t)c->pitch;            // doubles per halo block (whole padded rows)
+    while (n > 0) {
+        const int T = (int)std::min<int64_t>(n, Tmax);
+        // boundary tiles first, then the exchange overlaps the interior tiles
+        if ((rc = tma_pass(c, T, s->tiles.p + s->off_b[T], s->cnt_b[T], c->stream))) break;
+        if (up || down) {
+            CUS(cudaEventRecord(s->evA, c->stream));
+            CUS(cudaStreamWaitEvent(c->comm_stream, s->evA, 0));
+        }
+        c->grid_limit = (up || down) ? c->prop.multiProcessorCount - s->reserve_sms : 0;
+        rc = tma_pass(c, T, s->tiles.p + s->off_i[T], s->cnt_i[T], c->stream);
+        c->grid_limit = 0;
+        if (rc) break;
+        if (up || down) {
+            double *dst = c->x[c->cur ^ 1].p;                      // the buffer this pass wrote
+            NCCLCHECK(api->GroupStart());
+            if (up) {
+                // own top H rows -> upper neighbour's lower halo; its bottom H own rows -> my upper halo
+                NCCLCHECK(api->Send(dst + (size_t)(1 + c->halo_above) * c->pitch, count, ncclDouble, s->rank - 1, s->comm, c->comm_stream));
+                NCCLCHECK(api->Recv(dst + (size_t)(1 + c->halo_above - H) * c->pitch, count, ncclDouble, s->rank - 1, s->comm, c->comm_stream));
+            }
+            if (down) {
+                const size_t last_own = (size_t)(1 + c->halo_above + c->own_rows);    // padded row after the last own row
+                NCCLCHECK(api->Send(dst + (last_own - (size_t)H) * c->pitch, count, ncclDouble, s->rank + 1, s->comm, c->comm_stream));
+                NCCLCHECK(api->Recv(dst + last_own * c->pitch, count, ncclDouble, s->rank + 1, s->comm, c->comm_stream));
+            }
+            NCCLCHECK(api->GroupEnd());
+            CUS(cudaEventRecord(s->evC, c->comm_stream));
+            CUS(cudaStreamWaitEvent(c->stream, s->evC, 0));
+            c->launches++;                                         // the NCCL send/recv kernel
+        }
+        c->cur ^= 1;
+        n -= T;
+    }
+    c->tile_family = old_family;
+    if (rc) return rc;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error(c, "slab sweep launch failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
+    return DEFF2D_OK;
+}
+
+// {Q1, Q2} of this slab's rows -> global sums on every rank (in place in the device state).
+int slab_allreduce_q(deff2d_ctx *c)
+{
+    SlabState *s = static_cast<SlabState *>(c->slab);
+    if (!s || !s->comm || s->nranks < 2 || !c->slab_domain) return DEFF2D_OK;
+    NcclApi *api = nccl_api();
+    NCCLCHECK(api->AllReduce(c->d_state->q, c->d_state->q, 2, ncclDouble, ncclSum, s->comm, c->stream));
+    c->launches++;
+    return DEFF2D_OK;
+}
+
+void slab_destroy(deff2d_ctx *c)
+{
+    SlabState *s = static_cast<SlabState *>(c->slab);
+    if (!s) return;
+    NcclApi *api = nccl_api();
+    if (s->comm && api->CommDestroy) api->CommDestroy(s->comm);
+    if (s->evA) cudaEventDestroy(s->evA);
+    if (s->evC) cudaEventDestroy(s->evC);
+    if (s->tiles.p) cudaFree(s->tiles.p);
+    delete s;
+    c->slab = nullptr;
+}
+
 }  // namespace deff2d
 
-DEFF2D_EXPORT int deff2d_nccl_unique_id(uint8_t id[DEFF2D_NCCL_ID_BYTES]) { (void)id; return DEFF2D_ERR_NCCL; }
+using namespace deff2d;
+
+DEFF2D_EXPORT int deff2d_nccl_unique_id(uint8_t id[DEFF2D_NCCL_ID_BYTES])
+{
+    static_assert(sizeof(ncclUniqueId) == DEFF2D_NCCL_ID_BYTES, "ncclUniqueId size");
+    if (!id) return DEFF2D_ERR_ARG;
+    NcclApi *api = nccl_api();
+    if (!api->handle) { set_error(nullptr, "%s", api->error.c_str()); return DEFF2D_ERR_NCCL; }
+    ncclUniqueId u;
+    if (api->GetUniqueId(&u) != ncclSuccess) { set_error(nullptr, "ncclGetUniqueId failed"); return DEFF2D_ERR_NCCL; }
+    std::memcpy(id, &u, sizeof(u));
+    return DEFF2D_OK;
+}
+
 DEFF2D_EXPORT int deff2d_nccl_init(deff2d_ctx *c, const uint8_t id[DEFF2D_NCCL_ID_BYTES], int rank, int nranks)
 {
-    (void)id; (void)rank; (void)nranks;
-    deff2d::set_error(c, "NCCL slab mode not built yet");
-    return DEFF2D_ERR_NCCL;
+    if (!c || !id || nranks < 1 || rank < 0 || rank >= nranks) return DEFF2D_ERR_ARG;
+    NcclApi *api = nccl_api();
+    if (!api->handle) { set_error(c, "%s", api->error.c_str()); return DEFF2D_ERR_NCCL; }
+    slab_destroy(c);
+    SlabState *s = new SlabState();
+    c->slab = s;
+    s->rank = rank; s->nranks = nranks;
+    CUS(cudaSetDevice(c->device));
+    CUS(cudaEventCreateWithFlags(&s->evA, cudaEventDisableTiming));
+    CUS(cudaEventCreateWithFlags(&s->evC, cudaEventDisableTiming));
+    ncclUniqueId u;
+    std::memcpy(&u, id, sizeof(u));
+    NCCLCHECK(api->CommInitRank(&s->comm, nranks, u, rank));
+    return DEFF2D_OK;
 }
-DEFF2D_EXPORT int deff2d_slab_sweeps(deff2d_ctx *c, int64_t n) { (void)n; deff2d::set_error(c, "NCCL slab mode not built yet"); return DEFF2D_ERR_NCCL; }
-DEFF2D_EXPORT int deff2d_slab_flux(deff2d_ctx *c, double *d) { (void)d; deff2d::set_error(c, "NCCL slab mode not built yet"); return DEFF2D_ERR_NCCL; }
+
+DEFF2D_EXPORT int deff2d_slab_sweeps(deff2d_ctx *c, int64_t n)
+{
+    if (!c || n < 0) return DEFF2D_ERR_ARG;
+    if (!c->loaded) { set_error(c, "no domain loaded"); return DEFF2D_ERR_STATE; }
+    if (cudaSetDevice(c->device) != cudaSuccess) return DEFF2D_ERR_CUDA;
+    return slab_enqueue_sweeps(c, n);
+}
+
+DEFF2D_EXPORT int deff2d_slab_flux(deff2d_ctx *c, double *deff_raw)
+{
+    if (!c) return DEFF2D_ERR_ARG;
+    if (!c->loaded) { set_error(c, "no domain loaded"); return DEFF2D_ERR_STATE; }
+    CUS(cudaSetDevice(c->device));
+    launch_flux(c->stream, view(c), c->Dphase, c->CL, c->CR, c->NxG, c->own_first, c->own_rows, c->d_state);
+    c->launches++;
+    int rc = slab_allreduce_q(c);
+    if (rc) return rc;
+    CUS(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(SolveState), cudaMemcpyDeviceToHost, c->stream));
+    CUS(cudaStreamSynchronize(c->stream));
+    if (deff_raw) {
+        const double qAvg = (c->h_state->q[0] + c->h_state->q[1]) / (2.0 * (double)c->NyG);   // cuh:1263
+        *deff_raw = qAvg / (c->CR - c->CL);                                                  // cuh:1264
+    }
+    return DEFF2D_OK;
+}
+
+DEFF2D_EXPORT int deff2d_tile_geometry(int T, int *ow, int *oh, int *tw, int *th)
+{
+    if (T < 1 || T > 8) return DEFF2D_ERR_ARG;
+    int a = 0, b = 0;
+    tma_tile_geometry(nullptr, T, &a, &b);
+    if (ow) *ow = a;
+    if (oh) *oh = b;
+    if (tw) *tw = a + 2 * ((T + 1) & ~1);
+    if (th) *th = b + 2 * T;
+    return DEFF2D_OK;
+}
+
+DEFF2D_EXPORT int deff2d_slab_split_tiles(int64_t Nx, int64_t Ny, int64_t above, int64_t own, int64_t below,
+                                          int64_t halo, int T, uint32_t *boundary_tiles, int *nboundary,
+                                          uint32_t *interior_tiles, int cap)
+{
+    if (T < 1 || T > 8 || Nx < 1 || Ny < 1 || above + own + below != Ny || !nboundary) return DEFF2D_ERR_ARG;
+    int ow, oh;
+    tma_tile_geometry(nullptr, T, &ow, &oh);
+    std::vector<uint32_t> bd, in;
+    slab_split_tiles(Nx, Ny, above, own, below, halo, ow, oh, bd, in);
+    if ((int)bd.size() > cap || (int)in.size() > cap) return DEFF2D_ERR_ARG;
+    if (boundary_tiles) std::memcpy(boundary_tiles, bd.data(), bd.size() * sizeof(uint32_t));
+    if (interior_tiles) std::memcpy(interior_tiles, in.data(), in.size() * sizeof(uint32_t));
+    *nboundary = (int)bd.size();
+    return (int)in.size();
+}

@@ -420,6 +420,7 @@ static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, 
     const int ntiles = list ? count : ts->tiles_x * ts->tiles_y;
     if (ntiles < 1) return DEFF2D_OK;
     int grid = c->prop.multiProcessorCount;
+    if (c->grid_limit > 0 && grid > c->grid_limit) grid = c->grid_limit;
     if (grid > ntiles) grid = ntiles;
     kern<<<grid, C::NT, C::SMEM, stream>>>(ts->maps, src, c->lut.p, 1.0 - c->omega, (int)c->ghost_period, ts->tiles_x, ntiles,
                                            list, nullptr);

@@ -1,0 +1,132 @@
+"""Row-slab decomposition of one large domain across the GPUs of a box (one process per GPU).
+
+The reference is single-GPU (`cudaSetDevice(0)`, Deff2D.cuh:908).  Its solve loop
+(`JacobiGPU`, cuh:1163-1314) shards naturally by rows: the 5-point stencil only couples
+neighbouring rows, and the convergence check needs two sums over the boundary columns.
+`SlabLayout` is the pure geometry (which source rows a rank owns and which halo rows it also
+holds); `SlabDomain` loads a rank's slab into libdeff2d, initialises the library's NCCL
+communicator (unique id broadcast through `torch.distributed`) and drives the same calls as a
+single-GPU domain: `sweeps`, `flux`, `solve`.  Halo exchange (ncclSend/ncclRecv of the boundary
+rows after every temporally blocked pass) and the flux all-reduce happen inside the library
+(csrc/slab.cu).
+"""
+import numpy as np
+
+from . import api
+
+
+def partition_rows(nrows, world):
+    """Contiguous split of `nrows` source rows over `world` ranks: [(row0, rows), ...]."""
+    base, rem = divmod(int(nrows), int(world))
+    out, r0 = [], 0
+    for r in range(world):
+        n = base + (1 if r < rem else 0)
+        out.append((r0, n))
+        r0 += n
+    return out
+
+
+class SlabLayout:
+    """Geometry of rank `rank`'s slab of a global image of `H` source rows (amplified by amp_y).
+
+    halo: amplified halo rows held of each neighbour; rounded up to a multiple of amp_y because
+    the slab loader thresholds whole source rows (deff2d_domain_load_slab)."""
+
+    def __init__(self, H, rank, world, amp_y=1, halo=4):
+        if world < 1 or not (0 <= rank < world):
+            raise ValueError("bad rank/world")
+        self.H, self.rank, self.world, self.amp_y = int(H), int(rank), int(world), int(amp_y)
+        self.halo = -(-int(halo) // self.amp_y) * self.amp_y
+        self.halo_src = self.halo // self.amp_y
+        self.src_row0, self.src_rows = partition_rows(H, world)[rank]
+        if world > 1 and self.src_rows * self.amp_y < self.halo:
+            raise ValueError("slab of %d rows is thinner than its halo (%d)" % (self.src_rows * self.amp_y, self.halo))
+        self.src_above = self.halo_src if rank > 0 else 0
+        self.src_below = self.halo_src if rank < world - 1 else 0
+        self.ny_global = self.H * self.amp_y
+        self.row0 = self.src_row0 * self.amp_y                  # first own amplified row (global)
+        self.own_rows = self.src_rows * self.amp_y
+        self.above = self.src_above * self.amp_y
+        self.below = self.src_below * self.amp_y
+
+    @property
+    def local_src(self):
+        """(first, last+1) global source rows held locally, halo rows included."""
+        return self.src_row0 - self.src_above, self.src_row0 + self.src_rows + self.src_below
+
+    @property
+    def local_rows(self):
+        """(first, last+1) global amplified rows held locally, halo rows included."""
+        return self.row0 - self.above, self.row0 + self.own_rows + self.below
+
+
+def _take_rows(arr, lo, hi, period=None):
+    """Rows [lo, hi) of `arr`; with `period` the array repeats every `period` rows (weak scaling:
+    the global domain is `world` vertical copies of one image)."""
+    if period is None:
+        return np.ascontiguousarray(arr[lo:hi])
+    idx = np.arange(lo, hi) % period
+    return np.ascontiguousarray(arr[idx])
+
+
+class SlabDomain:
+    """One rank's slab, resident on this rank's GPU.
+
+    img:     the global 8-bit source image (H x W); with weak=True the global domain is `world`
+             vertical copies of `img` (every rank then owns one whole copy).
+    pinned:  3-phase only -- the global FloodFill mask (cuh:557-713) at amplified resolution, or
+             None to compute it here with the library's host FloodFill.
+    """
+
+    def __init__(self, ctx, img, params, rank, world, nphase=3, halo=4, pinned=None, weak=False, nccl_id=None):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        Hbase, W = img.shape
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        H = Hbase * world if weak else Hbase
+        period_src = Hbase if weak else None
+        self.layout = L = SlabLayout(H, rank, world, params.amp_y, halo)
+        self.Nx = W * params.amp_x
+        self.global_cells = self.Nx * L.ny_global
+        lo, hi = L.local_src
+        gray = _take_rows(img, lo, hi, period_src)
+        pin = None
+        self.pathflag = None
+        if nphase == 3:
+            if pinned is None:
+                # FloodFill is y-periodic (cuh:641-665): the mask of `world` stacked copies is the
+                # stacked mask of one copy, so the weak-scaling domain never needs a global flood
+                base = np.repeat(np.repeat(img > 200, params.amp_y, axis=0), params.amp_x, axis=1).astype(np.uint8)
+                pinned, self.pathflag = api.floodfill(base)
+                period = base.shape[0] if weak else None
+            else:
+                period = None
+            a, b = L.local_rows
+            pin = _take_rows(np.asarray(pinned, dtype=np.uint8), a, b, period)
+        if nccl_id is None:
+            nccl_id = self._broadcast_id()
+        ctx.nccl_init(nccl_id, rank, world)
+        ctx.domain_load_slab(gray, nphase, params, L.row0, L.ny_global, L.halo, L.src_rows, pin)
+
+    def _broadcast_id(self):
+        import torch.distributed as dist
+        if self.world == 1 and not (dist.is_available() and dist.is_initialized()):
+            return api.nccl_unique_id()
+        box = [api.nccl_unique_id() if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def sweeps(self, n):
+        self.ctx.slab_sweeps(n)
+
+    def flux(self):
+        return self.ctx.slab_flux()
+
+    def solve(self, tol, max_iter):
+        """The reference loop (cuh:1232-1290) on the decomposed domain; identical on every rank."""
+        return self.ctx.solve(tol, max_iter)
+
+    def own_field(self):
+        """This rank's own rows of the iterate (own_rows x Nx)."""
+        f = self.ctx.get_field()
+        L = self.layout
+        return f[L.above:L.above + L.own_rows]
