@@ -176,6 +176,37 @@ def cpu_baseline(img, sweeps, three_phase=True):
                       "%dx%d domain, %d OpenMP threads, %.1f s" % (sweeps, img.shape[1] * AMP, img.shape[0] * AMP, n, secs)}
 
 
+def ref_cuda_baseline(img, sweeps):
+    """The reference's own CUDA build (nvcc, sm_100a, unmodified JacobiGPU + updateX_SOR) timed on
+    this GPU by its own event timer -- a reported baseline (north_star), bounded to `sweeps`."""
+    import _oracle as O
+    if O.reference("cuda") is None:
+        return None
+    D = O.fill_D(img, AMP, AMP, 3, 0.0, 1.0, 1237500.0)
+    G, _ = O.floodfill(O.grid_mask(img, AMP, AMP, 200))
+    A, b = O.discretize(D, 0.0, 1.0, G)
+    Ny, Nx = D.shape
+    r = O.ref_jacobi(A, b, O.init_x(Nx, Ny, 0.0, 1.0), D, 0.0, 1.0, 1e-30, sweeps, kind="cuda")
+    return {"value": Nx * Ny * r["iters"] / (r["ms"] * 1e-3) / 1e9, "unit": "GLUP/s", "kind": "reference CUDA build (sm_100a)",
+            "sample": "%d sweeps of the reference's JacobiGPU loop (kernel + sync + D2D copy per sweep, one D2H check) on "
+                      "%dx%d cells, its own cudaEvent time %.1f ms" % (r["iters"], Nx, Ny, r["ms"])}
+
+
+def batch_leg(ctx, count, size=256):
+    """Deff images/s of the packed batch mode on config 3 inputs (host images in, Deff out)."""
+    import effectivediffusivityfvm_b200 as E
+    from effectivediffusivityfvm_b200.datasets import c3_image
+    imgs = np.stack([c3_image(k, size) for k in range(count)])
+    p = E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH, tol=1e-5, max_iter=500000)
+    ctx.solve_batch(imgs[:2], E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH, max_iter=50))
+    t0 = time.perf_counter()
+    res = ctx.solve_batch(imgs, p)
+    dt = time.perf_counter() - t0
+    sweeps = float(sum(r["total_iters"] for r in res))
+    return {"workload": "configs[2] sample: %d synthetic two-phase %dx%d images, Ds 1e-3, Df 1, tol 1e-5, MaxIter 5e5" % (count, size, size),
+            "images": count, "seconds": dt, "images_per_s": count / dt, "glups": sweeps * size * size / dt / 1e9}
+
+
 def run_ours(args):
     import torch
     import effectivediffusivityfvm_b200 as E
@@ -286,9 +317,26 @@ def run_ours(args):
                        "cells": cells, "sweeps_per_step": S, "l2_policy": "working set 2x%.0f MB > 126 MB L2, no flush needed" % (Nx * Ny * 8 / 1e6),
                        "kernel": args.kernel, "tblock": args.tblock},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "deff_raw": deff}
+    if args.batch_images > 0:
+        # image batches shard with no communication: every rank solves its own slice
+        bl = batch_leg(ctx, args.batch_images)
+        if world > 1:
+            t = torch.tensor([bl["seconds"]], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            bl["seconds"] = float(t.item())
+            bl["images"] = args.batch_images * world
+            bl["images_per_s"] = bl["images"] / bl["seconds"]
+            bl["glups"] = None
+        line["batch"] = bl
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(img, args.cpu_sweeps)
+            try:
+                rc = ref_cuda_baseline(img, args.ref_cuda_sweeps)
+            except Exception as e:      # a reported baseline must not take the bench line down
+                rc = {"unavailable": "%s: %s" % (type(e).__name__, e)}
+            if rc:
+                line["ref_cuda_baseline"] = rc
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
@@ -308,6 +356,8 @@ def main():
     ap.add_argument("--ref-sweeps", type=int, default=20)
     ap.add_argument("--ref-crop", type=int, default=0, help="use only the first N source rows for the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-cuda-sweeps", type=int, default=1001)
+    ap.add_argument("--batch-images", type=int, default=0, help="also time the packed batch mode on this many config-3 images per GPU")
     ap.add_argument("--allow-short-warmup", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

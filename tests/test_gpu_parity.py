@@ -134,6 +134,32 @@ def test_residual_matches_reference_definition(ctx):
     assert rel(ctx.residual(), ref) < 1e-10
 
 
+@pytest.mark.parametrize("nphase", [2, 3])
+def test_parity_with_reference_cuda_build(ctx, nphase):
+    """The reference's own JacobiGPU + updateX_SOR, compiled unmodified by nvcc for sm_100a
+    (oracle/_ref/libref_cuda.so), run on this GPU beside ours: same sweep count, Deff, field."""
+    if O.reference("cuda") is None:
+        pytest.skip("oracle/_ref/libref_cuda.so not built")
+    img = blobs(40 + nphase, (72, 96), levels=(0, 150, 255), fracs=(0.3, 0.4))
+    Ds, Dg, CL, CR = (0.0, 300.0, 0.0, 1.0) if nphase == 3 else (1e-3, 0.0, 0.0, 1.0)
+    D = O.fill_D(img, 1, 1, nphase, Ds, 1.0, Dg)
+    G, _ = O.floodfill(O.grid_mask(img, 1, 1, 200 if nphase == 3 else 150))
+    A, b = O.ref_discretize(D, CL, CR, G if nphase == 3 else None, kind="cuda")
+    Ny, Nx = D.shape
+    ref = O.ref_jacobi(A, b, O.init_x(Nx, Ny, CL, CR), D, CL, CR, 1e-5, 60001, kind="cuda")
+    p = E.default_params(Ds=Ds, Df=1.0, Dg=Dg, CL=CL, CR=CR)
+    for kernel in (1, 2):
+        ctx.set_kernel(kernel, 4)
+        ctx.domain_load(img, nphase, p)
+        got = ctx.solve(1e-5, 60001)
+        assert got["iters"] == ref["iters"]
+        assert rel(got["deff_raw"], ref["deff_raw"]) < DEFF_RTOL_TIGHT
+        f = ctx.get_field()
+        assert np.array_equal(np.isnan(f), np.isnan(ref["field"]))
+        assert np.nanmax(np.abs(f - ref["field"])) < FIELD_ATOL
+    ctx.set_kernel(0)
+
+
 # ----------------------------------------------------------------------------- driver flows
 
 def check_against_oracle(got, ref):
