@@ -169,5 +169,54 @@ def main():
         json.dump(drivers, f, indent=1, sort_keys=True)
 
 
+def make_jpeg_fixtures(out_path=None):
+    """JPEG files (bytes) + the pixels the reference's own decoder (stbi_load, Deff2D.cuh:342)
+    returns for them: the two bundled images and generated baseline / progressive /
+    restart-interval / optimised-Huffman grayscale files.  Needs /root/reference, PIL and
+    oracle/_ref/libref_cpu.so; run here, committed as tests/golden/jpeg.npz."""
+    import io
+    import tempfile
+    from PIL import Image
+    import _oracle as O
+    out_path = out_path or os.path.join(HERE, "jpeg.npz")
+    files = {}
+    for name in ("00000", "00042"):
+        files["bundled_" + name] = open("/root/reference/Deff2DGPU/%s.jpg" % name, "rb").read()
+    rng = np.random.default_rng(0)
+    z = rng.random((67, 131))
+    for _ in range(3):
+        z = (z + np.roll(z, 1, 0) + np.roll(z, 1, 1)) / 3
+    g = (255 * (z - z.min()) / (z.max() - z.min())).astype(np.uint8)
+    noise = rng.integers(0, 256, (120, 203), dtype=np.uint8)
+    two = np.where(z < np.median(z), 0, 255).astype(np.uint8)[:33, :17]
+    cases = {"smooth_q90": (g, dict(quality=90)), "smooth_q30": (g, dict(quality=30)),
+             "smooth_q100_prog": (g, dict(quality=100, progressive=True)),
+             "smooth_q75_prog": (g, dict(quality=75, progressive=True)),
+             "noise_q95": (noise, dict(quality=95)), "noise_q50_prog": (noise, dict(quality=50, progressive=True)),
+             "twotone_opt": (two, dict(quality=85, optimize=True)),
+             "noise_restart": (noise, dict(quality=80, restart_marker_blocks=7)),
+             "smooth_restart_rows": (g, dict(quality=85, restart_marker_rows=1)),
+             "tiny_1x1": (np.array([[200]], dtype=np.uint8), dict(quality=90)),
+             "tiny_9x7": (noise[:7, :9].copy(), dict(quality=90))}
+    for name, (arr, kw) in cases.items():
+        buf = io.BytesIO()
+        Image.fromarray(arr).save(buf, "JPEG", **kw)
+        files["gen_" + name] = buf.getvalue()
+    out = {}
+    with tempfile.TemporaryDirectory() as d:
+        for name, data in files.items():
+            p = os.path.join(d, "x.jpg")
+            with open(p, "wb") as f:
+                f.write(data)
+            pix, nch = O.ref_decode(p)
+            assert nch == 1
+            out["file_" + name] = np.frombuffer(data, dtype=np.uint8)
+            if not name.startswith("bundled_"):      # the bundled images' pixels already live in images.npz
+                out["pix_" + name] = pix
+    np.savez_compressed(out_path, **out)
+    return out_path
+
+
 if __name__ == "__main__":
     main()
+    make_jpeg_fixtures()

@@ -376,6 +376,31 @@ def test_drop_in_program(ctx, tmp_path, golden_drivers):
         os.chdir(cwd)
 
 
+def test_drop_in_executable_on_bundled_jpeg(tmp_path, golden_dir, golden_drivers):
+    """The `deff2d` executable in place of the reference's a.out: shipped input.txt (InputName
+    changed to the bundled 00000.jpg, as in BASELINE config 1), JPEG decoded by the library's own
+    decoder, CSV compared with the row the reference program wrote (Time excluded)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(E.LIB_PATH), "deff2d")
+    assert os.path.exists(exe), "drop-in executable not built"
+    z = np.load(os.path.join(golden_dir, "jpeg.npz"))
+    (tmp_path / "00000.jpg").write_bytes(z["file_bundled_00000"].tobytes())
+    (tmp_path / "input.txt").write_text(
+        "Input Parameters:\nPhases: 3\nDs: 0\nDf: 1\nDg: 1237500\nMeshAmpX: 1\nMeshAmpY: 1\nInputName: 00000.jpg\n"
+        "CR: 1\nCL: 0\nOutputName: TestOut.csv\nprintCMap: 1\nCMapName: CMAP_00000.csv\nConvergence: 1e-5\n"
+        "MaxIter: 5e5\nVerbose: 1\nRunBatch: 0\nNumImages: 1\n")
+    out = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("Iterations taken = ") == 7 and "Iterations taken = 80001" in out.stdout
+    mine = (tmp_path / "TestOut.csv").read_text().strip().splitlines()
+    ref = golden_drivers["bundled00000_3ph_single"]["csv"].strip().splitlines()
+    assert mine[0] == ref[0]
+    a, b = mine[1].split(","), ref[1].split(",")
+    assert a[:5] == b[:5] and a[6:] == b[6:]                     # everything but Time
+    cm = (tmp_path / "CMAP_00000.csv").read_text().splitlines()
+    assert cm[0] == "X,Y,C" and len(cm) == 128 * 128 + 1
+
+
 # ----------------------------------------------------------------------------- full-size properties
 
 def test_full_size_properties_config2(ctx, golden_images):

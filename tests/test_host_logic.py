@@ -194,3 +194,30 @@ def test_image_readers(tmp_path, golden_images):
     assert np.array_equal(got, exp)
     with pytest.raises(E.Deff2DError):
         E.load_image(tmp_path / "nope.png")
+
+
+def test_jpeg_decoder_matches_reference_decoder(tmp_path, golden_dir, golden_images):
+    """The library's own JPEG decoder returns, pixel for pixel, what the reference's decoder
+    (stbi_load(..., 1), Deff2D.cuh:342) returned for the same files: the two bundled images and
+    generated baseline / progressive / restart-interval / optimised-Huffman files
+    (tests/golden/jpeg.npz, made by tests/golden/make_golden.py)."""
+    z = np.load(os.path.join(golden_dir, "jpeg.npz"))
+    names = [k[5:] for k in z.files if k.startswith("file_")]
+    assert len(names) >= 12
+    for name in names:
+        path = tmp_path / (name + ".jpg")
+        path.write_bytes(z["file_" + name].tobytes())
+        got, ch = E.load_image(path)
+        want = golden_images[name[8:]] if name.startswith("bundled_") else z["pix_" + name]
+        assert ch == 1
+        assert got.shape == want.shape and np.array_equal(got, want), name
+
+
+def test_jpeg_decoder_rejects_garbage(tmp_path):
+    p = tmp_path / "bad.jpg"
+    p.write_bytes(b"\xff\xd8\xff\xe0\x00\x10JFIF" + b"\x00" * 40)
+    with pytest.raises(E.Deff2DError):
+        E.load_image(p)
+    p.write_bytes(b"\xff\xd8")
+    with pytest.raises(E.Deff2DError):
+        E.load_image(p)
