@@ -205,7 +205,19 @@ static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc,
     // un-amplified width there and reads out of bounds).
     const uint8_t *grid_dev = nullptr;
     c->pathflag = 0;
-    if (run_floodfill) {
+    c->floodfill_passes = 0;
+    const bool ff_device = run_floodfill && Nx >= 2 &&
+                           (c->floodfill_mode == 2 || (c->floodfill_mode == 0 && Nx * Ny >= ((int64_t)1 << 16)));
+    if (ff_device) {
+        // label propagation on the device (floodfill.cu): same reachability, no 1 B/cell mask upload
+        if ((rc = ensure(c, c->grid, (size_t)Nx * Ny))) return rc;
+        int pf = 0;
+        if ((rc = floodfill_device(c, c->img.p, W, p->amp_x, p->amp_y, (nphase == 3) ? 200 : 150, c->grid.p, Nx, Ny,
+                                   reinterpret_cast<int *>(c->d_scalar), reinterpret_cast<int *>(c->h_scalar), &pf,
+                                   &c->floodfill_passes))) return rc;
+        c->pathflag = pf;
+        if (nphase == 3) grid_dev = c->grid.p;
+    } else if (run_floodfill) {
         const int thr = (nphase == 3) ? 200 : 150;
         c->h_grid.resize((size_t)Nx * Ny);
         for (int64_t i = 0; i < Ny; i++) {
@@ -666,6 +678,13 @@ DEFF2D_EXPORT int deff2d_set_kernel(deff2d_ctx *c, int kernel, int tblock)
     if (kernel >= 3) kernel = 2;
     c->kernel = kernel;
     c->tblock = tblock > 0 ? tblock : 1;
+    return DEFF2D_OK;
+}
+
+DEFF2D_EXPORT int deff2d_set_floodfill(deff2d_ctx *c, int mode)
+{
+    if (!c || mode < 0 || mode > 2) return DEFF2D_ERR_ARG;
+    c->floodfill_mode = mode;
     return DEFF2D_OK;
 }
 

@@ -63,6 +63,8 @@ struct deff2d_ctx {
     // packed-batch state (batch.cu)
     void *batch = nullptr;
     int batch_max_slots = 0;         // 0: library default
+    int floodfill_mode = 0;          // 0 auto (device for >= 64 K cells), 1 host, 2 device
+    int floodfill_passes = 0;        // device passes of the last FloodFill (diagnostic)
 
     int grid_limit = 0;              // > 0: cap on the CTAs of a tiled pass (slab mode leaves SMs to NCCL)
 
@@ -93,6 +95,10 @@ int slab_allreduce_q(deff2d_ctx *c);     // no-op unless the resident domain is 
 int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n);
 void slab_destroy(deff2d_ctx *c);
 void batch_destroy(deff2d_ctx *c);
+
+// floodfill.cu: FloodFill (cuh:557-713) by label propagation on the device; blocks
+int floodfill_device(deff2d_ctx *c, const uint8_t *img, int W, int amp_x, int amp_y, int thr, uint8_t *st, int64_t Nx,
+                     int64_t Ny, int *d_flags, int *h_flags, int *pathflag, int *passes);
 
 // batch.cu: returns 1 when the resident small-image kernel does not cover the request
 int batch_resident_solve(deff2d_ctx *c, const uint8_t *gray, int count, int W, int H,

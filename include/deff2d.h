@@ -151,6 +151,9 @@ int deff2d_sync(deff2d_ctx *ctx);
 /* Select the sweep kernel: 0 = library default, 1 = plain streaming kernel (one sweep per
  * HBM pass), 2 = TMA-staged tiled kernel with `tblock` sweeps per pass. */
 int deff2d_set_kernel(deff2d_ctx *ctx, int kernel, int tblock);
+/* Where FloodFill (cuh:557-713) runs for whole-domain loads: 0 = automatic (device from 64 K cells),
+ * 1 = host (FIFO flood), 2 = device (label propagation).  Same result either way. */
+int deff2d_set_floodfill(deff2d_ctx *ctx, int mode);
 /* Packed batch mode (deff2d_solve_batch): at most `max_slots` images resident at a time
  * (0 = library default, sized from the image size); finished images are replaced from the
  * queue.  Tuning / test hook. */

@@ -160,6 +160,64 @@ def test_parity_with_reference_cuda_build(ctx, nphase):
     ctx.set_kernel(0)
 
 
+def _maze(n, seed):
+    """A tortuous open path: serpentine corridors with random gaps (many tile crossings)."""
+    rng = np.random.default_rng(seed)
+    img = np.full((n, n), 255, np.uint8)
+    img[1::4, :] = 0                         # horizontal corridors
+    for r in range(1, n - 4, 4):             # one connecting gap per corridor pair, alternating ends
+        c = rng.integers(0, 8) if (r // 4) % 2 else n - 1 - rng.integers(0, 8)
+        img[r:r + 5, c] = 0
+    return img
+
+
+@pytest.mark.parametrize("case", ["blobs", "quirk_solid_corner", "wall", "maze", "periodic", "amp", "percolation"])
+def test_device_floodfill_equals_host_floodfill(ctx, case):
+    """FloodFill by label propagation on the device (floodfill.cu) against the host FIFO flood,
+    which is pinned to the reference's FloodFill (tests/test_host_logic.py): same PathFlag, same
+    Grid (through the pinned bit of the 3-phase codes)."""
+    amp = (1, 1)
+    if case == "blobs":
+        img = blobs(5, (300, 700), levels=(0, 150, 255), fracs=(0.3, 0.3))
+    elif case == "quirk_solid_corner":
+        img = blobs(6, (200, 333), levels=(0, 150, 255), fracs=(0.2, 0.3))
+        img[0, 0] = 255
+        img[:, 150:160] = 255                # a full-height wall: only the quirk's right-column seeds reach the right half
+    elif case == "wall":
+        img = blobs(7, (150, 400), levels=(0, 150, 255), fracs=(0.4, 0.3))
+        img[0, 0] = 0
+        img[:, 200:203] = 255
+    elif case == "maze":
+        img = _maze(400, 3)
+    elif case == "periodic":
+        img = np.full((130, 300), 255, np.uint8)
+        img[:, 0:5] = 0
+        img[0, :200] = 0                     # reachable only through the y-periodic wrap from the bottom row
+        img[129, 150:290] = 0
+        img[100:130, 289] = 0
+        img[5, 199] = 0
+    elif case == "amp":
+        img = blobs(8, (90, 70), levels=(0, 150, 255), fracs=(0.3, 0.3))
+        amp = (3, 4)
+    else:
+        img = np.where(np.random.default_rng(5).random((512, 512)) < 0.60, 0, 255).astype(np.uint8)
+    for nphase in (3, 2):
+        p = E.default_params(Ds=0.0 if nphase == 3 else 1e-3, Df=1.0, Dg=50.0, amp_x=amp[0], amp_y=amp[1])
+        res = {}
+        for mode in (1, 2):
+            ctx.set_floodfill(mode)
+            ctx.domain_load(img, nphase, p)
+            res[mode] = (ctx.info()["pathflag"], ctx.get_codes())
+        ctx.set_floodfill(0)
+        assert res[1][0] == res[2][0], (case, nphase)
+        assert np.array_equal(res[1][1], res[2][1]), (case, nphase)
+        # and both agree with the oracle's FloodFill
+        G, pf = O.floodfill(O.grid_mask(img, amp[0], amp[1], 200 if nphase == 3 else 150))
+        assert pf == res[2][0]
+        if nphase == 3:
+            assert np.array_equal((res[2][1] & 4) != 0, (G == 1) | (G == 2))
+
+
 # ----------------------------------------------------------------------------- driver flows
 
 def check_against_oracle(got, ref):
