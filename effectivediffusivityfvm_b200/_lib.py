@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libdeff2d.so")
+LIB_PATH = os.environ.get("DEFF2D_LIB") or os.path.join(PKG_DIR, "libdeff2d.so")   # DEFF2D_LIB: A/B a development build
 
 MAX_STAGES = 16
 NCCL_ID_BYTES = 128
@@ -114,6 +114,8 @@ def lib():
         "deff2d_free": (None, [vp]),
     }
     for name, (res, args) in sig.items():
+        if os.environ.get("DEFF2D_LIB") and not hasattr(L, name):
+            continue                   # development A/B against an older build
         fn = getattr(L, name)          # AttributeError if the library lacks a declared symbol
         fn.restype = res
         fn.argtypes = args

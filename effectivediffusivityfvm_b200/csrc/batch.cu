@@ -146,7 +146,7 @@ k_batch_init(BatchGeom g, const BatchJob *__restrict__ jobs, const uint8_t *__re
 // bit-identical Deff values to a single-image solve.
 __global__ void __launch_bounds__(1024)
 k_batch_check(BatchGeom g, BatchStages stages, BatchSlot *slots, BatchOut *outs, const int *__restrict__ active,
-              long long nsweeps, const double *__restrict__ x, uint8_t *code)
+              long long nsweeps, const double *__restrict__ x, uint8_t *code, uint16_t *idx16)
 {
     __shared__ double s1[32], s2[32];
     __shared__ int sh_restage;
@@ -225,6 +225,7 @@ k_batch_check(BatchGeom g, BatchStages stages, BatchSlot *slots, BatchOut *outs,
             const long long i = k / g.Nx, j = k - i * g.Nx;
             const long long idx = (row0 + i + 1) * g.pitch + col0 + j + XOFF;
             code[idx] = (uint8_t)((code[idx] & 7u) | ((unsigned)rs << 3));
+            idx16[idx] = (uint16_t)((idx16[idx] & 0x87ffu) | ((unsigned)rs << 11));
         }
     }
 }
@@ -453,7 +454,8 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
         buf.cap = n;
         return DEFF2D_OK;
     };
-    if ((rc = grow(c->x[0], stack_cells)) || (rc = grow(c->x[1], stack_cells)) || (rc = grow(c->code, stack_cells))) return rc;
+    if ((rc = grow(c->x[0], stack_cells)) || (rc = grow(c->x[1], stack_cells)) || (rc = grow(c->code, stack_cells)) ||
+        (rc = grow(c->idx16, stack_cells))) return rc;
     if ((rc = grow(c->img, npix * count))) return rc;
     if (nphase == 3 && (rc = grow(c->grid, (size_t)cells * count))) return rc;
     if ((rc = grow(c->lut, (size_t)nstages * DEFF2D_LUT_ENTRIES * 4)) || (rc = grow(c->dead, (size_t)nstages * DEFF2D_LUT_ENTRIES))) return rc;
@@ -536,7 +538,9 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
             k_batch_init<<<dim3((unsigned)bx, (unsigned)njobs), 256, 0, s>>>(g, b->jobs.p, c->img.p, nphase == 3 ? c->grid.p : nullptr,
                                                                             c->x[c->cur].p, c->x[c->cur ^ 1].p, c->code.p,
                                                                             b->slots.p, b->outs.p);
-            c->launches++;
+            // the table indices of the new images (and of their neighbours' shared ghost ring)
+            launch_build_idx(s, c->code.p, c->idx16.p, c->Nx, c->Ny, c->pitch, c->ghost_period);
+            c->launches += 2;
         }
         if (active_changed) {
             nactive = 0;
@@ -576,7 +580,7 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
             c->cur ^= 1;
             left -= t;
         }
-        k_batch_check<<<nactive, 1024, 0, s>>>(g, stages, b->slots.p, b->outs.p, b->active.p, n, c->x[c->cur].p, c->code.p);
+        k_batch_check<<<nactive, 1024, 0, s>>>(g, stages, b->slots.p, b->outs.p, b->active.p, n, c->x[c->cur].p, c->code.p, c->idx16.p);
         c->launches++;
         CUB(cudaEventRecord(b->e1, s));
         CUB(cudaMemcpyAsync(b->h_slots, b->slots.p, (size_t)nslots * sizeof(BatchSlot), cudaMemcpyDeviceToHost, s));

@@ -195,6 +195,7 @@ static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc,
     if ((rc = ensure(c, c->x[0], cells))) return rc;
     if ((rc = ensure(c, c->x[1], cells))) return rc;
     if ((rc = ensure(c, c->code, cells))) return rc;
+    if ((rc = ensure(c, c->idx16, cells))) return rc;
     if ((rc = ensure(c, c->img, (size_t)W * Hsrc))) return rc;
     CU(cudaMemcpyAsync(c->img.p, gray, (size_t)W * Hsrc, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(c->d_counts, 0, sizeof(Counts), c->stream));
@@ -237,8 +238,9 @@ static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc,
     launch_init_domain(c->stream, c->img.p, W, Hsrc, p->amp_x, p->amp_y, nphase, grow0, img_row0, grid_dev,
                        c->x[0].p, c->x[1].p, c->code.p, Nx, Ny, c->pitch, c->NxG, c->CL, c->CR, own_first,
                        own_rows, c->d_counts);
+    launch_build_idx(c->stream, c->code.p, c->idx16.p, Nx, Ny, c->pitch, c->ghost_period);
     launch_count_below(c->stream, c->img.p, (int64_t)W * Hsrc, 150, c->d_counts);
-    c->launches += 2;
+    c->launches += 3;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(Counts), cudaMemcpyDeviceToHost, c->stream));
     if ((rc = upload_tables(c))) return rc;     // synchronises the stream
@@ -441,6 +443,7 @@ DEFF2D_EXPORT void deff2d_destroy(deff2d_ctx *c)
     tma_destroy(c);
     for (int k = 0; k < 2; k++) if (c->x[k].p) cudaFree(c->x[k].p);
     if (c->code.p) cudaFree(c->code.p);
+    if (c->idx16.p) cudaFree(c->idx16.p);
     if (c->img.p) cudaFree(c->img.p);
     if (c->grid.p) cudaFree(c->grid.p);
     if (c->lut.p) cudaFree(c->lut.p);

@@ -39,6 +39,7 @@ struct deff2d_ctx {
 
     DevBuf<double> x[2];
     DevBuf<uint8_t> code, img, grid, dead, dense8;
+    DevBuf<uint16_t> idx16;          // per-cell weight-table index derived from `code` (k_build_idx), read by the tiled sweep
     DevBuf<double> lut, dense;
     std::vector<uint8_t> h_grid;
 

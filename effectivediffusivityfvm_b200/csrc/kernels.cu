@@ -118,6 +118,56 @@ void launch_init_domain(cudaStream_t s, const uint8_t *img, int W, int Hsrc, int
                                          code, Nx, Ny, pitch, NxG, CL, CR, own_first, own_rows, counts);
 }
 
+// ------------------------------------------------------------------------------------------
+// build_idx: the weight-table index of every padded cell (bits 0-10), its stage (11-14, from
+// code bits 3-6) and the ghost-column flag (15).  One thread per 8 cells of a row, one 16-byte
+// store.  Runs once per image load; the tiled sweep then reads 2 B per cell instead of
+// recomputing the index from 5 code bytes per cell per pass.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_build_idx(const uint8_t *__restrict__ code, uint16_t *__restrict__ idx16, long long Nx, long long Ny,
+            long long pitch, long long period)
+{
+    const long long groups_per_row = pitch / 8;
+    const long long total = (Ny + 2) * groups_per_row;
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const long long r = g / groups_per_row;
+        const long long c0 = (g - r * groups_per_row) * 8;
+        const uint8_t *row = code + r * pitch;
+        const uint8_t *up = (r > 0) ? row - pitch : nullptr;
+        const uint8_t *dn = (r < Ny + 1) ? row + pitch : nullptr;
+        unsigned out[8];
+        unsigned prev = (c0 > 0) ? row[c0 - 1] : 3u;
+        unsigned cur = row[c0];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const long long c = c0 + k;
+            const unsigned next = (c + 1 < pitch) ? row[c + 1] : 3u;
+            const unsigned n = up ? up[c] : 3u, s = dn ? dn[c] : 3u;
+            unsigned v = (cur & 3u) | ((prev & 3u) << 2) | ((next & 3u) << 4) | ((s & 3u) << 6) | ((n & 3u) << 8) |
+                         ((cur & 4u) << 8) | (((cur >> 3) & 15u) << 11);
+            const long long j = c - XOFF;                      // interior column
+            if (j >= -1 && j <= Nx && (j + 1) % period == 0) v |= 0x8000u;
+            out[k] = v;
+            prev = cur;
+            cur = next;
+        }
+        *reinterpret_cast<uint4 *>(idx16 + r * pitch + c0) =
+            make_uint4(out[0] | (out[1] << 16), out[2] | (out[3] << 16), out[4] | (out[5] << 16), out[6] | (out[7] << 16));
+    }
+}
+
+void launch_build_idx(cudaStream_t s, const uint8_t *code, uint16_t *idx16, int64_t Nx, int64_t Ny, int64_t pitch,
+                      int64_t ghost_period)
+{
+    const long long total = (Ny + 2) * (pitch / 8);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    k_build_idx<<<blocks, 256, 0, s>>>(code, idx16, Nx, Ny, pitch, ghost_period);
+}
+
 // calcPorosity's counting loop (cuh:399-405) as a reduction over the source image
 __global__ void __launch_bounds__(256)
 k_count_below(const uint8_t *__restrict__ img, long long n, int thr, Counts *counts)

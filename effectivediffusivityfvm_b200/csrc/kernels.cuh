@@ -7,6 +7,9 @@
 //          ghost rows (weight 0).  pitch is a multiple of 16 doubles (128 B rows, TMA needs 16 B).
 //   code   one byte per cell in the same padded geometry (pitch bytes per row):
 //          bits 0-1 phase (0 fluid, 1 solid, 2 gas, 3 ghost), bit 2 pinned (3-phase Grid in {1,2}).
+//   idx16  two bytes per cell, same geometry, derived from `code` (k_build_idx): bits 0-10 the
+//          weight-table index p | pW<<2 | pE<<4 | pS<<6 | pN<<8 | pinned<<10 of the cell, bits 11-14
+//          its continuation stage, bit 15 "Dirichlet ghost column".  Read by the tiled sweep (K2).
 //   lut    2048 x 4 doubles: sweep weights for every (p, pW, pE, pS, pN, pinned), per stage.
 // The reference's A[n][5] + b[n] (48 B/cell, cuh:1396-1397) are never materialised.
 #pragma once
@@ -57,6 +60,9 @@ void launch_init_domain(cudaStream_t s, const uint8_t *img, int W, int Hsrc, int
                         double *x0, double *x1, uint8_t *code, int64_t Nx, int64_t Ny, int64_t pitch,
                         int64_t NxG, double CL, double CR, int64_t own_first, int64_t own_rows,
                         Counts *counts);
+// per-cell table index of every padded cell from the codes (see idx16 above)
+void launch_build_idx(cudaStream_t s, const uint8_t *code, uint16_t *idx16, int64_t Nx, int64_t Ny, int64_t pitch,
+                      int64_t ghost_period);
 void launch_count_below(cudaStream_t s, const uint8_t *img, int64_t n, int thr, Counts *counts);
 
 // K3: plain streaming sweep, one sweep per HBM pass (cuh:69-92 matrix-free)

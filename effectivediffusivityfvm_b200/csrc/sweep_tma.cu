@@ -4,8 +4,8 @@
 // device-to-device copy (cuh:1281) by ONE pass over HBM:
 //
 //   * persistent CTAs walk a static list of (TW x TH) tiles; every tile, halo included, is
-//     brought into shared memory by two bulk tensor copies (FP64 iterate + u8 phase codes,
-//     cp.async.bulk.tensor.2d, mbarrier complete_tx), double buffered so the next tile's
+//     brought into shared memory by two bulk tensor copies (FP64 iterate + the u16 weight-table
+//     index of every cell, cp.async.bulk.tensor.2d, mbarrier complete_tx), double buffered so the next tile's
 //     copy overlaps the current tile's sweeps; out-of-range boxes are zero filled by TMA;
 //   * each thread owns a PX x PY patch of cells for the whole tile visit: the patch values
 //     and its 4 x PX x PY sweep weights (looked up once per tile from the per-stage LUT with
@@ -77,7 +77,7 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map)
 struct TmaMaps {
     CUtensorMap x_load[2];     // padded iterate buffers, box TW x TH
     CUtensorMap x_store[2];    // interior of the iterate buffers, box OW x OH
-    CUtensorMap code;          // padded codes, box TW x TH (u8)
+    CUtensorMap idx;           // padded per-cell table indices, box IW x TH (u16)
 };
 
 template <int T_, int PX_, int PY_, int NWX_, int NWY_>
@@ -87,16 +87,16 @@ struct Cfg {
     static constexpr int NT = 32 * NWX * NWY;
     // TMA needs the innermost box coordinate 16-byte aligned (measured on B200: an odd FP64
     // column or a u8 column that is not a multiple of 16 raises "illegal instruction").  The x
-    // halo is therefore rounded up to an even number of columns, and the code box is 16 bytes
-    // wider than the tile and starts at the previous multiple of 16.
+    // halo is therefore rounded up to an even number of columns, and the index box (u16) is 8
+    // elements wider than the tile and starts at the previous multiple of 8.
     static constexpr int TE = (T + 1) & ~1;
     static constexpr int OW = TW - 2 * TE, OH = TH - 2 * T;
     static constexpr int CELLS = TW * TH;
-    static constexpr int CW = TW + 16;                           // code box width
+    static constexpr int IW = TW + 8;                            // index box width (u16 elements)
     static constexpr int PLANE_W = TW / PX;                      // columns per phase plane
     // shared memory map (bytes)
     static constexpr size_t IN_BYTES = (size_t)CELLS * 8;
-    static constexpr size_t CODE_BYTES = ((size_t)CW * TH + 127) / 128 * 128;
+    static constexpr size_t CODE_BYTES = ((size_t)IW * TH * 2 + 127) / 128 * 128;
     static constexpr size_t OFF_IN = 0;                           // IN[2]
     static constexpr size_t OFF_P = OFF_IN + 2 * IN_BYTES;        // P[2] planar exchange
     static constexpr size_t OFF_OUT = OFF_P + 2 * IN_BYTES;       // OUT: dense OW x OH box for the bulk store
@@ -108,14 +108,13 @@ struct Cfg {
     static_assert(TW <= 256 && TH <= 256, "TMA box dimension limit");
 };
 
-template <class C>
+template <class C, bool LIST>
 __global__ void __launch_bounds__(C::NT, 1)
 k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, double om,
-            int ghost_period, int tiles_x, int ntiles, const uint32_t *__restrict__ tile_list,
-            const int *__restrict__ stop)
+            int tiles_x, int ntiles, const uint32_t *__restrict__ tile_list, const int *__restrict__ stop)
 {
     constexpr int T = C::T, TE = C::TE, PX = C::PX, PY = C::PY, TW = C::TW, TH = C::TH, OW = C::OW, OH = C::OH;
-    constexpr int PW = C::PLANE_W, CW = C::CW;
+    constexpr int PW = C::PLANE_W, IW = C::IW;
     if (stop && *stop) return;
 
     // No integer round trip on the base pointer: the compiler must keep seeing the shared
@@ -136,29 +135,29 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
 
     const CUtensorMap *map_in = &maps.x_load[src];
     const CUtensorMap *map_out = &maps.x_store[src ^ 1];
-    constexpr uint32_t TX_BYTES = (uint32_t)(C::IN_BYTES + (size_t)CW * TH);
+    constexpr uint32_t TX_BYTES = (uint32_t)(C::IN_BYTES + (size_t)IW * TH * 2);
 
     // interior-coordinate origin of the OUTPUT box of tile t: the whole tile grid, or -- packed
     // batches and slab boundary/interior splits -- the entries of an explicit tile list
     auto tile_origin = [&](int t, int &ox, int &oy) {
         int tx, ty;
-        if (tile_list) { const uint32_t v = __ldg(tile_list + t); tx = (int)(v & 0xffffu); ty = (int)(v >> 16); }
+        if constexpr (LIST) { const uint32_t v = __ldg(tile_list + t); tx = (int)(v & 0xffffu); ty = (int)(v >> 16); }
         else { ty = t / tiles_x; tx = t - ty * tiles_x; }
         ox = tx * OW; oy = ty * OH;
     };
     auto issue_load = [&](int t, int b) {
         int ox, oy;
         tile_origin(t, ox, oy);
-        org[2 * b] = ox; org[2 * b + 1] = oy;            // released to the consumers by the arrive below
+        if constexpr (LIST) { org[2 * b] = ox; org[2 * b + 1] = oy; }   // released to the consumers by the arrive below
         mbar_expect_tx(&bar[b], TX_BYTES);
         // padded coordinates of the input box: interior (ox-TE, oy-T) -> (+XOFF, +1); even
         const int xs = ox - TE + DEFF2D_XOFF;
         tma_load_2d(IN0 + b * C::CELLS, map_in, xs, oy - T + 1, &bar[b]);
-        tma_load_2d(CODE0 + b * C::CODE_BYTES, &maps.code, xs & ~15, oy - T + 1, &bar[b]);
+        tma_load_2d(CODE0 + b * C::CODE_BYTES, &maps.idx, xs & ~7, oy - T + 1, &bar[b]);
     };
 
     if (tid == 0) {
-        prefetch_tmap(map_in); prefetch_tmap(map_out); prefetch_tmap(&maps.code);
+        prefetch_tmap(map_in); prefetch_tmap(map_out); prefetch_tmap(&maps.idx);
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         fence_barrier_init();
@@ -185,10 +184,14 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         double x[PY][PX];
         double w[PY][PX][4];
         double omc[PX];
-        const int ox = org[2 * b], oy = org[2 * b + 1];
+        int ox, oy;
+        if constexpr (LIST) { ox = org[2 * b]; oy = org[2 * b + 1]; }      // one global read per tile (thread 0), not 256
+        else tile_origin(tile, ox, oy);
         {
             const double *in = IN0 + b * C::CELLS;
-            const uint8_t *cd = CODE0 + b * C::CODE_BYTES + ((ox - TE + DEFF2D_XOFF) & 15);
+            // table index of every cell of the patch: precomputed per cell (k_build_idx, kernels.cu),
+            // bits 0-10 phase neighbourhood, 11-14 continuation stage, 15 "Dirichlet ghost column"
+            const uint16_t *id = reinterpret_cast<const uint16_t *>(CODE0 + b * C::CODE_BYTES) + ((ox - TE + DEFF2D_XOFF) & 7);
 #pragma unroll
             for (int py = 0; py < PY; py++) {
                 if constexpr (PX % 2 == 0) {       // 16-byte loads: conflict-free for PX == 2
@@ -202,41 +205,35 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
                     for (int px = 0; px < PX; px++) x[py][px] = in[(r0 + py) * TW + c0 + px];
                 }
             }
-            // phase codes of the (PY+2) x (PX+2) neighbourhood, clamped at the tile edge
-            unsigned cc[PY + 2][PX + 2];
-#pragma unroll
-            for (int py = 0; py < PY + 2; py++) {
-                int r = r0 + py - 1;
-                r = r < 0 ? 0 : (r > TH - 1 ? TH - 1 : r);
-#pragma unroll
-                for (int px = 0; px < PX + 2; px++) {
-                    int c = c0 + px - 1;
-                    c = c < 0 ? 0 : (c > TW - 1 ? TW - 1 : c);
-                    cc[py][px] = cd[r * CW + c];
-                }
-            }
-            {
-                // a Dirichlet ghost column (column -1 or Nx of the domain; in a packed batch every
-                // (Nx+1)-th column separates two images) keeps its value: its weights are 0
-                // (LUT, p == 3) and its (1-omega) factor is 1
-#pragma unroll
-                for (int px = 0; px < PX; px++) {
-                    const int jg = ox - TE + c0 + px;
-                    omc[px] = ((jg + 1) % ghost_period == 0) ? 1.0 : om;
-                }
-            }
             unsigned idx[PY][PX];
             bool uniform = true;
+            unsigned first = 0;
+#pragma unroll
+            for (int py = 0; py < PY; py++) {
+                const uint32_t *p32 = reinterpret_cast<const uint32_t *>(id + (r0 + py) * IW + c0);   // 4-byte aligned: c0, TE, XOFF even
+#pragma unroll
+                for (int px = 0; px < PX; px += 2) {
+                    const uint32_t u = p32[px >> 1];
+                    if (py == 0 && px == 0) first = (u & 0xffffu) * 0x10001u;
+                    uniform = uniform && (u == first);
+                    idx[py][px] = u & 0xffffu;
+                    idx[py][px + 1] = u >> 16;
+                }
+            }
+            // a Dirichlet ghost column (column -1 or Nx of the domain; in a packed batch every
+            // (Nx+1)-th column separates two images) keeps its value: its weights are 0 (LUT,
+            // p == 3) and its (1-omega) factor is 1
+#pragma unroll
+            for (int px = 0; px < PX; px++) {
+                unsigned any = 0;
+#pragma unroll
+                for (int py = 0; py < PY; py++) any |= idx[py][px];
+                omc[px] = (any & 0x8000u) ? 1.0 : om;
+            }
 #pragma unroll
             for (int py = 0; py < PY; py++)
 #pragma unroll
-                for (int px = 0; px < PX; px++) {
-                    const unsigned c = cc[py + 1][px + 1];
-                    idx[py][px] = (c & 3u) | ((cc[py + 1][px] & 3u) << 2) | ((cc[py + 1][px + 2] & 3u) << 4) |
-                                  ((cc[py + 2][px + 1] & 3u) << 6) | ((cc[py][px + 1] & 3u) << 8) | ((c & 4u) << 8) |
-                                  ((c >> 3) << 11);          // bits 3-7: continuation stage of the image (packed batches)
-                    uniform = uniform && (idx[py][px] == idx[0][0]);
-                }
+                for (int px = 0; px < PX; px++) idx[py][px] &= 0x7fffu;
             // Most patches lie inside one phase (every cell has the same neighbourhood index):
             // one LUT entry then serves all PX*PY cells -- 2 instead of 2*PX*PY 16-byte loads.
             // The LSU data pipe is the busiest unit of this kernel (ncu: ~80 % of peak).
@@ -374,7 +371,7 @@ struct TmaState {
     int ow = 0, oh = 0, tiles_x = 0, tiles_y = 0;
     void *key_x0 = nullptr, *key_x1 = nullptr, *key_code = nullptr;
     int64_t key_Nx = 0, key_Ny = 0, key_pitch = 0;
-    bool attr_set[3][17] = {{false}};
+    bool attr_set[2][3][17] = {{{false}}};
     int cfg_F = -1;
     int max_smem_optin = 0;
 };
@@ -411,19 +408,18 @@ template <int T, int F>
 static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, int count, cudaStream_t stream)
 {
     using C = typename Family<T, F>::type;
-    auto kern = k_sweep_tma<C>;
-    if (!ts->attr_set[F][T]) {
+    auto kern = list ? k_sweep_tma<C, true> : k_sweep_tma<C, false>;
+    if (!ts->attr_set[list ? 1 : 0][F][T]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
         if (e != cudaSuccess) { set_error(c, "cudaFuncSetAttribute(smem %zu) failed: %s", C::SMEM, cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
-        ts->attr_set[F][T] = true;
+        ts->attr_set[list ? 1 : 0][F][T] = true;
     }
     const int ntiles = list ? count : ts->tiles_x * ts->tiles_y;
     if (ntiles < 1) return DEFF2D_OK;
     int grid = c->prop.multiProcessorCount;
     if (c->grid_limit > 0 && grid > c->grid_limit) grid = c->grid_limit;
     if (grid > ntiles) grid = ntiles;
-    kern<<<grid, C::NT, C::SMEM, stream>>>(ts->maps, src, c->lut.p, 1.0 - c->omega, (int)c->ghost_period, ts->tiles_x, ntiles,
-                                           list, nullptr);
+    kern<<<grid, C::NT, C::SMEM, stream>>>(ts->maps, src, c->lut.p, 1.0 - c->omega, ts->tiles_x, ntiles, list, nullptr);
     return DEFF2D_OK;
 }
 
@@ -432,7 +428,7 @@ static int prepare_T(deff2d_ctx *c, TmaState *ts)
 {
     using C = typename Family<T, F>::type;
     if ((int)C::SMEM > ts->max_smem_optin) { set_error(c, "tile needs %zu B smem > %d", C::SMEM, ts->max_smem_optin); return DEFF2D_ERR_STATE; }
-    const bool same = ts->cfg_T == T && ts->cfg_F == F && ts->key_x0 == c->x[0].p && ts->key_x1 == c->x[1].p && ts->key_code == c->code.p &&
+    const bool same = ts->cfg_T == T && ts->cfg_F == F && ts->key_x0 == c->x[0].p && ts->key_x1 == c->x[1].p && ts->key_code == c->idx16.p &&
                       ts->key_Nx == c->Nx && ts->key_Ny == c->Ny && ts->key_pitch == c->pitch;
     if (same) return DEFF2D_OK;
     int rc;
@@ -443,14 +439,15 @@ static int prepare_T(deff2d_ctx *c, TmaState *ts)
                             c->x[b].p + c->pitch + DEFF2D_XOFF, (uint64_t)c->Nx, (uint64_t)c->Ny, (uint64_t)c->pitch * 8,
                             C::OW, C::OH))) return rc;
     }
-    if ((rc = encode_2d(c, ts, &ts->maps.code, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, c->code.p, (uint64_t)c->pitch,
-                        (uint64_t)c->rows, (uint64_t)c->pitch, C::CW, C::TH))) return rc;
+    if (!c->idx16.p) { set_error(c, "tiled sweep: the per-cell table indices have not been built"); return DEFF2D_ERR_STATE; }
+    if ((rc = encode_2d(c, ts, &ts->maps.idx, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, c->idx16.p, (uint64_t)c->pitch,
+                        (uint64_t)c->rows, (uint64_t)c->pitch * 2, C::IW, C::TH))) return rc;
     ts->cfg_T = T;
     ts->cfg_F = F;
     ts->ow = C::OW; ts->oh = C::OH;
     ts->tiles_x = (int)((c->Nx + C::OW - 1) / C::OW);
     ts->tiles_y = (int)((c->Ny + C::OH - 1) / C::OH);
-    ts->key_x0 = c->x[0].p; ts->key_x1 = c->x[1].p; ts->key_code = c->code.p;
+    ts->key_x0 = c->x[0].p; ts->key_x1 = c->x[1].p; ts->key_code = c->idx16.p;
     ts->key_Nx = c->Nx; ts->key_Ny = c->Ny; ts->key_pitch = c->pitch;
     return DEFF2D_OK;
 }
