@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 #include <vector>
@@ -225,7 +226,7 @@ k_batch_check(BatchGeom g, BatchStages stages, BatchSlot *slots, BatchOut *outs,
             const long long i = k / g.Nx, j = k - i * g.Nx;
             const long long idx = (row0 + i + 1) * g.pitch + col0 + j + XOFF;
             code[idx] = (uint8_t)((code[idx] & 7u) | ((unsigned)rs << 3));
-            idx16[idx] = (uint16_t)((idx16[idx] & 0x87ffu) | ((unsigned)rs << 11));
+            idx16[idx] = (uint16_t)((idx16[idx] & 0xc3ffu) | ((unsigned)rs << 10));
         }
     }
 }
@@ -389,7 +390,9 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     int GX, GY;
     batch_plan(Nx, Ny, count, c->batch_max_slots, &GX, &GY);
     const int nslots = GX * GY;
-    const int T = 4;                                     // sweeps per HBM pass (profiles/: best measured depth)
+    int T = 6;                                           // sweeps per HBM pass: interface-rich small images amortise the
+                                                         // per-tile weight gather best at depth 6 (measured 424 / 436 / 452 / 422 GLUP/s at T = 4 / 5 / 6 / 8)
+    if (const char *e = std::getenv("DEFF2D_BATCH_T")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) T = v; }   // tuning
 
     // ---- FloodFill on host threads (cuh:557-713): PathFlag always, pinned mask in 3-phase -----------
     std::vector<int> pathflag((size_t)count, 0);
@@ -433,6 +436,7 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     c->pitch = ((c->Nx + 2 * XOFF) + 15) / 16 * 16;
     c->rows = c->Ny + 2;
     c->ghost_period = Nx + 1;
+    c->prefer_smem_lut = false;
     c->own_first = 0; c->own_rows = c->Ny;
     c->nphase = nphase;
     c->CL = p->CL; c->CR = p->CR;
@@ -458,7 +462,9 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
         (rc = grow(c->idx16, stack_cells))) return rc;
     if ((rc = grow(c->img, npix * count))) return rc;
     if (nphase == 3 && (rc = grow(c->grid, (size_t)cells * count))) return rc;
-    if ((rc = grow(c->lut, (size_t)nstages * DEFF2D_LUT_ENTRIES * 4)) || (rc = grow(c->dead, (size_t)nstages * DEFF2D_LUT_ENTRIES))) return rc;
+    if ((rc = grow(c->lut, (size_t)nstages * DEFF2D_LUT_ENTRIES * 4)) || (rc = grow(c->dead, (size_t)nstages * DEFF2D_LUT_ENTRIES)) ||
+        (rc = grow(c->clut, (size_t)nstages * DEFF2D_CLUT_ENTRIES * 4))) return rc;
+    c->lut_stages = nstages;
     if (fields && (rc = grow(c->dense, (size_t)cells))) return rc;
     if ((rc = dev_ensure(c, b->slots, (size_t)nslots)) || (rc = dev_ensure(c, b->outs, (size_t)count)) ||
         (rc = dev_ensure(c, b->jobs, (size_t)nslots)) || (rc = dev_ensure(c, b->active, (size_t)nslots))) return rc;
@@ -476,9 +482,13 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     {
         std::vector<double> lut((size_t)nstages * DEFF2D_LUT_ENTRIES * 4);
         std::vector<uint8_t> dead((size_t)nstages * DEFF2D_LUT_ENTRIES);
-        for (int k = 0; k < nstages; k++)
+        std::vector<double> clut((size_t)nstages * DEFF2D_CLUT_ENTRIES * 4);
+        for (int k = 0; k < nstages; k++) {
             build_tables(stages.s[k].D, Nx, Ny, c->CL, c->CR, c->omega, lut.data() + (size_t)k * DEFF2D_LUT_ENTRIES * 4,
                          dead.data() + (size_t)k * DEFF2D_LUT_ENTRIES);
+            compact_table(lut.data() + (size_t)k * DEFF2D_LUT_ENTRIES * 4, clut.data() + (size_t)k * DEFF2D_CLUT_ENTRIES * 4);
+        }
+        CUB(cudaMemcpyAsync(c->clut.p, clut.data(), clut.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         CUB(cudaMemcpyAsync(c->lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         CUB(cudaMemcpyAsync(c->dead.p, dead.data(), dead.size(), cudaMemcpyHostToDevice, s));
         CUB(cudaStreamSynchronize(s));

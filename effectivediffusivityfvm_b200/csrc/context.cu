@@ -79,8 +79,13 @@ static int upload_tables(deff2d_ctx *c)
     std::vector<uint8_t> dead(DEFF2D_LUT_ENTRIES);
     build_tables(c->Dphase, c->NxG, c->NyG, c->CL, c->CR, c->omega, lut.data(), dead.data());
     int rc;
+    std::vector<double> clut((size_t)DEFF2D_CLUT_ENTRIES * 4);
+    compact_table(lut.data(), clut.data());
     if ((rc = ensure(c, c->lut, lut.size()))) return rc;
+    if ((rc = ensure(c, c->clut, clut.size()))) return rc;
     if ((rc = ensure(c, c->dead, dead.size()))) return rc;
+    c->lut_stages = 1;
+    CU(cudaMemcpyAsync(c->clut.p, clut.data(), clut.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     // pageable source: the copy is staged before the call returns, the vectors may die
     CU(cudaMemcpyAsync(c->lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->dead.p, dead.data(), dead.size(), cudaMemcpyHostToDevice, c->stream));
@@ -182,6 +187,7 @@ static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc,
     c->rows = Ny + 2;
     c->ghost_period = Nx + 1;
     c->tile_list = nullptr; c->tile_count = 0;
+    c->prefer_smem_lut = (p->amp_x >= 2 && p->amp_y >= 2);
     c->own_first = own_first; c->own_rows = own_rows;
     c->nphase = nphase;
     c->CL = p->CL; c->CR = p->CR;
@@ -447,6 +453,7 @@ DEFF2D_EXPORT void deff2d_destroy(deff2d_ctx *c)
     if (c->img.p) cudaFree(c->img.p);
     if (c->grid.p) cudaFree(c->grid.p);
     if (c->lut.p) cudaFree(c->lut.p);
+    if (c->clut.p) cudaFree(c->clut.p);
     if (c->dead.p) cudaFree(c->dead.p);
     if (c->dense.p) cudaFree(c->dense.p);
     if (c->dense8.p) cudaFree(c->dense8.p);

@@ -119,7 +119,7 @@ void launch_init_domain(cudaStream_t s, const uint8_t *img, int W, int Hsrc, int
 }
 
 // ------------------------------------------------------------------------------------------
-// build_idx: the weight-table index of every padded cell (bits 0-10), its stage (11-14, from
+// build_idx: the compact weight-table index of every padded cell (bits 0-9), its stage (10-13, from
 // code bits 3-6) and the ghost-column flag (15).  One thread per 8 cells of a row, one 16-byte
 // store.  Runs once per image load; the tiled sweep then reads 2 B per cell instead of
 // recomputing the index from 5 code bytes per cell per pass.
@@ -145,8 +145,13 @@ k_build_idx(const uint8_t *__restrict__ code, uint16_t *__restrict__ idx16, long
             const long long c = c0 + k;
             const unsigned next = (c + 1 < pitch) ? row[c + 1] : 3u;
             const unsigned n = up ? up[c] : 3u, s = dn ? dn[c] : 3u;
-            unsigned v = (cur & 3u) | ((prev & 3u) << 2) | ((next & 3u) << 4) | ((s & 3u) << 6) | ((n & 3u) << 8) |
-                         ((cur & 4u) << 8) | (((cur >> 3) & 15u) << 11);
+            // compact table index (tables.cpp: compact_table): p*256 + pW | pE<<2 | pS<<4 | pN<<6, or the
+            // inert entry 768 for ghost and pinned cells; stage in bits 10-13
+            unsigned v = 768u;
+            if ((cur & 3u) != 3u && !(cur & 4u))
+                v = ((cur & 3u) << 8) | (prev & 3u) | ((next & 3u) << 2) | ((s & 3u) << 4) | ((n & 3u) << 6);
+            v = DEFF2D_CLUT_SLOT(v);
+            v |= ((cur >> 3) & 15u) << 10;
             const long long j = c - XOFF;                      // interior column
             if (j >= -1 && j <= Nx && (j + 1) % period == 0) v |= 0x8000u;
             out[k] = v;

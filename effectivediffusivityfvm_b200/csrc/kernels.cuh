@@ -7,9 +7,10 @@
 //          ghost rows (weight 0).  pitch is a multiple of 16 doubles (128 B rows, TMA needs 16 B).
 //   code   one byte per cell in the same padded geometry (pitch bytes per row):
 //          bits 0-1 phase (0 fluid, 1 solid, 2 gas, 3 ghost), bit 2 pinned (3-phase Grid in {1,2}).
-//   idx16  two bytes per cell, same geometry, derived from `code` (k_build_idx): bits 0-10 the
-//          weight-table index p | pW<<2 | pE<<4 | pS<<6 | pN<<8 | pinned<<10 of the cell, bits 11-14
-//          its continuation stage, bit 15 "Dirichlet ghost column".  Read by the tiled sweep (K2).
+//   idx16  two bytes per cell, same geometry, derived from `code` (k_build_idx): bits 0-9 the
+//          compact weight-table index p*256 + (pW | pE<<2 | pS<<4 | pN<<6) of the cell (768: ghost or
+//          pinned), bits 10-13 its continuation stage, bit 15 "Dirichlet ghost column".  Read by
+//          the tiled sweep (K2) together with `clut`, the compact form of `lut`.
 //   lut    2048 x 4 doubles: sweep weights for every (p, pW, pE, pS, pN, pinned), per stage.
 // The reference's A[n][5] + b[n] (48 B/cell, cuh:1396-1397) are never materialised.
 #pragma once

@@ -102,13 +102,21 @@ struct Cfg {
     static constexpr size_t OFF_OUT = OFF_P + 2 * IN_BYTES;       // OUT: dense OW x OH box for the bulk store
     static constexpr size_t OUT_BYTES = ((size_t)OW * OH * 8 + 127) / 128 * 128;
     static constexpr size_t OFF_CODE = OFF_OUT + OUT_BYTES;       // CODE[2]
-    static constexpr size_t OFF_BAR = OFF_CODE + 2 * CODE_BYTES;  // 2 mbarriers
+    static constexpr size_t OFF_BAR = OFF_CODE + 2 * CODE_BYTES;  // 2 mbarriers + tile origins
+    static constexpr size_t OFF_LUT = OFF_BAR + 128;              // compact weight table of the stage (SLUT kernels)
+    static constexpr size_t LUT_BYTES = (size_t)DEFF2D_CLUT_USED * 32;
     static constexpr size_t SMEM = OFF_BAR + 64 + 128;            // + alignment slack
+    static constexpr size_t SMEM_SLUT = OFF_LUT + LUT_BYTES + 128;
     static_assert(OW > 0 && OH > 0, "tile too small for this temporal depth");
     static_assert(TW <= 256 && TH <= 256, "TMA box dimension limit");
 };
 
-template <class C, bool LIST>
+// LIST: walk an explicit tile list.  SLUT: every image is in the same continuation stage, so the
+// stage's compact weight table (24 KB) can be staged in shared memory once per CTA.  Measured:
+// +2 % on mesh-amplified domains (most patches single-phase, one broadcast read per patch),
+// -4 % on interface-rich media (per-cell gathers cost about the same through L1) -- chosen per
+// domain by the context (prefer_smem_lut).
+template <class C, bool LIST, bool SLUT>
 __global__ void __launch_bounds__(C::NT, 1)
 k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, double om,
             int tiles_x, int ntiles, const uint32_t *__restrict__ tile_list, const int *__restrict__ stop)
@@ -164,6 +172,14 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     }
     __syncthreads();
     int tile = blockIdx.x;
+    const double *wtab = lut;
+    if constexpr (SLUT) {
+        double *sl = reinterpret_cast<double *>(smem + C::OFF_LUT);
+        for (int k = tid; k < DEFF2D_CLUT_USED * 2; k += C::NT)
+            reinterpret_cast<double2 *>(sl)[k] = __ldg(reinterpret_cast<const double2 *>(lut) + k);
+        wtab = sl;
+        __syncthreads();
+    }
     if (tid == 0) {
         if (tile < ntiles) issue_load(tile, 0);
         if (tile + (int)gridDim.x < ntiles) issue_load(tile + gridDim.x, 1);
@@ -233,13 +249,15 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
 #pragma unroll
             for (int py = 0; py < PY; py++)
 #pragma unroll
-                for (int px = 0; px < PX; px++) idx[py][px] &= 0x7fffu;
+                for (int px = 0; px < PX; px++) idx[py][px] &= SLUT ? 0x3ffu : 0x3fffu;     // SLUT: one stage
             // Most patches lie inside one phase (every cell has the same neighbourhood index):
             // one LUT entry then serves all PX*PY cells -- 2 instead of 2*PX*PY 16-byte loads.
             // The LSU data pipe is the busiest unit of this kernel (ncu: ~80 % of peak).
-            if (uniform) {
-                const double2 *lp = reinterpret_cast<const double2 *>(lut + (size_t)idx[0][0] * 4);
-                const double2 a = __ldg(lp), bb = __ldg(lp + 1);
+            // warp-wide decision: a mixed warp would execute both paths
+            if (__all_sync(0xffffffffu, uniform)) {
+                const double2 *lp = reinterpret_cast<const double2 *>(wtab + (size_t)idx[0][0] * 4);
+                double2 a, bb;
+                if constexpr (SLUT) { a = lp[0]; bb = lp[1]; } else { a = __ldg(lp); bb = __ldg(lp + 1); }
 #pragma unroll
                 for (int py = 0; py < PY; py++)
 #pragma unroll
@@ -251,8 +269,9 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
                 for (int py = 0; py < PY; py++)
 #pragma unroll
                     for (int px = 0; px < PX; px++) {
-                        const double2 *lp = reinterpret_cast<const double2 *>(lut + (size_t)idx[py][px] * 4);
-                        const double2 a = __ldg(lp), bb = __ldg(lp + 1);
+                        const double2 *lp = reinterpret_cast<const double2 *>(wtab + (size_t)idx[py][px] * 4);
+                        double2 a, bb;
+                        if constexpr (SLUT) { a = lp[0]; bb = lp[1]; } else { a = __ldg(lp); bb = __ldg(lp + 1); }
                         w[py][px][0] = a.x; w[py][px][1] = a.y; w[py][px][2] = bb.x; w[py][px][3] = bb.y;
                     }
             }
@@ -371,7 +390,7 @@ struct TmaState {
     int ow = 0, oh = 0, tiles_x = 0, tiles_y = 0;
     void *key_x0 = nullptr, *key_x1 = nullptr, *key_code = nullptr;
     int64_t key_Nx = 0, key_Ny = 0, key_pitch = 0;
-    bool attr_set[2][3][17] = {{{false}}};
+    bool attr_set[4][3][17] = {{{false}}};
     int cfg_F = -1;
     int max_smem_optin = 0;
 };
@@ -408,18 +427,22 @@ template <int T, int F>
 static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, int count, cudaStream_t stream)
 {
     using C = typename Family<T, F>::type;
-    auto kern = list ? k_sweep_tma<C, true> : k_sweep_tma<C, false>;
-    if (!ts->attr_set[list ? 1 : 0][F][T]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) { set_error(c, "cudaFuncSetAttribute(smem %zu) failed: %s", C::SMEM, cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
-        ts->attr_set[list ? 1 : 0][F][T] = true;
+    const bool slut = c->prefer_smem_lut && (c->lut_stages == 1) && ((int)C::SMEM_SLUT <= ts->max_smem_optin);
+    auto kern = list ? (slut ? k_sweep_tma<C, true, true> : k_sweep_tma<C, true, false>)
+                     : (slut ? k_sweep_tma<C, false, true> : k_sweep_tma<C, false, false>);
+    const size_t smem = slut ? C::SMEM_SLUT : C::SMEM;
+    const int variant = (list ? 1 : 0) + (slut ? 2 : 0);
+    if (!ts->attr_set[variant][F][T]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error(c, "cudaFuncSetAttribute(smem %zu) failed: %s", smem, cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
+        ts->attr_set[variant][F][T] = true;
     }
     const int ntiles = list ? count : ts->tiles_x * ts->tiles_y;
     if (ntiles < 1) return DEFF2D_OK;
     int grid = c->prop.multiProcessorCount;
     if (c->grid_limit > 0 && grid > c->grid_limit) grid = c->grid_limit;
     if (grid > ntiles) grid = ntiles;
-    kern<<<grid, C::NT, C::SMEM, stream>>>(ts->maps, src, c->lut.p, 1.0 - c->omega, ts->tiles_x, ntiles, list, nullptr);
+    kern<<<grid, C::NT, smem, stream>>>(ts->maps, src, c->clut.p, 1.0 - c->omega, ts->tiles_x, ntiles, list, nullptr);
     return DEFF2D_OK;
 }
 

@@ -96,6 +96,15 @@ void build_tables(const double Dphase[3], int64_t Nx, int64_t Ny, double CL, dou
     }
 }
 
+void compact_table(const double *lut, double *clut)
+{
+    std::memset(clut, 0, sizeof(double) * 4 * DEFF2D_CLUT_ENTRIES);
+    for (int p = 0; p < 3; p++)
+        for (int n8 = 0; n8 < 256; n8++)
+            std::memcpy(clut + (size_t)DEFF2D_CLUT_SLOT((unsigned)(p * 256 + n8)) * 4, lut + (size_t)(p | (n8 << 2)) * 4,
+                        4 * sizeof(double));
+}
+
 }  // namespace deff2d
 
 DEFF2D_EXPORT int deff2d_build_tables(double Ds, double Df, double Dg, int64_t Nx, int64_t Ny, double CL,
