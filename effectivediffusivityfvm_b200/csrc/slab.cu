@@ -21,6 +21,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -254,6 +255,7 @@ DEFF2D_EXPORT int deff2d_nccl_init(deff2d_ctx *c, const uint8_t id[DEFF2D_NCCL_I
     SlabState *s = new SlabState();
     c->slab = s;
     s->rank = rank; s->nranks = nranks;
+    if (const char *e = std::getenv("DEFF2D_SLAB_RESERVE_SMS")) { const int v = std::atoi(e); if (v >= 0 && v <= 64) s->reserve_sms = v; }   // tuning
     CUS(cudaSetDevice(c->device));
     CUS(cudaEventCreateWithFlags(&s->evA, cudaEventDisableTiming));
     CUS(cudaEventCreateWithFlags(&s->evC, cudaEventDisableTiming));

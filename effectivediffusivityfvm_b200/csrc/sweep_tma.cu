@@ -278,12 +278,16 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         }
 
         // ---- publish the patch boundary of level 0 ----------------------------------------
+        // XSHFL (one warp spans the tile width): the W / E halo comes from the neighbouring lanes by
+        // warp shuffles, so only the top and bottom patch rows go through shared memory
+        constexpr bool XSHFL = (C::NWX == 1);
         auto publish = [&](double *pb) {
 #pragma unroll
             for (int py = 0; py < PY; py++)
 #pragma unroll
                 for (int px = 0; px < PX; px++) {
-                    const bool edge = (px == 0) || (px == PX - 1) || (py == 0) || (py == PY - 1);
+                    const bool edge = XSHFL ? ((py == 0) || (py == PY - 1))
+                                            : ((px == 0) || (px == PX - 1) || (py == 0) || (py == PY - 1));
                     if (edge) pb[(px * TH + r0 + py) * PW + g] = x[py][px];
                 }
         };
@@ -306,8 +310,14 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
             double hW[PY], hE[PY], hN[PX], hS[PX];
 #pragma unroll
             for (int py = 0; py < PY; py++) {
-                hW[py] = pr[((PX - 1) * TH + r0 + py) * PW + gW];
-                hE[py] = pr[(0 * TH + r0 + py) * PW + gE];
+                if constexpr (XSHFL) {
+                    // lanes 0 / 31 sit on the tile edge: they get their own value back (halo garbage, never stored)
+                    hW[py] = __shfl_up_sync(0xffffffffu, x[py][PX - 1], 1);
+                    hE[py] = __shfl_down_sync(0xffffffffu, x[py][0], 1);
+                } else {
+                    hW[py] = pr[((PX - 1) * TH + r0 + py) * PW + gW];
+                    hE[py] = pr[(0 * TH + r0 + py) * PW + gE];
+                }
             }
 #pragma unroll
             for (int px = 0; px < PX; px++) {
