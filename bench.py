@@ -250,7 +250,8 @@ def run_ours(args):
         step()
     barrier()
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if not args.no_clock_sampler:
+        sampler.start()
     l0 = ctx.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
@@ -262,7 +263,7 @@ def run_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = ctx.kernel_launches - l0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if not args.no_clock_sampler else {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled"]}
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -359,6 +360,7 @@ def main():
     ap.add_argument("--ref-cuda-sweeps", type=int, default=1001)
     ap.add_argument("--batch-images", type=int, default=0, help="also time the packed batch mode on this many config-3 images per GPU")
     ap.add_argument("--allow-short-warmup", action="store_true")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not poll NVML during the timed region")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

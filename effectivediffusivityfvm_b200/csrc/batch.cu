@@ -584,11 +584,10 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
         }
         if (n < 1) { restore(); set_error(c, "packed batch: internal scheduling error"); return DEFF2D_ERR_STATE; }
         CUB(cudaEventRecord(b->e0, s));
-        for (long long left = n; left > 0;) {
-            const int t = (int)std::min<long long>(left, T);
+        if (n >= T && (rc = tma_passes(c, T, n / T, b->tiles.p + tile_off[T], tile_cnt[T]))) { restore(); return rc; }
+        if (const int t = (int)(n % T)) {
             if ((rc = tma_pass(c, t, b->tiles.p + tile_off[t], tile_cnt[t], s))) { restore(); return rc; }
             c->cur ^= 1;
-            left -= t;
         }
         k_batch_check<<<nactive, 1024, 0, s>>>(g, stages, b->slots.p, b->outs.p, b->active.p, n, c->x[c->cur].p, c->code.p, c->idx16.p);
         c->launches++;

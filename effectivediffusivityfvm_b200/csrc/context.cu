@@ -99,12 +99,15 @@ static int enqueue_sweeps(deff2d_ctx *c, int64_t n)
     if (c->slab && c->slab_domain) return slab_enqueue_sweeps(c, n);
     while (n > 0) {
         int64_t done = 0;
-        // kernel 0 (default): the TMA tiled kernel (4x4 patches, 4 sweeps per HBM pass -- the
-        // fastest measured configuration, profiles/) once the domain fills the machine with
-        // tiles; the streaming kernel for small domains.
-        const bool big = c->Nx >= 512 && c->Ny >= 128 && c->Nx * c->Ny >= (int64_t)1 << 21;
-        if (c->kernel == 2 || (c->kernel == 0 && big)) {
-            if (c->kernel == 0) { c->tile_family = 1; c->tblock = 4; }
+        // kernel 0 (default): the TMA tiled kernel from 4096 cells up.  Depth by size (measured,
+        // profiles/): 4 sweeps per pass where HBM traffic matters (>= 16 M cells), 6 in between,
+        // 8 on small domains, which are bound by per-pass latency; tiny domains stream (K3).
+        const int64_t ncell = c->Nx * c->Ny;
+        if (c->kernel == 2 || (c->kernel == 0 && ncell >= 4096)) {
+            if (c->kernel == 0) {
+                c->tile_family = 1;
+                c->tblock = ncell >= ((int64_t)1 << 24) ? 4 : (ncell >= ((int64_t)1 << 20) ? 6 : 8);
+            }
             int rc = launch_sweep_tma(c, n, &done);
             if (rc) return rc;
         }

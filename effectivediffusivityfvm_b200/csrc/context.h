@@ -70,6 +70,7 @@ struct deff2d_ctx {
     int floodfill_mode = 0;          // 0 auto (device for >= 64 K cells), 1 host, 2 device
     int floodfill_passes = 0;        // device passes of the last FloodFill (diagnostic)
 
+    bool use_graphs = true;          // replay long runs of passes as CUDA graphs (sweep_tma.cu: tma_passes)
     int grid_limit = 0;              // > 0: cap on the CTAs of a tiled pass (slab mode leaves SMs to NCCL)
 
     // multi-GPU slab state (slab.cu)
@@ -91,6 +92,8 @@ int solve_image_impl(deff2d_ctx *c, const uint8_t *gray, int W, int H, const def
 int launch_sweep_tma(deff2d_ctx *c, int64_t n, int64_t *done);
 // one pass of depth T over an explicit tile list on `stream`, without flipping c->cur
 int tma_pass(deff2d_ctx *c, int T, const uint32_t *list, int count, cudaStream_t stream);
+// npasses passes of depth T on c->stream, flipping c->cur after each (CUDA graphs for long runs)
+int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int count);
 void tma_tile_geometry(const deff2d_ctx *c, int T, int *ow, int *oh);
 void tma_destroy(deff2d_ctx *c);
 

@@ -68,8 +68,20 @@ static NcclApi *nccl_api()
     return &api;
 }
 
+struct SlabGraph {
+    cudaGraphExec_t exec = nullptr;
+    int T = 0, launches = 0;
+    const void *x0 = nullptr, *x1 = nullptr, *idx = nullptr, *lut = nullptr;
+    double omega = 0;
+    uint64_t lists = 0;
+    bool slut = false;
+};
+
 struct SlabState {
     ncclComm_t comm = nullptr;
+    SlabGraph graph[2];           // one per parity of c->cur at the start of the run
+    bool use_graphs = true;
+    uint64_t lists_version = 0;
     int rank = 0, nranks = 1;
     cudaEvent_t evA = nullptr, evC = nullptr;
     // per pass depth T (1..8): boundary and interior tile lists (device), built lazily per domain
@@ -79,7 +91,7 @@ struct SlabState {
     bool lists_ready = false;
     int64_t key_Nx = 0, key_Ny = 0, key_above = -1, key_below = -1, key_own = -1;
     int key_family = -1;
-    int reserve_sms = 4;          // SMs the interior launch leaves to the NCCL kernel
+    int reserve_sms = 0;          // SMs the interior launch leaves to the NCCL kernel (measured best on 2 GPUs: 0)
 };
 
 #define NCCLCHECK(call)                                                                      \
@@ -144,11 +156,56 @@ static int build_lists(deff2d_ctx *c, SlabState *s)
     s->key_Nx = c->Nx; s->key_Ny = c->Ny; s->key_above = c->halo_above; s->key_below = c->halo_below;
     s->key_own = c->own_rows; s->key_family = c->tile_family;
     s->lists_ready = true;
+    s->lists_version++;
     return DEFF2D_OK;
 }
 
-// n sweeps on a slab: passes of depth T = min(tblock, halo rows) with a halo exchange after
-// each.  Enqueue only.
+// One pass of depth T on a slab incl. the halo exchange; flips c->cur.  Enqueue only (also used
+// under stream capture).
+static int slab_pass(deff2d_ctx *c, SlabState *s, NcclApi *api, int T)
+{
+    const int64_t H = std::max(c->halo_above, c->halo_below);
+    const bool up = c->halo_above > 0, down = c->halo_below > 0;
+    const size_t count = (size_t)H * (size_t)c->pitch;            // doubles per halo block (whole padded rows)
+    int rc;
+    // boundary tiles first, then the exchange overlaps the interior tiles
+    if ((rc = tma_pass(c, T, s->tiles.p + s->off_b[T], s->cnt_b[T], c->stream))) return rc;
+    if (up || down) {
+        CUS(cudaEventRecord(s->evA, c->stream));
+        CUS(cudaStreamWaitEvent(c->comm_stream, s->evA, 0));
+    }
+    c->grid_limit = (up || down) && s->reserve_sms > 0 ? c->prop.multiProcessorCount - s->reserve_sms : 0;
+    rc = tma_pass(c, T, s->tiles.p + s->off_i[T], s->cnt_i[T], c->stream);
+    c->grid_limit = 0;
+    if (rc) return rc;
+    if (up || down) {
+        double *dst = c->x[c->cur ^ 1].p;                      // the buffer this pass wrote
+        NCCLCHECK(api->GroupStart());
+        if (up) {
+            // own top H rows -> upper neighbour's lower halo; its bottom H own rows -> my upper halo
+            NCCLCHECK(api->Send(dst + (size_t)(1 + c->halo_above) * c->pitch, count, ncclDouble, s->rank - 1, s->comm, c->comm_stream));
+            NCCLCHECK(api->Recv(dst + (size_t)(1 + c->halo_above - H) * c->pitch, count, ncclDouble, s->rank - 1, s->comm, c->comm_stream));
+        }
+        if (down) {
+            const size_t last_own = (size_t)(1 + c->halo_above + c->own_rows);    // padded row after the last own row
+            NCCLCHECK(api->Send(dst + (last_own - (size_t)H) * c->pitch, count, ncclDouble, s->rank + 1, s->comm, c->comm_stream));
+            NCCLCHECK(api->Recv(dst + last_own * c->pitch, count, ncclDouble, s->rank + 1, s->comm, c->comm_stream));
+        }
+        NCCLCHECK(api->GroupEnd());
+        CUS(cudaEventRecord(s->evC, c->comm_stream));
+        CUS(cudaStreamWaitEvent(c->stream, s->evC, 0));
+        c->launches++;                                         // the NCCL send/recv kernel
+    }
+    c->cur ^= 1;
+    return DEFF2D_OK;
+}
+
+#define SLAB_GRAPH_PASSES 16
+
+// n sweeps on a slab: passes of depth T = min(tblock, halo rows) with a halo exchange after each.
+// Runs of SLAB_GRAPH_PASSES passes -- kernels, events and the NCCL send/recv pairs -- are captured
+// once into a CUDA graph and replayed: per pass the host otherwise issues two launches, four
+// event operations and an NCCL group (measured: the host then falls behind the GPU).  Enqueue only.
 int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
 {
     SlabState *s = static_cast<SlabState *>(c->slab);
@@ -164,39 +221,42 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
     if (c->kernel == 0) Tmax = 4;
     if (Tmax > 8) Tmax = 8;
     if (s->nranks > 1 && Tmax > H) Tmax = (int)H;
-    const bool up = c->halo_above > 0, down = c->halo_below > 0;
-    const size_t count = (size_t)H * (size_t)c->pitch;            // doubles per halo block (whole padded rows)
-    while (n > 0) {
+    while (n > 0 && !rc) {
         const int T = (int)std::min<int64_t>(n, Tmax);
-        // boundary tiles first, then the exchange overlaps the interior tiles
-        if ((rc = tma_pass(c, T, s->tiles.p + s->off_b[T], s->cnt_b[T], c->stream))) break;
-        if (up || down) {
-            CUS(cudaEventRecord(s->evA, c->stream));
-            CUS(cudaStreamWaitEvent(c->comm_stream, s->evA, 0));
-        }
-        c->grid_limit = (up || down) ? c->prop.multiProcessorCount - s->reserve_sms : 0;
-        rc = tma_pass(c, T, s->tiles.p + s->off_i[T], s->cnt_i[T], c->stream);
-        c->grid_limit = 0;
-        if (rc) break;
-        if (up || down) {
-            double *dst = c->x[c->cur ^ 1].p;                      // the buffer this pass wrote
-            NCCLCHECK(api->GroupStart());
-            if (up) {
-                // own top H rows -> upper neighbour's lower halo; its bottom H own rows -> my upper halo
-                NCCLCHECK(api->Send(dst + (size_t)(1 + c->halo_above) * c->pitch, count, ncclDouble, s->rank - 1, s->comm, c->comm_stream));
-                NCCLCHECK(api->Recv(dst + (size_t)(1 + c->halo_above - H) * c->pitch, count, ncclDouble, s->rank - 1, s->comm, c->comm_stream));
+        if (c->use_graphs && s->use_graphs && n >= (int64_t)T * SLAB_GRAPH_PASSES) {
+            SlabGraph &g = s->graph[c->cur];
+            const bool valid = g.exec && g.T == T && g.x0 == c->x[0].p && g.x1 == c->x[1].p && g.idx == c->idx16.p &&
+                               g.lut == c->clut.p && g.omega == c->omega && g.lists == s->lists_version &&
+                               g.slut == (c->prefer_smem_lut && c->lut_stages == 1);
+            if (!valid) {
+                if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+                // one direct pass pair first: encodes the tensor maps outside the capture
+                if ((rc = slab_pass(c, s, api, T)) || (rc = slab_pass(c, s, api, T))) break;
+                n -= 2 * T;
+                if (n < (int64_t)T * SLAB_GRAPH_PASSES) continue;
+                cudaGraph_t graph = nullptr;
+                const int64_t launches0 = c->launches;
+                cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+                if (e != cudaSuccess) { set_error(c, "cudaStreamBeginCapture failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
+                for (int k = 0; k < SLAB_GRAPH_PASSES && !rc; k++) rc = slab_pass(c, s, api, T);
+                e = cudaStreamEndCapture(c->stream, &graph);
+                g.launches = (int)(c->launches - launches0);
+                c->launches = launches0;                           // nothing ran yet
+                if (rc) { if (graph) cudaGraphDestroy(graph); break; }
+                if (e != cudaSuccess || !graph) { set_error(c, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
+                e = cudaGraphInstantiate(&g.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (e != cudaSuccess) { g.exec = nullptr; set_error(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
+                g.T = T; g.x0 = c->x[0].p; g.x1 = c->x[1].p; g.idx = c->idx16.p; g.lut = c->clut.p; g.omega = c->omega;
+                g.lists = s->lists_version; g.slut = (c->prefer_smem_lut && c->lut_stages == 1);
             }
-            if (down) {
-                const size_t last_own = (size_t)(1 + c->halo_above + c->own_rows);    // padded row after the last own row
-                NCCLCHECK(api->Send(dst + (last_own - (size_t)H) * c->pitch, count, ncclDouble, s->rank + 1, s->comm, c->comm_stream));
-                NCCLCHECK(api->Recv(dst + last_own * c->pitch, count, ncclDouble, s->rank + 1, s->comm, c->comm_stream));
-            }
-            NCCLCHECK(api->GroupEnd());
-            CUS(cudaEventRecord(s->evC, c->comm_stream));
-            CUS(cudaStreamWaitEvent(c->stream, s->evC, 0));
-            c->launches++;                                         // the NCCL send/recv kernel
+            cudaError_t e = cudaGraphLaunch(s->graph[c->cur].exec, c->stream);
+            if (e != cudaSuccess) { set_error(c, "cudaGraphLaunch failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
+            c->launches += s->graph[c->cur].launches;
+            n -= (int64_t)T * SLAB_GRAPH_PASSES;                   // an even number of passes: c->cur unchanged
+            continue;
         }
-        c->cur ^= 1;
+        rc = slab_pass(c, s, api, T);
         n -= T;
     }
     c->tile_family = old_family;
@@ -222,6 +282,7 @@ void slab_destroy(deff2d_ctx *c)
     SlabState *s = static_cast<SlabState *>(c->slab);
     if (!s) return;
     NcclApi *api = nccl_api();
+    for (auto &g : s->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (s->comm && api->CommDestroy) api->CommDestroy(s->comm);
     if (s->evA) cudaEventDestroy(s->evA);
     if (s->evC) cudaEventDestroy(s->evC);
@@ -255,6 +316,7 @@ DEFF2D_EXPORT int deff2d_nccl_init(deff2d_ctx *c, const uint8_t id[DEFF2D_NCCL_I
     SlabState *s = new SlabState();
     c->slab = s;
     s->rank = rank; s->nranks = nranks;
+    if (const char *e = std::getenv("DEFF2D_SLAB_GRAPHS")) s->use_graphs = std::atoi(e) != 0;   // tuning
     if (const char *e = std::getenv("DEFF2D_SLAB_RESERVE_SMS")) { const int v = std::atoi(e); if (v >= 0 && v <= 64) s->reserve_sms = v; }   // tuning
     CUS(cudaSetDevice(c->device));
     CUS(cudaEventCreateWithFlags(&s->evA, cudaEventDisableTiming));

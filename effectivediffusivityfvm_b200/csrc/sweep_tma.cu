@@ -24,6 +24,8 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "context.h"
 
 namespace deff2d {
@@ -393,8 +395,21 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t version = 0;        // tensor-map generation the graph was captured with
+    int T = 0, fam = 0, src = 0, count = 0, grid_limit = 0;
+    const uint32_t *list = nullptr;
+    const double *lut = nullptr;
+    double omega = 0;
+    bool slut = false;
+};
+
 struct TmaState {
     EncodeTiledFn encode = nullptr;
+    uint64_t version = 0;        // bumped whenever the tensor maps are re-encoded
+    std::vector<GraphEntry> graphs;
+    size_t graph_evict = 0;
     TmaMaps maps;
     int cfg_T = 0;               // temporal depth the maps were encoded for
     int ow = 0, oh = 0, tiles_x = 0, tiles_y = 0;
@@ -475,6 +490,7 @@ static int prepare_T(deff2d_ctx *c, TmaState *ts)
     if (!c->idx16.p) { set_error(c, "tiled sweep: the per-cell table indices have not been built"); return DEFF2D_ERR_STATE; }
     if ((rc = encode_2d(c, ts, &ts->maps.idx, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, c->idx16.p, (uint64_t)c->pitch,
                         (uint64_t)c->rows, (uint64_t)c->pitch * 2, C::IW, C::TH))) return rc;
+    ts->version++;
     ts->cfg_T = T;
     ts->cfg_F = F;
     ts->ow = C::OW; ts->oh = C::OH;
@@ -513,9 +529,9 @@ void tma_tile_geometry(const deff2d_ctx *c, int T, int *ow, int *oh)
     *oh = th - 2 * T;
 }
 
-// One pass of depth T (1..8) from x[c->cur] into x[c->cur ^ 1] over the tiles of `list` (NULL: the
-// whole tile grid) on `stream`; does not flip c->cur.
-int tma_pass(deff2d_ctx *c, int T, const uint32_t *list, int count, cudaStream_t stream)
+// One pass of depth T (1..8) from x[src] into x[src ^ 1] over the tiles of `list` (NULL: the whole
+// tile grid) on `stream`.
+static int pass_from(deff2d_ctx *c, int T, int src, const uint32_t *list, int count, cudaStream_t stream)
 {
     TmaState *ts = tma_state(c);
     if (!ts->encode) { set_error(c, "cuTensorMapEncodeTiled is not available from this driver"); return DEFF2D_ERR_CUDA; }
@@ -526,38 +542,119 @@ int tma_pass(deff2d_ctx *c, int T, const uint32_t *list, int count, cudaStream_t
     case TT:                                                                              \
         if (fam == 1) {                                                                   \
             if ((rc = prepare_T<TT, 1>(c, ts))) return rc;                                \
-            if ((rc = launch_T<TT, 1>(c, ts, c->cur, list, count, stream))) return rc;    \
+            if ((rc = launch_T<TT, 1>(c, ts, src, list, count, stream))) return rc;       \
         } else if (fam == 2) {                                                            \
             if ((rc = prepare_T<TT, 2>(c, ts))) return rc;                                \
-            if ((rc = launch_T<TT, 2>(c, ts, c->cur, list, count, stream))) return rc;    \
+            if ((rc = launch_T<TT, 2>(c, ts, src, list, count, stream))) return rc;       \
         } else {                                                                          \
             if ((rc = prepare_T<TT, 0>(c, ts))) return rc;                                \
-            if ((rc = launch_T<TT, 0>(c, ts, c->cur, list, count, stream))) return rc;    \
+            if ((rc = launch_T<TT, 0>(c, ts, src, list, count, stream))) return rc;       \
         }                                                                                 \
         break;
     switch (T) {
         DEFF2D_CASE(1) DEFF2D_CASE(2) DEFF2D_CASE(3) DEFF2D_CASE(4) DEFF2D_CASE(5) DEFF2D_CASE(6) DEFF2D_CASE(7) DEFF2D_CASE(8)
     }
 #undef DEFF2D_CASE
+    return DEFF2D_OK;
+}
+
+// One pass from x[c->cur] into x[c->cur ^ 1]; does not flip c->cur.
+int tma_pass(deff2d_ctx *c, int T, const uint32_t *list, int count, cudaStream_t stream)
+{
+    int rc = pass_from(c, T, c->cur, list, count, stream);
+    if (rc) return rc;
     c->launches++;
     return DEFF2D_OK;
 }
 
+// `npasses` passes of depth T on c->stream, flipping c->cur after each.  Long runs go through a
+// CUDA graph of GRAPH_PASSES kernel nodes (captured once per configuration and replayed): the
+// host then issues one launch per 32 passes -- on small domains and in slab mode the per-launch
+// host cost (6-8 us measured on the GPU box) otherwise exceeds the kernel time.
+#define GRAPH_PASSES 32
+
+int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int count)
+{
+    TmaState *ts = tma_state(c);
+    int rc;
+    while (npasses >= GRAPH_PASSES && c->use_graphs) {
+        // make sure the tensor maps are current before looking a graph up (re-encoding bumps the version)
+        if (ts->cfg_T != T || ts->cfg_F != c->tile_family || ts->key_x0 != c->x[0].p || ts->key_x1 != c->x[1].p ||
+            ts->key_code != c->idx16.p || ts->key_Nx != c->Nx || ts->key_Ny != c->Ny || ts->key_pitch != c->pitch) {
+            // a direct pass re-encodes the maps; then the graphs of the old maps are dropped below
+            if ((rc = tma_pass(c, T, list, count, c->stream))) return rc;
+            c->cur ^= 1;
+            npasses--;
+            continue;
+        }
+        const bool slut = c->prefer_smem_lut && c->lut_stages == 1;
+        GraphEntry *g = nullptr;
+        for (auto &e : ts->graphs)
+            if (e.exec && e.version == ts->version && e.T == T && e.fam == c->tile_family && e.src == c->cur && e.list == list &&
+                e.count == count && e.grid_limit == c->grid_limit && e.slut == slut && e.lut == c->clut.p && e.omega == c->omega) { g = &e; break; }
+        if (!g) {
+            // drop stale graphs, then capture GRAPH_PASSES passes
+            for (auto &e : ts->graphs)
+                if (e.exec && e.version != ts->version) { cudaGraphExecDestroy(e.exec); e.exec = nullptr; }
+            GraphEntry *slot = nullptr;
+            for (auto &e : ts->graphs) if (!e.exec) { slot = &e; break; }
+            if (!slot) {
+                if (ts->graphs.size() < 12) { ts->graphs.emplace_back(); slot = &ts->graphs.back(); }
+                else { slot = &ts->graphs[ts->graph_evict++ % ts->graphs.size()]; cudaGraphExecDestroy(slot->exec); slot->exec = nullptr; }
+            }
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+            if (e != cudaSuccess) { set_error(c, "cudaStreamBeginCapture failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
+            rc = DEFF2D_OK;
+            for (int k = 0; k < GRAPH_PASSES && !rc; k++) rc = pass_from(c, T, c->cur ^ (k & 1), list, count, c->stream);
+            e = cudaStreamEndCapture(c->stream, &graph);
+            if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+            if (e != cudaSuccess || !graph) { set_error(c, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
+            e = cudaGraphInstantiate(&slot->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { slot->exec = nullptr; set_error(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
+            slot->version = ts->version; slot->T = T; slot->fam = c->tile_family; slot->src = c->cur; slot->list = list;
+            slot->count = count; slot->grid_limit = c->grid_limit; slot->slut = slut; slot->lut = c->clut.p; slot->omega = c->omega;
+            g = slot;
+        }
+        cudaError_t e = cudaGraphLaunch(g->exec, c->stream);
+        if (e != cudaSuccess) { set_error(c, "cudaGraphLaunch failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
+        c->launches += GRAPH_PASSES;
+        npasses -= GRAPH_PASSES;          // an even number of passes: c->cur is unchanged
+    }
+    while (npasses > 0) {
+        if ((rc = tma_pass(c, T, list, count, c->stream))) return rc;
+        c->cur ^= 1;
+        npasses--;
+    }
+    return DEFF2D_OK;
+}
+
+// Up to n sweeps with the context's tile list and depth: whole passes of depth tblock (through
+// tma_passes), or one shallower pass for the remainder.  *done = sweeps enqueued.
 int launch_sweep_tma(deff2d_ctx *c, int64_t n, int64_t *done)
 {
     *done = 0;
-    int T = (int)std::min<int64_t>(n, c->tblock);
+    int T = c->tblock;
     if (T < 1) T = 1;
     if (T > 8) T = 8;
-    int rc = tma_pass(c, T, c->tile_list, c->tile_count, c->stream);
-    if (rc) return rc;
-    c->cur ^= 1;
-    *done = T;
+    int rc;
+    if (n >= T) {
+        const int64_t passes = n / T;
+        if ((rc = tma_passes(c, T, passes, c->tile_list, c->tile_count))) return rc;
+        *done = passes * T;
+    } else {
+        if ((rc = tma_pass(c, (int)n, c->tile_list, c->tile_count, c->stream))) return rc;
+        c->cur ^= 1;
+        *done = n;
+    }
     return DEFF2D_OK;
 }
 
 void tma_destroy(deff2d_ctx *c)
 {
+    if (TmaState *ts = static_cast<TmaState *>(c->tma))
+        for (auto &e : ts->graphs) if (e.exec) cudaGraphExecDestroy(e.exec);
     delete static_cast<TmaState *>(c->tma);
     c->tma = nullptr;
 }

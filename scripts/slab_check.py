@@ -39,6 +39,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--size", default="600x900")
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--sweeps", type=int, default=2000)
+    ap.add_argument("--skip-check", action="store_true")
     args = ap.parse_args()
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
@@ -46,7 +48,7 @@ def main():
     H, W = (int(v) for v in args.size.split("x"))
     ok = True
     report = {}
-    for nphase, amp in ((3, (2, 2)), (2, (1, 1))):
+    for nphase, amp in (() if args.skip_check else ((3, (2, 2)), (2, (1, 1)))):
         img = blobs(11 + nphase, (H, W))
         p = E.default_params(Ds=0.0 if nphase == 3 else 1e-3, Df=1.0, Dg=80.0, amp_x=amp[0], amp_y=amp[1],
                              CL=0.25, CR=1.5, check_every=400)
@@ -91,7 +93,7 @@ def main():
         dom.flux()
         dist.barrier()
         torch.cuda.synchronize()
-        S = 2000
+        S = args.sweeps
         stream = torch.cuda.ExternalStream(ctx.stream)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
