@@ -527,6 +527,7 @@ DEFF2D_EXPORT int deff2d_domain_load_slab(deff2d_ctx *c, const uint8_t *gray, in
     const int Hsrc = (int)(NyLocal / p->amp_y);
     c->halo_above = above; c->halo_below = below; c->grow0 = row0 - above;
     c->slab_domain = true;
+    c->halo_valid = std::max(above, below);                  // x0 is exact everywhere
     return domain_load_impl(c, gray, W, Hsrc, nphase, p, row0 - above, (row0 - above) / p->amp_y, NyLocal,
                             NyGlobal, above, own_rows, pinned, false);
 }
@@ -639,6 +640,7 @@ DEFF2D_EXPORT int deff2d_domain_set_field(deff2d_ctx *c, const double *field)
     v.x_out = v.x_in;                  // write into the current iterate
     launch_inject_field(c->stream, v, c->dense.p);
     c->launches++;
+    c->halo_valid = 0;                                       // slab mode: exchange before the next pass
     CU(cudaStreamSynchronize(c->stream));
     return DEFF2D_OK;
 }

@@ -75,6 +75,7 @@ struct deff2d_ctx {
 
     // multi-GPU slab state (slab.cu)
     void *slab = nullptr;
+    int64_t halo_valid = 0;          // slab mode: halo rows that are still exact (a pass of depth T consumes T)
     bool slab_domain = false;        // the resident domain is one slab of a decomposed global domain
 };
 

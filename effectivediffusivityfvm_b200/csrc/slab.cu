@@ -71,6 +71,7 @@ static NcclApi *nccl_api()
 struct SlabGraph {
     cudaGraphExec_t exec = nullptr;
     int T = 0, launches = 0;
+    int64_t halo_after = 0;       // c->halo_valid at the end of the captured run
     const void *x0 = nullptr, *x1 = nullptr, *idx = nullptr, *lut = nullptr;
     double omega = 0;
     uint64_t lists = 0;
@@ -81,6 +82,8 @@ struct SlabState {
     ncclComm_t comm = nullptr;
     SlabGraph graph[2];           // one per parity of c->cur at the start of the run
     bool use_graphs = true;
+    bool split = false;           // boundary tiles in an own launch, exchange overlapped with the interior launch
+    bool debug_nocomm = false;    // timing experiments only: skip the halo exchange (results are then wrong)
     uint64_t lists_version = 0;
     int rank = 0, nranks = 1;
     cudaEvent_t evA = nullptr, evC = nullptr;
@@ -160,43 +163,67 @@ static int build_lists(deff2d_ctx *c, SlabState *s)
     return DEFF2D_OK;
 }
 
-// One pass of depth T on a slab incl. the halo exchange; flips c->cur.  Enqueue only (also used
-// under stream capture).
-static int slab_pass(deff2d_ctx *c, SlabState *s, NcclApi *api, int T)
+// Halo exchange of the current iterate x[c->cur] on stream `cs`: H whole padded rows to and from
+// each neighbour.  Afterwards every local row is exact again.
+static int slab_exchange(deff2d_ctx *c, SlabState *s, NcclApi *api, double *buf, cudaStream_t cs)
 {
     const int64_t H = std::max(c->halo_above, c->halo_below);
     const bool up = c->halo_above > 0, down = c->halo_below > 0;
-    const size_t count = (size_t)H * (size_t)c->pitch;            // doubles per halo block (whole padded rows)
+    const size_t count = (size_t)H * (size_t)c->pitch;            // doubles per halo block
+    NCCLCHECK(api->GroupStart());
+    if (up) {
+        // own top H rows -> upper neighbour's lower halo; its bottom H own rows -> my upper halo
+        NCCLCHECK(api->Send(buf + (size_t)(1 + c->halo_above) * c->pitch, count, ncclDouble, s->rank - 1, s->comm, cs));
+        NCCLCHECK(api->Recv(buf + (size_t)(1 + c->halo_above - H) * c->pitch, count, ncclDouble, s->rank - 1, s->comm, cs));
+    }
+    if (down) {
+        const size_t last_own = (size_t)(1 + c->halo_above + c->own_rows);    // padded row after the last own row
+        NCCLCHECK(api->Send(buf + (last_own - (size_t)H) * c->pitch, count, ncclDouble, s->rank + 1, s->comm, cs));
+        NCCLCHECK(api->Recv(buf + last_own * c->pitch, count, ncclDouble, s->rank + 1, s->comm, cs));
+    }
+    NCCLCHECK(api->GroupEnd());
+    c->launches++;                                                 // the NCCL send/recv kernel
+    return DEFF2D_OK;
+}
+
+// One pass of depth T on a slab; flips c->cur.  Enqueue only (also used under stream capture).
+//
+// Default (deep halo): a pass of depth T invalidates T more halo rows, so with H halo rows the
+// exchange is only needed every H / T passes -- c->halo_valid counts the halo rows that are
+// still exact.  With H = 16, T = 4 the NCCL latency (~16 us per exchange, measured) is paid
+// once per 4 passes (~740 us of sweeping).
+// Split mode (DEFF2D_SLAB_SPLIT=1): exchange after every pass, boundary tiles launched first
+// and the exchange on a second stream beside the interior tiles.  Measured slower on B200
+// (the two-launch split costs more than the exchange it hides), kept for comparison.
+static int slab_pass(deff2d_ctx *c, SlabState *s, NcclApi *api, int T)
+{
+    const bool comm = (c->halo_above > 0 || c->halo_below > 0) && !s->debug_nocomm;
     int rc;
-    // boundary tiles first, then the exchange overlaps the interior tiles
-    if ((rc = tma_pass(c, T, s->tiles.p + s->off_b[T], s->cnt_b[T], c->stream))) return rc;
-    if (up || down) {
-        CUS(cudaEventRecord(s->evA, c->stream));
-        CUS(cudaStreamWaitEvent(c->comm_stream, s->evA, 0));
-    }
-    c->grid_limit = (up || down) && s->reserve_sms > 0 ? c->prop.multiProcessorCount - s->reserve_sms : 0;
-    rc = tma_pass(c, T, s->tiles.p + s->off_i[T], s->cnt_i[T], c->stream);
-    c->grid_limit = 0;
-    if (rc) return rc;
-    if (up || down) {
-        double *dst = c->x[c->cur ^ 1].p;                      // the buffer this pass wrote
-        NCCLCHECK(api->GroupStart());
-        if (up) {
-            // own top H rows -> upper neighbour's lower halo; its bottom H own rows -> my upper halo
-            NCCLCHECK(api->Send(dst + (size_t)(1 + c->halo_above) * c->pitch, count, ncclDouble, s->rank - 1, s->comm, c->comm_stream));
-            NCCLCHECK(api->Recv(dst + (size_t)(1 + c->halo_above - H) * c->pitch, count, ncclDouble, s->rank - 1, s->comm, c->comm_stream));
+    if (s->split) {
+        if ((rc = tma_pass(c, T, s->tiles.p + s->off_b[T], s->cnt_b[T], c->stream))) return rc;
+        if (comm) {
+            CUS(cudaEventRecord(s->evA, c->stream));
+            CUS(cudaStreamWaitEvent(c->comm_stream, s->evA, 0));
         }
-        if (down) {
-            const size_t last_own = (size_t)(1 + c->halo_above + c->own_rows);    // padded row after the last own row
-            NCCLCHECK(api->Send(dst + (last_own - (size_t)H) * c->pitch, count, ncclDouble, s->rank + 1, s->comm, c->comm_stream));
-            NCCLCHECK(api->Recv(dst + last_own * c->pitch, count, ncclDouble, s->rank + 1, s->comm, c->comm_stream));
+        c->grid_limit = comm && s->reserve_sms > 0 ? c->prop.multiProcessorCount - s->reserve_sms : 0;
+        rc = tma_pass(c, T, s->tiles.p + s->off_i[T], s->cnt_i[T], c->stream);
+        c->grid_limit = 0;
+        if (rc) return rc;
+        if (comm) {
+            if ((rc = slab_exchange(c, s, api, c->x[c->cur ^ 1].p, c->comm_stream))) return rc;
+            CUS(cudaEventRecord(s->evC, c->comm_stream));
+            CUS(cudaStreamWaitEvent(c->stream, s->evC, 0));
         }
-        NCCLCHECK(api->GroupEnd());
-        CUS(cudaEventRecord(s->evC, c->comm_stream));
-        CUS(cudaStreamWaitEvent(c->stream, s->evC, 0));
-        c->launches++;                                         // the NCCL send/recv kernel
+        c->cur ^= 1;
+        return DEFF2D_OK;
     }
+    if (comm && c->halo_valid < T) {
+        if ((rc = slab_exchange(c, s, api, c->x[c->cur].p, c->stream))) return rc;
+        c->halo_valid = std::max(c->halo_above, c->halo_below);
+    }
+    if ((rc = tma_pass(c, T, nullptr, 0, c->stream))) return rc;
     c->cur ^= 1;
+    if (comm) c->halo_valid -= T;
     return DEFF2D_OK;
 }
 
@@ -238,7 +265,9 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
                 const int64_t launches0 = c->launches;
                 cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
                 if (e != cudaSuccess) { set_error(c, "cudaStreamBeginCapture failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
+                c->halo_valid = 0;                                 // the captured run starts with an exchange: replays do not depend on the state before
                 for (int k = 0; k < SLAB_GRAPH_PASSES && !rc; k++) rc = slab_pass(c, s, api, T);
+                g.halo_after = c->halo_valid;
                 e = cudaStreamEndCapture(c->stream, &graph);
                 g.launches = (int)(c->launches - launches0);
                 c->launches = launches0;                           // nothing ran yet
@@ -253,6 +282,7 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
             cudaError_t e = cudaGraphLaunch(s->graph[c->cur].exec, c->stream);
             if (e != cudaSuccess) { set_error(c, "cudaGraphLaunch failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
             c->launches += s->graph[c->cur].launches;
+            c->halo_valid = s->graph[c->cur].halo_after;
             n -= (int64_t)T * SLAB_GRAPH_PASSES;                   // an even number of passes: c->cur unchanged
             continue;
         }
@@ -316,6 +346,8 @@ DEFF2D_EXPORT int deff2d_nccl_init(deff2d_ctx *c, const uint8_t id[DEFF2D_NCCL_I
     SlabState *s = new SlabState();
     c->slab = s;
     s->rank = rank; s->nranks = nranks;
+    if (const char *e = std::getenv("DEFF2D_SLAB_SPLIT")) s->split = std::atoi(e) != 0;          // tuning
+    if (const char *e = std::getenv("DEFF2D_SLAB_DEBUG_NOCOMM")) s->debug_nocomm = std::atoi(e) != 0;
     if (const char *e = std::getenv("DEFF2D_SLAB_GRAPHS")) s->use_graphs = std::atoi(e) != 0;   // tuning
     if (const char *e = std::getenv("DEFF2D_SLAB_RESERVE_SMS")) { const int v = std::atoi(e); if (v >= 0 && v <= 64) s->reserve_sms = v; }   // tuning
     CUS(cudaSetDevice(c->device));

@@ -48,7 +48,7 @@ def main():
     H, W = (int(v) for v in args.size.split("x"))
     ok = True
     report = {}
-    for nphase, amp in (() if args.skip_check else ((3, (2, 2)), (2, (1, 1)))):
+    for nphase, amp, halo in (() if args.skip_check else ((3, (2, 2), 4), (2, (1, 1), 16), (3, (1, 1), 12))):
         img = blobs(11 + nphase, (H, W))
         p = E.default_params(Ds=0.0 if nphase == 3 else 1e-3, Df=1.0, Dg=80.0, amp_x=amp[0], amp_y=amp[1],
                              CL=0.25, CR=1.5, check_every=400)
@@ -57,7 +57,7 @@ def main():
         ref.domain_load(img, nphase, p)
         ctx = E.Deff2D(local)
         ctx.set_kernel(2, 4)
-        dom = SlabDomain(ctx, img, p, rank, world, nphase=nphase, halo=4)
+        dom = SlabDomain(ctx, img, p, rank, world, nphase=nphase, halo=halo)
         L = dom.layout
         for n in (1, 4, 203):
             ref.sweeps(n)
@@ -68,16 +68,16 @@ def main():
             d_ref, d = ref.flux()[0], dom.flux()
             rel = abs(d - d_ref) / abs(d_ref)
             ok = ok and same and rel < 1e-12
-            report["p%d_n%d" % (nphase, n)] = {"field_equal": bool(same), "deff_rel": rel}
+            report["p%d_h%d_n%d" % (nphase, halo, n)] = {"field_equal": bool(same), "deff_rel": rel}
         # the reference loop on the decomposed domain: same sweep count, same Deff on every rank
         ref.domain_load(img, nphase, p)
         r_ref = ref.solve(1e-4, 6000)
         ctx2 = ctx
-        dom = SlabDomain(ctx2, img, p, rank, world, nphase=nphase, halo=4)
+        dom = SlabDomain(ctx2, img, p, rank, world, nphase=nphase, halo=halo)
         r = dom.solve(1e-4, 6000)
         rel = abs(r["deff_raw"] - r_ref["deff_raw"]) / abs(r_ref["deff_raw"])
         ok = ok and r["iters"] == r_ref["iters"] and rel < 1e-12
-        report["p%d_solve" % nphase] = {"iters": r["iters"], "iters_ref": r_ref["iters"], "deff_rel": rel}
+        report["p%d_h%d_solve" % (nphase, halo)] = {"iters": r["iters"], "iters_ref": r_ref["iters"], "deff_rel": rel}
         ref.close()
         ctx.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")

@@ -3,8 +3,9 @@
 * tile planning exported by libdeff2d (slab boundary/interior split, packed-batch tile lists);
 * the row-slab geometry (`SlabLayout`) and -- with two `gloo` ranks on CPU -- the decomposition
   algebra itself: every rank sweeps its slab (numpy emulation of the device data model, the
-  library's own weight tables), exchanges halo rows after every pass of T sweeps and all-reduces
-  the boundary-flux sums, exactly as csrc/slab.cu does with NCCL.  The result must equal the
+  library's own weight tables), exchanges halo rows whenever the next pass of T sweeps would
+  need more exact halo rows than are left (every pass with H = T, every m-th with H = m T) and
+  all-reduces the boundary-flux sums, exactly as csrc/slab.cu does with NCCL.  The result must equal the
   undecomposed run bit for bit.
 """
 import os
@@ -107,7 +108,7 @@ def _free_port():
     return p
 
 
-def _slab_worker(rank, world, port, img, nphase, T, nsweeps, out):
+def _slab_worker(rank, world, port, img, nphase, T, nsweeps, out, halo_mult=1):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -117,7 +118,8 @@ def _slab_worker(rank, world, port, img, nphase, T, nsweeps, out):
         Ds, Dg, CL, CR = (0.0, 50.0, 0.25, 1.5) if nphase == 3 else (1e-3, 0.0, 0.25, 1.5)
         H, W = img.shape
         Nx, NyG = W, H
-        L = SlabLayout(H, rank, world, 1, T)
+        L = SlabLayout(H, rank, world, 1, T * halo_mult)
+        valid = L.halo                      # halo rows still exact (csrc/slab.cu: c->halo_valid)
         grid = None
         if nphase == 3:
             grid, _ = E.floodfill((img > 200).astype(np.uint8))
@@ -131,8 +133,13 @@ def _slab_worker(rank, world, port, img, nphase, T, nsweeps, out):
         done = 0
         while done < nsweeps:
             t = min(T, nsweeps - done)
-            px = EM.sweep(px, pc, lut, Nx, Ny, nsweeps=t)
-            # halo exchange: H = T whole padded rows each way (csrc/slab.cu)
+            if valid >= t:                   # deep halo: a pass of depth t only consumes t halo rows
+                px = EM.sweep(px, pc, lut, Nx, Ny, nsweeps=t)
+                valid -= t
+                done += t
+                continue
+            # halo exchange of the current iterate: H whole padded rows each way (csrc/slab.cu)
+            valid = L.halo
             reqs = []
             if L.above:
                 send = torch.from_numpy(px[1 + L.above:1 + L.above + L.halo].copy())
@@ -150,7 +157,6 @@ def _slab_worker(rank, world, port, img, nphase, T, nsweeps, out):
                 px[1 + L.above - L.halo:1 + L.above] = up.numpy()
             if L.below:
                 px[last:last + L.halo] = recv2.numpy()
-            done += t
         own = px[1 + L.above:1 + L.above + L.own_rows, EM.XOFF:EM.XOFF + Nx]
         # boundary-flux partial sums of the own rows, all-reduced (cuh:1252-1264)
         Dtab = np.array([1.0, Ds, Dg])
@@ -166,14 +172,14 @@ def _slab_worker(rank, world, port, img, nphase, T, nsweeps, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nphase,T,nsweeps", [(2, 4, 23), (3, 3, 14)])
-def test_slab_decomposition_two_gloo_ranks_equals_single_domain(tmp_path, nphase, T, nsweeps):
+@pytest.mark.parametrize("nphase,T,nsweeps,halo_mult", [(2, 4, 23, 1), (3, 3, 14, 1), (2, 2, 21, 3)])
+def test_slab_decomposition_two_gloo_ranks_equals_single_domain(tmp_path, nphase, T, nsweeps, halo_mult):
     import torch.multiprocessing as mp
     rng = np.random.default_rng(5 + nphase)
     img = np.choose(rng.integers(0, 3, size=(37, 24)), [0, 150, 255]).astype(np.uint8)
     world = 2
     port = _free_port()
-    mp.spawn(_slab_worker, args=(world, port, img, nphase, T, nsweeps, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_slab_worker, args=(world, port, img, nphase, T, nsweeps, str(tmp_path), halo_mult), nprocs=world, join=True)
     # undecomposed run with the same emulation
     Ds, Dg, CL, CR = (0.0, 50.0, 0.25, 1.5) if nphase == 3 else (1e-3, 0.0, 0.25, 1.5)
     H, W = img.shape
