@@ -17,10 +17,15 @@ def c3_image(k, size=256):
 
 
 def c4_image(size=16384, seed=4, sigma=8.0, eps=0.6):
-    """Config 4: one large two-phase porous domain (sigma 8 px, porosity 0.6)."""
+    """Config 4: one large two-phase porous domain (sigma 8 px, porosity 0.6).  Single precision
+    noise and a separable filter row block by row block keep the 268 M-pixel case to seconds."""
+    from scipy.ndimage import gaussian_filter1d
     rng = np.random.default_rng(seed)
-    z = _smooth_noise(rng, (size, size), sigma).astype(np.float32)
-    return np.where(z < np.quantile(z, eps), 0, 255).astype(np.uint8)
+    z = rng.standard_normal((size, size), dtype=np.float32)
+    gaussian_filter1d(z, sigma, axis=1, mode="wrap", output=z)
+    gaussian_filter1d(z, sigma, axis=0, mode="wrap", output=z)
+    thr = np.partition(z.ravel()[::7], int(eps * (z.size // 7 + 1)))[int(eps * (z.size // 7 + 1))]   # eps-quantile of a 1/7 sample
+    return np.where(z < thr, 0, 255).astype(np.uint8)
 
 
 def c5_image(size=2048, seed=5, p=0.60):

