@@ -107,7 +107,14 @@ class SlabDomain:
         if nccl_id is None:
             nccl_id = self._broadcast_id()
         ctx.nccl_init(nccl_id, rank, world)
-        ctx.domain_load_slab(gray, nphase, params, L.row0, L.ny_global, L.halo, L.src_rows, pin)
+        self._load_args = (gray, nphase, params, L.row0, L.ny_global, L.halo, L.src_rows, pin)
+        self.h2d_bytes = int(gray.size + (pin.size if pin is not None else 0))
+        ctx.domain_load_slab(*self._load_args)
+
+    def reload(self):
+        """Upload the slab again from the host buffers (image rows + pinned mask) and reset the
+        iterate to x0: what a fresh solve of the same domain costs end to end."""
+        self.ctx.domain_load_slab(*self._load_args)
 
     def _broadcast_id(self):
         import torch.distributed as dist
