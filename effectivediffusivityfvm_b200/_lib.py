@@ -51,7 +51,7 @@ class Input(C.Structure):
     """deff2d_input: a parsed input.txt (Deff2D.cuh:234-324)."""
     _fields_ = [("p", Params), ("nphase", C.c_int), ("batch", C.c_int), ("num_images", C.c_int),
                 ("print_cmap", C.c_int), ("input_name", C.c_char * 1000),
-                ("output_name", C.c_char * 1000), ("cmap_name", C.c_char * 1000)]
+                ("output_name", C.c_char * 1000), ("cmap_name", C.c_char * 1000), ("devices", C.c_int)]
 
 
 _lib = None

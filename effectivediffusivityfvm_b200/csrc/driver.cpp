@@ -8,6 +8,7 @@
 #include <cstring>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 // printOptions, cuh:121-175
@@ -100,6 +101,16 @@ DEFF2D_EXPORT int deff2d_run_input_file(deff2d_ctx *ctx, const char *path)
     // results are written once at the end (cuh:2051); only the 3-phase batch writes
     // per-image CMAP_%05d.csv files (cuh:2395-2398, quirk Q17).
     std::vector<deff2d_result> results((size_t)std::max(in.num_images, 0));
+    const bool cmap = (in.nphase == 3 && in.print_cmap == 1);
+    // Decode every image first (decoding overlaps nothing here, but it decides the path): a batch of
+    // equally sized images without per-image verbose output is solved PACKED -- all images resident
+    // at once, many per launch (batch.cu) -- and, with the optional `Devices: N` key (ignored by the
+    // reference parser, cuh:261-311), split over N GPUs with no communication.
+    std::vector<uint8_t> packed;
+    int W0 = 0, H0 = 0;
+    bool uniform = in.num_images > 0;
+    std::vector<std::vector<uint8_t>> singles;
+    std::vector<int> Ws, Hs;
     for (int k = 0; k < in.num_images; k++) {
         char name[100];
         std::snprintf(name, sizeof(name), "%05d.jpg", k);           // cuh:1876
@@ -112,14 +123,56 @@ DEFF2D_EXPORT int deff2d_run_input_file(deff2d_ctx *ctx, const char *path)
             deff2d_free(gray);
             return DEFF2D_ERR_ARG;
         }
+        if (k == 0) { W0 = W; H0 = H; }
+        if (W != W0 || H != H0) uniform = false;
+        singles.emplace_back(gray, gray + (size_t)W * H);
+        Ws.push_back(W); Hs.push_back(H);
+        deff2d_free(gray);
+    }
+    if (uniform && in.p.verbose != 1 && in.num_images >= 2) {
+        const size_t npix = (size_t)W0 * H0, ncell = npix * (size_t)in.p.amp_x * (size_t)in.p.amp_y;
+        packed.resize(npix * (size_t)in.num_images);
+        for (int k = 0; k < in.num_images; k++) std::memcpy(packed.data() + npix * k, singles[(size_t)k].data(), npix);
+        singles.clear();
+        std::vector<double> fields;
+        if (cmap) fields.resize(ncell * (size_t)in.num_images);
+        // one context per device; device 0 is the caller's
+        std::vector<deff2d_ctx *> ctxs{ctx};
+        for (int d = 1; d < in.devices && d < in.num_images; d++) {
+            deff2d_ctx *cx = nullptr;
+            if (deff2d_create(&cx, d) != DEFF2D_OK) break;          // fewer GPUs than asked for: use what is there
+            ctxs.push_back(cx);
+        }
+        const int nd = (int)ctxs.size();
+        std::vector<int> rcs((size_t)nd, 0);
+        std::vector<std::thread> pool;
+        auto work = [&](int d) {
+            const int k0 = (int)((int64_t)in.num_images * d / nd), k1 = (int)((int64_t)in.num_images * (d + 1) / nd);
+            deff2d_params p = in.p;
+            rcs[(size_t)d] = deff2d_solve_batch(ctxs[(size_t)d], packed.data() + npix * k0, k1 - k0, W0, H0, &p, results.data() + k0,
+                                                cmap ? fields.data() + ncell * k0 : nullptr);
+        };
+        for (int d = 1; d < nd; d++) pool.emplace_back(work, d);
+        work(0);
+        for (auto &t : pool) t.join();
+        for (int d = 1; d < nd; d++) deff2d_destroy(ctxs[(size_t)d]);
+        for (int d = 0; d < nd; d++) if (rcs[(size_t)d]) return rcs[(size_t)d];
+        if (cmap)
+            for (int k = 0; k < in.num_images; k++) {
+                char cm[100];
+                std::snprintf(cm, sizeof(cm), "CMAP_%05d.csv", k);  // cuh:2396
+                if ((rc = deff2d_write_cmap(cm, fields.data() + ncell * k, (int64_t)W0 * in.p.amp_x, (int64_t)H0 * in.p.amp_y))) return rc;
+            }
+        return deff2d_write_csv_batch(&in, results.data(), in.num_images);
+    }
+    // one image at a time: keeps the reference's per-image stdout order (Verbose: 1) and handles
+    // images of different sizes
+    for (int k = 0; k < in.num_images; k++) {
+        const int W = Ws[(size_t)k], H = Hs[(size_t)k];
         std::vector<double> field;
-        const bool cmap = (in.nphase == 3 && in.print_cmap == 1);
         if (cmap) field.resize((size_t)W * in.p.amp_x * (size_t)H * in.p.amp_y);
         deff2d_params p = in.p;
-        // one image at a time keeps the reference's per-image stdout order; a packed
-        // same-size batch goes through deff2d_solve_batch
-        rc = deff2d_solve_batch(ctx, gray, 1, W, H, &p, &results[(size_t)k], cmap ? field.data() : nullptr);
-        deff2d_free(gray);
+        rc = deff2d_solve_batch(ctx, singles[(size_t)k].data(), 1, W, H, &p, &results[(size_t)k], cmap ? field.data() : nullptr);
         if (rc) return rc;
         if (cmap) {
             char cm[100];

@@ -102,7 +102,7 @@ DEFF2D_EXPORT int deff2d_read_input_file(const char *path, deff2d_input *in)
     if (!path || !in) return DEFF2D_ERR_ARG;
     std::memset(in, 0, sizeof(*in));
     deff2d_default_params(&in->p);
-    in->nphase = 3; in->batch = 0; in->num_images = 0; in->print_cmap = 0;
+    in->nphase = 3; in->batch = 0; in->num_images = 0; in->print_cmap = 0; in->devices = 1;
     std::ifstream f(path);
     if (!f.is_open()) return DEFF2D_ERR_IO;
     std::string line;
@@ -134,6 +134,7 @@ DEFF2D_EXPORT int deff2d_read_input_file(const char *path, deff2d_input *in)
         else if (is("RunBatch:")) in->batch = (int)v;
         else if (is("NumImages:")) in->num_images = (int)v;
         else if (is("Phases:")) in->nphase = (int)v;
+        else if (is("Devices:")) in->devices = (int)v < 1 ? 1 : (int)v;
     }
     if (in->nphase == 3) in->p.mode = DEFF2D_MODE_3PH;
     else in->p.mode = in->batch ? DEFF2D_MODE_2PH_BATCH : DEFF2D_MODE_2PH_SINGLE;

@@ -218,6 +218,8 @@ typedef struct {
     char input_name[1000];    /* InputName: cuh:275-277 */
     char output_name[1000];   /* OutputName:cuh:285-287 */
     char cmap_name[1000];     /* CMapName:  cuh:292-294 */
+    int devices;              /* Devices: N -- extension, unknown to (and ignored by) the reference parser:
+                               * split a packed batch over N GPUs; default 1 */
 } deff2d_input;
 int deff2d_read_input_file(const char *path, deff2d_input *in);
 /* CSV / CMAP writers with the reference's exact formats (cuh:177-232, 497-554). */

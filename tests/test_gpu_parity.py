@@ -459,6 +459,31 @@ def test_drop_in_executable_on_bundled_jpeg(tmp_path, golden_dir, golden_drivers
     assert cm[0] == "X,Y,C" and len(cm) == 128 * 128 + 1
 
 
+def test_drop_in_executable_packed_batch(tmp_path):
+    """RunBatch: 1 through the `deff2d` executable: equally sized images are solved packed (and,
+    with the `Devices:` extension key, split over the GPUs present); the CSV rows equal the
+    oracle's per-image results in the reference's %f format."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(E.LIB_PATH), "deff2d")
+    imgs = [blobs(400 + k, (40, 56), fracs=(0.5 + 0.05 * k,)) for k in range(5)]
+    for k, im in enumerate(imgs):
+        (tmp_path / ("%05d.jpg" % k)).write_bytes(b"P5\n56 40\n255\n" + im.tobytes())      # PGM content, .jpg name
+    (tmp_path / "input.txt").write_text(
+        "Input Parameters:\nPhases: 2\nDs: 0.01\nDf: 1\nDg: 0\nMeshAmpX: 1\nMeshAmpY: 1\nInputName: unused.jpg\n"
+        "CR: 1\nCL: 0\nOutputName: batch.csv\nprintCMap: 0\nCMapName: unused.csv\nConvergence: 1e-4\n"
+        "MaxIter: 100000\nVerbose: 0\nRunBatch: 1\nNumImages: 5\nDevices: 2\n")
+    out = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    rows = (tmp_path / "batch.csv").read_text().strip().splitlines()
+    assert rows[0] == "imgNum,porosity,PathFlag,Deff,Time,nElements,converge,ds,df" and len(rows) == 6
+    for k, im in enumerate(imgs):
+        ref = O.solve_image(im, O.make_opts(Ds=0.01, Df=1.0, nphase=2, tol=1e-4, max_iter=100000), O.MODE_2PH_BATCH)
+        f = rows[1 + k].split(",")
+        assert f[0] == str(k) and f[1] == "%f" % ref["porosity"] and f[2] == "%d" % ref["pathflag"]
+        assert f[3] == "%f" % ref["deff"] and f[5] == "2240" and f[6] == "%f" % ref["conv"]
+        assert f[7] == "%f" % 0.01 and f[8] == "%f" % 1.0
+
+
 # ----------------------------------------------------------------------------- full-size properties
 
 def test_full_size_properties_config2(ctx, golden_images):
