@@ -486,7 +486,7 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
         for (int k = 0; k < nstages; k++) {
             build_tables(stages.s[k].D, Nx, Ny, c->CL, c->CR, c->omega, lut.data() + (size_t)k * DEFF2D_LUT_ENTRIES * 4,
                          dead.data() + (size_t)k * DEFF2D_LUT_ENTRIES);
-            compact_table(lut.data() + (size_t)k * DEFF2D_LUT_ENTRIES * 4, clut.data() + (size_t)k * DEFF2D_CLUT_ENTRIES * 4);
+            compact_table(lut.data() + (size_t)k * DEFF2D_LUT_ENTRIES * 4, clut.data() + (size_t)k * DEFF2D_CLUT_ENTRIES * 4, nphase);
         }
         CUB(cudaMemcpyAsync(c->clut.p, clut.data(), clut.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         CUB(cudaMemcpyAsync(c->lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -549,7 +549,7 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
                                                                             c->x[c->cur].p, c->x[c->cur ^ 1].p, c->code.p,
                                                                             b->slots.p, b->outs.p);
             // the table indices of the new images (and of their neighbours' shared ghost ring)
-            launch_build_idx(s, c->code.p, c->idx16.p, c->Nx, c->Ny, c->pitch, c->ghost_period);
+            launch_build_idx(s, c->code.p, c->idx16.p, c->Nx, c->Ny, c->pitch, c->ghost_period, nphase);
             c->launches += 2;
         }
         if (active_changed) {

@@ -80,7 +80,7 @@ static int upload_tables(deff2d_ctx *c)
     build_tables(c->Dphase, c->NxG, c->NyG, c->CL, c->CR, c->omega, lut.data(), dead.data());
     int rc;
     std::vector<double> clut((size_t)DEFF2D_CLUT_ENTRIES * 4);
-    compact_table(lut.data(), clut.data());
+    compact_table(lut.data(), clut.data(), c->nphase);
     if ((rc = ensure(c, c->lut, lut.size()))) return rc;
     if ((rc = ensure(c, c->clut, clut.size()))) return rc;
     if ((rc = ensure(c, c->dead, dead.size()))) return rc;
@@ -247,7 +247,7 @@ static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc,
     launch_init_domain(c->stream, c->img.p, W, Hsrc, p->amp_x, p->amp_y, nphase, grow0, img_row0, grid_dev,
                        c->x[0].p, c->x[1].p, c->code.p, Nx, Ny, c->pitch, c->NxG, c->CL, c->CR, own_first,
                        own_rows, c->d_counts);
-    launch_build_idx(c->stream, c->code.p, c->idx16.p, Nx, Ny, c->pitch, c->ghost_period);
+    launch_build_idx(c->stream, c->code.p, c->idx16.p, Nx, Ny, c->pitch, c->ghost_period, nphase);
     launch_count_below(c->stream, c->img.p, (int64_t)W * Hsrc, 150, c->d_counts);
     c->launches += 3;
     CU(cudaGetLastError());

@@ -8,8 +8,8 @@
 #include "../../include/deff2d.h"
 
 #define DEFF2D_LUT_ENTRIES 2048
-#define DEFF2D_CLUT_ENTRIES 1024        // compact table of the tiled sweep: p*256 + (pW|pE<<2|pS<<4|pN<<6), 768 = inert
-#define DEFF2D_CLUT_USED 776             // entries a CTA stages in shared memory (769 rounded up)
+#define DEFF2D_CLUT_ENTRIES 1024        // slots per plane of the compact table of the tiled sweep (see clut_slot)
+#define DEFF2D_CLUT_INERT 1023u         // ghost and pinned cells: all four weights 0
 #define DEFF2D_XOFF 16            // interior column j lives at padded index j + XOFF
 #define DEFF2D_PHASE_FLUID 0
 #define DEFF2D_PHASE_SOLID 1
@@ -24,13 +24,29 @@ namespace deff2d {
 void build_tables(const double Dphase[3], int64_t Nx, int64_t Ny, double CL, double CR, double omega,
                   double *lut, uint8_t *dead);
 
-// The compact per-stage table read by the tiled sweep: entry p*256 + n8 (p < 3, not pinned) is
-// lut[p | n8 << 2]; entries >= 768 are zero (ghost and pinned cells: x' = (1-omega) x).
-void compact_table(const double *lut, double *clut);
-// Slot of compact entry e: the two low bits (which 8-bank group a 32-byte entry occupies in shared
-// memory) are XOR-folded with the neighbour phases so that the few entries one warp gathers at a
-// phase interface fall into different bank groups.
-#define DEFF2D_CLUT_SLOT(e) ((e) ^ ((((e) >> 2) ^ ((e) >> 4) ^ ((e) >> 6) ^ ((e) >> 8)) & 3u))
+// The compact per-stage table read by the tiled sweep: four planes (wW, wE, wS, wN) of
+// DEFF2D_CLUT_ENTRIES doubles.  Slots are DENSE for the cells that matter: a cell whose four
+// neighbours are real phases gets slot p*16 + (pW | pE<<1 | pS<<2 | pN<<3) in a 2-phase domain
+// (32 slots = 256 bytes per plane: the gathers of a warp at a phase interface touch two cache
+// lines per plane) or p*81 + (pW + 3 pE + 9 pS + 27 pN) in a 3-phase domain (243 slots); cells on
+// the domain edge (a ghost neighbour) follow at base + p*256 + (pW | pE<<2 | pS<<4 | pN<<6).
+#if defined(__CUDACC__)
+#define DEFF2D_HD __host__ __device__
+#else
+#define DEFF2D_HD
+#endif
+DEFF2D_HD inline unsigned clut_slot(unsigned p, unsigned w, unsigned e, unsigned s, unsigned n, bool pinned, int nphase)
+{
+    if (pinned || p == 3u) return DEFF2D_CLUT_INERT;
+    const bool edge = (w == 3u) || (e == 3u) || (s == 3u) || (n == 3u);
+    if (nphase == 2) {
+        if (!edge) return p * 16u + (w | (e << 1) | (s << 2) | (n << 3));
+        return 32u + p * 256u + (w | (e << 2) | (s << 4) | (n << 6));
+    }
+    if (!edge) return p * 81u + (w + 3u * e + 9u * s + 27u * n);
+    return 243u + p * 256u + (w | (e << 2) | (s << 4) | (n << 6));
+}
+void compact_table(const double *lut, double *clut, int nphase);
 
 // FloodFill (cuh:557-713) on a byte grid; returns PathFlag.
 int floodfill(uint8_t *grid, int64_t Nx, int64_t Ny);

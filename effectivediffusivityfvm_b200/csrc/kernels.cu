@@ -126,7 +126,7 @@ void launch_init_domain(cudaStream_t s, const uint8_t *img, int W, int Hsrc, int
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_build_idx(const uint8_t *__restrict__ code, uint16_t *__restrict__ idx16, long long Nx, long long Ny,
-            long long pitch, long long period)
+            long long pitch, long long period, int nphase)
 {
     const long long groups_per_row = pitch / 8;
     const long long total = (Ny + 2) * groups_per_row;
@@ -145,12 +145,8 @@ k_build_idx(const uint8_t *__restrict__ code, uint16_t *__restrict__ idx16, long
             const long long c = c0 + k;
             const unsigned next = (c + 1 < pitch) ? row[c + 1] : 3u;
             const unsigned n = up ? up[c] : 3u, s = dn ? dn[c] : 3u;
-            // compact table index (tables.cpp: compact_table): p*256 + pW | pE<<2 | pS<<4 | pN<<6, or the
-            // inert entry 768 for ghost and pinned cells; stage in bits 10-13
-            unsigned v = 768u;
-            if ((cur & 3u) != 3u && !(cur & 4u))
-                v = ((cur & 3u) << 8) | (prev & 3u) | ((next & 3u) << 2) | ((s & 3u) << 4) | ((n & 3u) << 6);
-            v = DEFF2D_CLUT_SLOT(v);
+            // slot in the compact table (deff2d_internal.h: clut_slot); stage in bits 10-13
+            unsigned v = clut_slot(cur & 3u, prev & 3u, next & 3u, s & 3u, n & 3u, (cur & 4u) != 0, nphase);
             v |= ((cur >> 3) & 15u) << 10;
             const long long j = c - XOFF;                      // interior column
             if (j >= -1 && j <= Nx && (j + 1) % period == 0) v |= 0x8000u;
@@ -164,13 +160,13 @@ k_build_idx(const uint8_t *__restrict__ code, uint16_t *__restrict__ idx16, long
 }
 
 void launch_build_idx(cudaStream_t s, const uint8_t *code, uint16_t *idx16, int64_t Nx, int64_t Ny, int64_t pitch,
-                      int64_t ghost_period)
+                      int64_t ghost_period, int nphase)
 {
     const long long total = (Ny + 2) * (pitch / 8);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    k_build_idx<<<blocks, 256, 0, s>>>(code, idx16, Nx, Ny, pitch, ghost_period);
+    k_build_idx<<<blocks, 256, 0, s>>>(code, idx16, Nx, Ny, pitch, ghost_period, nphase);
 }
 
 // calcPorosity's counting loop (cuh:399-405) as a reduction over the source image

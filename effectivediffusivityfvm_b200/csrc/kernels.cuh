@@ -8,9 +8,9 @@
 //   code   one byte per cell in the same padded geometry (pitch bytes per row):
 //          bits 0-1 phase (0 fluid, 1 solid, 2 gas, 3 ghost), bit 2 pinned (3-phase Grid in {1,2}).
 //   idx16  two bytes per cell, same geometry, derived from `code` (k_build_idx): bits 0-9 the
-//          compact weight-table index p*256 + (pW | pE<<2 | pS<<4 | pN<<6) of the cell (768: ghost or
+//          cell's slot in the compact weight table (deff2d_internal.h: clut_slot; 1023: ghost or
 //          pinned), bits 10-13 its continuation stage, bit 15 "Dirichlet ghost column".  Read by
-//          the tiled sweep (K2) together with `clut`, the compact form of `lut`.
+//          the tiled sweep (K2) together with `clut`, the compact planar form of `lut`.
 //   lut    2048 x 4 doubles: sweep weights for every (p, pW, pE, pS, pN, pinned), per stage.
 // The reference's A[n][5] + b[n] (48 B/cell, cuh:1396-1397) are never materialised.
 #pragma once
@@ -63,7 +63,7 @@ void launch_init_domain(cudaStream_t s, const uint8_t *img, int W, int Hsrc, int
                         Counts *counts);
 // per-cell table index of every padded cell from the codes (see idx16 above)
 void launch_build_idx(cudaStream_t s, const uint8_t *code, uint16_t *idx16, int64_t Nx, int64_t Ny, int64_t pitch,
-                      int64_t ghost_period);
+                      int64_t ghost_period, int nphase);
 void launch_count_below(cudaStream_t s, const uint8_t *img, int64_t n, int thr, Counts *counts);
 
 // K3: plain streaming sweep, one sweep per HBM pass (cuh:69-92 matrix-free)

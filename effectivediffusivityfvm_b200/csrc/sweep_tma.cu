@@ -106,7 +106,7 @@ struct Cfg {
     static constexpr size_t OFF_CODE = OFF_OUT + OUT_BYTES;       // CODE[2]
     static constexpr size_t OFF_BAR = OFF_CODE + 2 * CODE_BYTES;  // 2 mbarriers + tile origins
     static constexpr size_t OFF_LUT = OFF_BAR + 128;              // compact weight table of the stage (SLUT kernels)
-    static constexpr size_t LUT_BYTES = (size_t)DEFF2D_CLUT_USED * 32;
+    static constexpr size_t LUT_BYTES = (size_t)DEFF2D_CLUT_ENTRIES * 32;    // four planes of doubles
     static constexpr size_t SMEM = OFF_BAR + 64 + 128;            // + alignment slack
     static constexpr size_t SMEM_SLUT = OFF_LUT + LUT_BYTES + 128;
     static_assert(OW > 0 && OH > 0, "tile too small for this temporal depth");
@@ -177,7 +177,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     const double *wtab = lut;
     if constexpr (SLUT) {
         double *sl = reinterpret_cast<double *>(smem + C::OFF_LUT);
-        for (int k = tid; k < DEFF2D_CLUT_USED * 2; k += C::NT)
+        for (int k = tid; k < DEFF2D_CLUT_ENTRIES * 2; k += C::NT)
             reinterpret_cast<double2 *>(sl)[k] = __ldg(reinterpret_cast<const double2 *>(lut) + k);
         wtab = sl;
         __syncthreads();
@@ -251,35 +251,39 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
 #pragma unroll
             for (int py = 0; py < PY; py++)
 #pragma unroll
-                for (int px = 0; px < PX; px++) idx[py][px] &= SLUT ? 0x3ffu : 0x3fffu;     // SLUT: one stage
+                for (int px = 0; px < PX; px++)      // offset into the planar table: stage * 4096 + slot (SLUT: one stage)
+                    idx[py][px] = SLUT ? (idx[py][px] & 0x3ffu) : (((idx[py][px] & 0x3c00u) << 2) | (idx[py][px] & 0x3ffu));
             // Most patches lie inside one phase (every cell has the same neighbourhood index):
             // one LUT entry then serves all PX*PY cells -- 2 instead of 2*PX*PY 16-byte loads.
             // The LSU data pipe is the busiest unit of this kernel (ncu: ~80 % of peak).
             // warp-wide decision: a mixed warp would execute both paths
+            auto fetch = [&](unsigned e, double &w0, double &w1, double &w2, double &w3) {
+                const double *q = wtab + e;
+                if constexpr (SLUT) {
+                    w0 = q[0]; w1 = q[DEFF2D_CLUT_ENTRIES]; w2 = q[2 * DEFF2D_CLUT_ENTRIES]; w3 = q[3 * DEFF2D_CLUT_ENTRIES];
+                } else {
+                    w0 = __ldg(q); w1 = __ldg(q + DEFF2D_CLUT_ENTRIES); w2 = __ldg(q + 2 * DEFF2D_CLUT_ENTRIES);
+                    w3 = __ldg(q + 3 * DEFF2D_CLUT_ENTRIES);
+                }
+            };
             if (__all_sync(0xffffffffu, uniform)) {
-                const double2 *lp = reinterpret_cast<const double2 *>(wtab + (size_t)idx[0][0] * 4);
-                double2 a, bb;
-                if constexpr (SLUT) { a = lp[0]; bb = lp[1]; } else { a = __ldg(lp); bb = __ldg(lp + 1); }
+                double a0, a1, a2, a3;
+                fetch(idx[0][0], a0, a1, a2, a3);
 #pragma unroll
                 for (int py = 0; py < PY; py++)
 #pragma unroll
                     for (int px = 0; px < PX; px++) {
-                        w[py][px][0] = a.x; w[py][px][1] = a.y; w[py][px][2] = bb.x; w[py][px][3] = bb.y;
+                        w[py][px][0] = a0; w[py][px][1] = a1; w[py][px][2] = a2; w[py][px][3] = a3;
                     }
             } else {
 #pragma unroll
                 for (int py = 0; py < PY; py++)
 #pragma unroll
-                    for (int px = 0; px < PX; px++) {
-                        const double2 *lp = reinterpret_cast<const double2 *>(wtab + (size_t)idx[py][px] * 4);
-                        double2 a, bb;
-                        if constexpr (SLUT) { a = lp[0]; bb = lp[1]; } else { a = __ldg(lp); bb = __ldg(lp + 1); }
-                        w[py][px][0] = a.x; w[py][px][1] = a.y; w[py][px][2] = bb.x; w[py][px][3] = bb.y;
-                    }
+                    for (int px = 0; px < PX; px++)
+                        fetch(idx[py][px], w[py][px][0], w[py][px][1], w[py][px][2], w[py][px][3]);
             }
         }
 
-        // ---- publish the patch boundary of level 0 ----------------------------------------
         // XSHFL (one warp spans the tile width): the W / E halo comes from the neighbouring lanes by
         // warp shuffles, so only the top and bottom patch rows go through shared memory
         constexpr bool XSHFL = (C::NWX == 1);

@@ -96,13 +96,18 @@ void build_tables(const double Dphase[3], int64_t Nx, int64_t Ny, double CL, dou
     }
 }
 
-void compact_table(const double *lut, double *clut)
+void compact_table(const double *lut, double *clut, int nphase)
 {
     std::memset(clut, 0, sizeof(double) * 4 * DEFF2D_CLUT_ENTRIES);
-    for (int p = 0; p < 3; p++)
-        for (int n8 = 0; n8 < 256; n8++)
-            std::memcpy(clut + (size_t)DEFF2D_CLUT_SLOT((unsigned)(p * 256 + n8)) * 4, lut + (size_t)(p | (n8 << 2)) * 4,
-                        4 * sizeof(double));
+    const unsigned np = (nphase == 2) ? 2u : 3u;
+    for (unsigned p = 0; p < np; p++)
+        for (unsigned n8 = 0; n8 < 256; n8++) {
+            const unsigned w = n8 & 3u, e = (n8 >> 2) & 3u, s = (n8 >> 4) & 3u, n = (n8 >> 6) & 3u;
+            if ((w != 3u && w >= np) || (e != 3u && e >= np) || (s != 3u && s >= np) || (n != 3u && n >= np)) continue;
+            const unsigned slot = clut_slot(p, w, e, s, n, false, nphase);
+            const double *src = lut + (size_t)(p | (n8 << 2)) * 4;
+            for (int f = 0; f < 4; f++) clut[(size_t)f * DEFF2D_CLUT_ENTRIES + slot] = src[f];
+        }
 }
 
 }  // namespace deff2d
