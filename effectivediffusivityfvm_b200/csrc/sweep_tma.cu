@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <vector>
 
 #include "context.h"
@@ -114,10 +115,10 @@ struct Cfg {
 };
 
 // LIST: walk an explicit tile list.  SLUT: every image is in the same continuation stage, so the
-// stage's compact weight table (24 KB) can be staged in shared memory once per CTA.  Measured:
-// +2 % on mesh-amplified domains (most patches single-phase, one broadcast read per patch),
-// -4 % on interface-rich media (per-cell gathers cost about the same through L1) -- chosen per
-// domain by the context (prefer_smem_lut).
+// stage's compact weight table (32 KB) can be staged in shared memory once per CTA
+// (DEFF2D_SMEM_LUT=1).  Measured with the dense planar table: gathers through L1 are faster on
+// both mesh-amplified (704 vs 695 GLUP/s) and interface-rich media (543 vs 513), so this is off
+// by default and kept as a tuning switch.
 template <class C, bool LIST, bool SLUT>
 __global__ void __launch_bounds__(C::NT, 1)
 k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, double om,
@@ -452,11 +453,19 @@ template <int T> struct Family<T, 1> { using type = Cfg<T, 4, 4, 1, 8>; };
 //   family 2: 2 x 4 cells per thread, 2 x 8 warps, 512 threads (more warps, <= 128 registers)
 template <int T> struct Family<T, 2> { using type = Cfg<T, 2, 4, 2, 8>; };
 
+// DEFF2D_SMEM_LUT=0/1 overrides the per-domain choice (tuning)
+static bool smem_lut_wanted(const deff2d_ctx *c)
+{
+    static const int env = [] { const char *e = std::getenv("DEFF2D_SMEM_LUT"); return e ? std::atoi(e) : -1; }();
+    if (c->lut_stages != 1) return false;
+    return env < 0 ? c->prefer_smem_lut : env != 0;
+}
+
 template <int T, int F>
 static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, int count, cudaStream_t stream)
 {
     using C = typename Family<T, F>::type;
-    const bool slut = c->prefer_smem_lut && (c->lut_stages == 1) && ((int)C::SMEM_SLUT <= ts->max_smem_optin);
+    const bool slut = smem_lut_wanted(c) && ((int)C::SMEM_SLUT <= ts->max_smem_optin);
     auto kern = list ? (slut ? k_sweep_tma<C, true, true> : k_sweep_tma<C, true, false>)
                      : (slut ? k_sweep_tma<C, false, true> : k_sweep_tma<C, false, false>);
     const size_t smem = slut ? C::SMEM_SLUT : C::SMEM;
@@ -591,7 +600,7 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
             npasses--;
             continue;
         }
-        const bool slut = c->prefer_smem_lut && c->lut_stages == 1;
+        const bool slut = smem_lut_wanted(c);
         GraphEntry *g = nullptr;
         for (auto &e : ts->graphs)
             if (e.exec && e.version == ts->version && e.T == T && e.fam == c->tile_family && e.src == c->cur && e.list == list &&
