@@ -117,6 +117,14 @@ def run_reference(args):
     img, data = load_workload()
     three_phase = True
     ref = O.reference("cpu")
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(ncpu))
+    except OSError:
+        pass
+    O.oracle().orc_set_num_threads(int(ncpu))
     nthreads = O.oracle().orc_num_threads()
     if args.ref_crop:
         img = img[:args.ref_crop, :]
@@ -165,6 +173,8 @@ def run_reference(args):
 
 def cpu_baseline(img, sweeps, three_phase=True):
     import _oracle as O
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    O.oracle().orc_set_num_threads(int(ncpu))
     o = O.make_opts(Ds=0.0, Df=1.0, Dg=1237500.0, ampx=AMP, ampy=AMP, nphase=3 if three_phase else 2)
     d = np.zeros(1)
     img = np.ascontiguousarray(img)
