@@ -51,7 +51,7 @@ class Input(C.Structure):
     """deff2d_input: a parsed input.txt (Deff2D.cuh:234-324)."""
     _fields_ = [("p", Params), ("nphase", C.c_int), ("batch", C.c_int), ("num_images", C.c_int),
                 ("print_cmap", C.c_int), ("input_name", C.c_char * 1000),
-                ("output_name", C.c_char * 1000), ("cmap_name", C.c_char * 1000), ("devices", C.c_int)]
+                ("output_name", C.c_char * 1000), ("cmap_name", C.c_char * 1000), ("devices", C.c_int), ("field_npy", C.c_int)]
 
 
 _lib = None
@@ -109,6 +109,7 @@ def lib():
         "deff2d_write_csv_single": (i32, [C.POINTER(Input), C.POINTER(Result)]),
         "deff2d_write_csv_batch": (i32, [C.POINTER(Input), C.POINTER(Result), i32]),
         "deff2d_write_cmap": (i32, [C.c_char_p, c_double_p, i64, i64]),
+        "deff2d_write_field_npy": (i32, [C.c_char_p, c_double_p, i64, i64]),
         "deff2d_run_input_file": (i32, [vp, C.c_char_p]),
         "deff2d_load_image": (i32, [C.c_char_p, C.POINTER(c_ubyte_p), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
         "deff2d_free": (None, [vp]),

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <atomic>
 #include <string>
 #include <thread>
 #include <vector>
@@ -93,8 +94,12 @@ DEFF2D_EXPORT int deff2d_run_input_file(deff2d_ctx *ctx, const char *path)
         deff2d_free(gray);
         if (rc) return rc;
         if ((rc = deff2d_write_csv_single(&in, &res))) return rc;   // cuh:1821, cuh:1612
-        if (in.print_cmap == 1)                                     // cuh:1825-1827
+        if (in.print_cmap == 1) {                                   // cuh:1825-1827
             rc = deff2d_write_cmap(in.cmap_name, field.data(), (int64_t)W * in.p.amp_x, (int64_t)H * in.p.amp_y);
+            if (!rc && in.field_npy == 1)
+                rc = deff2d_write_field_npy((std::string(in.cmap_name) + ".npy").c_str(), field.data(), (int64_t)W * in.p.amp_x,
+                                            (int64_t)H * in.p.amp_y);
+        }
         return rc;
     }
     // BatchSim (cuh:1843-2054) / BatchSim3Phase (cuh:2056-2419): images "%05d.jpg" from 0;
@@ -109,25 +114,37 @@ DEFF2D_EXPORT int deff2d_run_input_file(deff2d_ctx *ctx, const char *path)
     std::vector<uint8_t> packed;
     int W0 = 0, H0 = 0;
     bool uniform = in.num_images > 0;
-    std::vector<std::vector<uint8_t>> singles;
-    std::vector<int> Ws, Hs;
+    std::vector<std::vector<uint8_t>> singles((size_t)std::max(in.num_images, 0));
+    std::vector<int> Ws((size_t)std::max(in.num_images, 0), 0), Hs(Ws), chs(Ws), rcs_load(Ws);
+    {
+        // decode on the host threads (file order is kept: slot k belongs to "%05d.jpg" % k)
+        std::atomic<int> next(0);
+        auto load = [&]() {
+            for (;;) {
+                const int k = next.fetch_add(1);
+                if (k >= in.num_images) break;
+                char name[100];
+                std::snprintf(name, sizeof(name), "%05d.jpg", k);   // cuh:1876
+                uint8_t *gray = nullptr;
+                rcs_load[(size_t)k] = deff2d_load_image(name, &gray, &Ws[(size_t)k], &Hs[(size_t)k], &chs[(size_t)k]);
+                if (!rcs_load[(size_t)k] && chs[(size_t)k] == 1) singles[(size_t)k].assign(gray, gray + (size_t)Ws[(size_t)k] * Hs[(size_t)k]);
+                deff2d_free(gray);
+            }
+        };
+        const int nt = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt && t < in.num_images; t++) pool.emplace_back(load);
+        load();
+        for (auto &t : pool) t.join();
+    }
     for (int k = 0; k < in.num_images; k++) {
-        char name[100];
-        std::snprintf(name, sizeof(name), "%05d.jpg", k);           // cuh:1876
-        uint8_t *gray = nullptr;
-        int W = 0, H = 0, ch = 0;
-        rc = deff2d_load_image(name, &gray, &W, &H, &ch);
-        if (rc) { std::printf("Error: could not read image %s\n", name); return rc; }
-        if (ch != 1) {
-            std::printf("Error: please enter a grascale image with 1 channel.\n Current number of channels = %d\n", ch);
-            deff2d_free(gray);
+        if (rcs_load[(size_t)k]) { std::printf("Error: could not read image %05d.jpg\n", k); return rcs_load[(size_t)k]; }
+        if (chs[(size_t)k] != 1) {
+            std::printf("Error: please enter a grascale image with 1 channel.\n Current number of channels = %d\n", chs[(size_t)k]);
             return DEFF2D_ERR_ARG;
         }
-        if (k == 0) { W0 = W; H0 = H; }
-        if (W != W0 || H != H0) uniform = false;
-        singles.emplace_back(gray, gray + (size_t)W * H);
-        Ws.push_back(W); Hs.push_back(H);
-        deff2d_free(gray);
+        if (k == 0) { W0 = Ws[0]; H0 = Hs[0]; }
+        if (Ws[(size_t)k] != W0 || Hs[(size_t)k] != H0) uniform = false;
     }
     if (uniform && in.p.verbose != 1 && in.num_images >= 2) {
         const size_t npix = (size_t)W0 * H0, ncell = npix * (size_t)in.p.amp_x * (size_t)in.p.amp_y;

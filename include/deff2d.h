@@ -220,12 +220,15 @@ typedef struct {
     char cmap_name[1000];     /* CMapName:  cuh:292-294 */
     int devices;              /* Devices: N -- extension, unknown to (and ignored by) the reference parser:
                                * split a packed batch over N GPUs; default 1 */
+    int field_npy;            /* FieldNpy: 1 -- extension: with printCMap, also write <CMapName>.npy (binary field) */
 } deff2d_input;
 int deff2d_read_input_file(const char *path, deff2d_input *in);
 /* CSV / CMAP writers with the reference's exact formats (cuh:177-232, 497-554). */
 int deff2d_write_csv_single(const deff2d_input *in, const deff2d_result *r);
 int deff2d_write_csv_batch(const deff2d_input *in, const deff2d_result *r, int count);
 int deff2d_write_cmap(const char *path, const double *field, int64_t Nx, int64_t Ny);
+/* The same map as a NumPy .npy file (float64, shape (Ny, Nx)): binary companion of the CMAP text. */
+int deff2d_write_field_npy(const char *path, const double *field, int64_t Nx, int64_t Ny);
 /* The reference program: read ./input.txt-style file, run the selected driver (cu:17-50),
  * write the same files.  Images are decoded by the library's own readers (PGM/PNG content
  * under any file name; baseline JPEG). */

@@ -221,3 +221,42 @@ def test_jpeg_decoder_rejects_garbage(tmp_path):
     p.write_bytes(b"\xff\xd8")
     with pytest.raises(E.Deff2DError):
         E.load_image(p)
+
+
+def test_cmap_writer_parallel_blocks_and_npy(tmp_path):
+    """createCMAP's text (cuh:497-524) from the block-parallel writer: byte-identical to per-cell
+    C formatting, row blocks in order; the .npy companion round-trips through numpy.load."""
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    Ny, Nx = 77, 1030                                   # several row blocks, ragged last block
+    f = rng.random((Ny, Nx)) * 10.0 ** rng.integers(-12, 3, size=(Ny, Nx))
+    f[5, 7] = np.nan
+    f[6, 8] = 0.0
+    f[7, 9] = -1.5e-300
+    p = tmp_path / "cmap.csv"
+    assert L.deff2d_write_cmap(str(p).encode(), f.ctypes.data_as(_lib.c_double_p), Nx, Ny) == 0
+    lines = p.read_text().split("\n")
+    assert lines[0] == "X,Y,C" and lines[-1] == "" and len(lines) == Ny * Nx + 2
+    libc = C.CDLL(None)
+    libc.snprintf.restype = C.c_int
+    buf = C.create_string_buffer(64)
+    for (i, j) in [(0, 0), (0, Nx - 1), (5, 7), (6, 8), (7, 9), (63, 1029), (64, 0), (Ny - 1, Nx - 1)] + \
+            [tuple(x) for x in rng.integers(0, [Ny, Nx], size=(200, 2))]:
+        libc.snprintf(buf, 64, b"%d,%d,%1.3e", C.c_int(int(j)), C.c_int(int(i)), C.c_double(float(f[i, j])))
+        assert lines[1 + i * Nx + j] == buf.value.decode(), (i, j)
+    q = tmp_path / "field.npy"
+    assert L.deff2d_write_field_npy(str(q).encode(), f.ctypes.data_as(_lib.c_double_p), Nx, Ny) == 0
+    g = np.load(q)
+    assert g.shape == (Ny, Nx) and g.dtype == np.float64 and np.array_equal(g, f, equal_nan=True)
+
+
+def test_input_file_extension_keys(tmp_path):
+    """Keys the reference parser does not know are ignored by it (cuh:261-311), so the extensions
+    Devices: and FieldNpy: keep an input.txt usable by both programs."""
+    p = tmp_path / "input.txt"
+    p.write_text("Phases: 2\nDevices: 4\nFieldNpy: 1\nRunBatch: 1\nNumImages: 3\nSomethingElse: 9\n")
+    inp = E.read_input_file(p)
+    assert (inp.nphase, inp.devices, inp.field_npy, inp.batch, inp.num_images) == (2, 4, 1, 1, 3)
+    p.write_text("Phases: 3\n")
+    inp = E.read_input_file(p)
+    assert (inp.devices, inp.field_npy) == (1, 0)
