@@ -399,7 +399,8 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     std::vector<uint8_t> masks;
     if (nphase == 3) masks.resize((size_t)count * cells);
     {
-        const int thr = (nphase == 3) ? 200 : 150;       // cuh:1368, cuh:1695
+        const bool strict = p->strict_reference != 0;    // see domain_load_impl (context.cu)
+        const int thr = (nphase == 3) ? 200 : (strict ? 150 : 149);       // cuh:1368, cuh:1695
         std::atomic<int> next(0);
         const int nthreads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
         auto work = [&]() {
@@ -416,7 +417,7 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
                     uint8_t *gr = g + (size_t)i * Nx;
                     for (int64_t j = 0; j < Nx; j++) gr[j] = srow[j / p->amp_x] > thr;
                 }
-                pathflag[(size_t)k] = floodfill(g, Nx, Ny);
+                pathflag[(size_t)k] = floodfill(g, Nx, Ny, strict);
             }
         };
         std::vector<std::thread> pool;

@@ -216,19 +216,23 @@ static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc,
     const uint8_t *grid_dev = nullptr;
     c->pathflag = 0;
     c->floodfill_passes = 0;
+    // strict_reference = 0 (defined behaviour where the reference has quirks): no right-column
+    // seeding (Q11) and pixel == 150 is solid in the FloodFill mask as it is in D (Q12: cuh:1695 vs cuh:1779)
+    const bool strict = p->strict_reference != 0;
+    const int ff_thr = (nphase == 3) ? 200 : (strict ? 150 : 149);
     const bool ff_device = run_floodfill && Nx >= 2 &&
                            (c->floodfill_mode == 2 || (c->floodfill_mode == 0 && Nx * Ny >= ((int64_t)1 << 16)));
     if (ff_device) {
         // label propagation on the device (floodfill.cu): same reachability, no 1 B/cell mask upload
         if ((rc = ensure(c, c->grid, (size_t)Nx * Ny))) return rc;
         int pf = 0;
-        if ((rc = floodfill_device(c, c->img.p, W, p->amp_x, p->amp_y, (nphase == 3) ? 200 : 150, c->grid.p, Nx, Ny,
+        if ((rc = floodfill_device(c, c->img.p, W, p->amp_x, p->amp_y, ff_thr, c->grid.p, Nx, Ny,
                                    reinterpret_cast<int *>(c->d_scalar), reinterpret_cast<int *>(c->h_scalar), &pf,
-                                   &c->floodfill_passes))) return rc;
+                                   &c->floodfill_passes, strict))) return rc;
         c->pathflag = pf;
         if (nphase == 3) grid_dev = c->grid.p;
     } else if (run_floodfill) {
-        const int thr = (nphase == 3) ? 200 : 150;
+        const int thr = ff_thr;
         c->h_grid.resize((size_t)Nx * Ny);
         for (int64_t i = 0; i < Ny; i++) {
             const uint8_t *srow = gray + (size_t)(i / p->amp_y) * W;
@@ -236,7 +240,7 @@ static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc,
             if (p->amp_x == 1) for (int64_t j = 0; j < Nx; j++) g[j] = srow[j] > thr;
             else for (int64_t j = 0; j < Nx; j++) g[j] = srow[j / p->amp_x] > thr;
         }
-        c->pathflag = floodfill(c->h_grid.data(), Nx, Ny);
+        c->pathflag = floodfill(c->h_grid.data(), Nx, Ny, strict);
         grid_host = (nphase == 3) ? c->h_grid.data() : nullptr;
     }
     if (grid_host) {
@@ -358,6 +362,11 @@ int solve_image_impl(deff2d_ctx *c, const uint8_t *gray, int W, int H, const def
         double DCF = 10.0;                                      // cuh:1714
         int count = 1;
         res->last_df = p->Df;
+        if (DCF > DCF_Max && p->strict_reference == 0) {        // defined behaviour for quirk Q8: one stage at Df
+            if ((rc = run_stage(c, p, res, p->Ds, DCF_Max, 0.0, DCF_Max, p->tol, p->max_iter, false, p->Df))) return rc;
+            res->deff = res->deff_raw / DCF_Max;
+            res->last_df = DCF_Max;
+        }
         while (DCF <= DCF_Max) {                                // cuh:1761 (no stage when Df < 10, quirk Q8)
             DCF = std::pow(100, count);                         // cuh:1762
             if (DCF >= DCF_Max) DCF = DCF_Max;

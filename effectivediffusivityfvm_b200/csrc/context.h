@@ -106,7 +106,7 @@ void batch_destroy(deff2d_ctx *c);
 
 // floodfill.cu: FloodFill (cuh:557-713) by label propagation on the device; blocks
 int floodfill_device(deff2d_ctx *c, const uint8_t *img, int W, int amp_x, int amp_y, int thr, uint8_t *st, int64_t Nx,
-                     int64_t Ny, int *d_flags, int *h_flags, int *pathflag, int *passes);
+                     int64_t Ny, int *d_flags, int *h_flags, int *pathflag, int *passes, bool reference_quirk);
 
 // batch.cu: returns 1 when the resident small-image kernel does not cover the request
 int batch_resident_solve(deff2d_ctx *c, const uint8_t *gray, int count, int W, int H,

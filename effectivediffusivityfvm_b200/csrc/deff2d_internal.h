@@ -49,7 +49,8 @@ DEFF2D_HD inline unsigned clut_slot(unsigned p, unsigned w, unsigned e, unsigned
 void compact_table(const double *lut, double *clut, int nphase);
 
 // FloodFill (cuh:557-713) on a byte grid; returns PathFlag.
-int floodfill(uint8_t *grid, int64_t Nx, int64_t Ny);
+// reference_quirk: keep the right-column seeding of cuh:601 (quirk Q11); false = flood from the left column only
+int floodfill(uint8_t *grid, int64_t Nx, int64_t Ny, bool reference_quirk = true);
 
 // repeated `+= 1/total` accumulation of the reference (cuh:402, cuh:437)
 double accumulate_fraction(int64_t count, int64_t total);

@@ -32,11 +32,11 @@ __device__ __forceinline__ bool ff_reached(unsigned v) { return v == 0u || v == 
 
 __global__ void __launch_bounds__(256)
 k_ff_init(const uint8_t *__restrict__ img, int W, int amp_x, int amp_y, int thr, uint8_t *__restrict__ st,
-          long long Nx, long long Ny)
+          long long Nx, long long Ny, int reference_quirk)
 {
     const long long n = Nx * Ny;
     // cuh:601 tests Domain[0]: the quirk is on while cell (0,0) is solid
-    const bool quirk = img[0] > thr;
+    const bool quirk = reference_quirk && img[0] > thr;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
         const long long i = k / Nx, j = k - i * Nx;
         const bool solid = img[(i / amp_y) * W + (int)(j / amp_x)] > thr;
@@ -155,12 +155,12 @@ k_ff_finish(uint8_t *st, long long Nx, long long Ny, int *pathflag)
 // FloodFill of the amplified solid mask of `img` (device, W x Hsrc) into `st` (device, Nx * Ny
 // bytes: 0 reached, 1 solid, 2 unreached open).  flags: device int[2] scratch.  Blocks.
 int floodfill_device(deff2d_ctx *c, const uint8_t *img, int W, int amp_x, int amp_y, int thr, uint8_t *st, int64_t Nx,
-                     int64_t Ny, int *d_flags, int *h_flags, int *pathflag, int *passes)
+                     int64_t Ny, int *d_flags, int *h_flags, int *pathflag, int *passes, bool reference_quirk)
 {
     cudaStream_t s = c->stream;
     const long long n = Nx * Ny;
     int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
-    k_ff_init<<<blocks, 256, 0, s>>>(img, W, amp_x, amp_y, thr, st, Nx, Ny);
+    k_ff_init<<<blocks, 256, 0, s>>>(img, W, amp_x, amp_y, thr, st, Nx, Ny, reference_quirk ? 1 : 0);
     c->launches++;
     dim3 grid((unsigned)((Nx + FF_TW - 1) / FF_TW), (unsigned)((Ny + FF_TH - 1) / FF_TH));
     int total = 0;

@@ -21,7 +21,7 @@ namespace deff2d {
 // `Domain[indexR == -1]` reads Domain[0], so while cell (0,0) is marked solid every
 // right-column cell, solid or not, is seeded as well.  Unreached open cells become 2
 // (cuh:701-708).  PathFlag = some visited cell lies in the last column (cuh:619-621).
-int floodfill(uint8_t *grid, int64_t Nx, int64_t Ny)
+int floodfill(uint8_t *grid, int64_t Nx, int64_t Ny, bool reference_quirk)
 {
     const int64_t n = Nx * Ny;
     // state: 1 solid, 0 reached, 0xFF not reached yet   (Domain of cuh:573-587)
@@ -32,7 +32,7 @@ int floodfill(uint8_t *grid, int64_t Nx, int64_t Ny)
     for (int64_t row = 0; row < Ny; row++) {
         const int64_t iL = row * Nx, iR = (row + 1) * Nx - 1;
         if (dom[(size_t)iL] == 0xFF) { dom[(size_t)iL] = 0; queue.push_back(iL); }
-        if (dom[0] != 0) {                       // cuh:601
+        if (reference_quirk && dom[0] != 0) {    // cuh:601
             dom[(size_t)iR] = 0;
             queue.push_back(iR);
         }

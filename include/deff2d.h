@@ -54,7 +54,10 @@ typedef struct {
     double omega;             /* 0 -> 2/3, the reference's damping               cuh:72   */
     int tblock;               /* sweeps fused per HBM pass; 0 -> library default         */
     int verbose;              /* 1: print the reference's per-check / per-stage stdout lines */
-    int strict_reference;     /* 1 (default semantics): keep reference quirks Q8/Q11; 0 reserved */
+    int strict_reference;     /* 1 (default): bit-faithful reference quirks.  0: defined behaviour instead --
+                               * 2-phase single with Df < 10 runs one stage at Df (Q8, cuh:1714/1761), FloodFill
+                               * seeds the left column only (Q11, cuh:601), pixel == 150 is solid in the
+                               * FloodFill mask as in D (Q12, cuh:1695 vs 1779) */
 } deff2d_params;
 
 #define DEFF2D_MAX_STAGES 16

@@ -303,6 +303,36 @@ def test_quirks(ctx, golden_images):
     assert np.max(np.abs(got["field"] - ref["field"])) < FIELD_ATOL
 
 
+def test_strict_reference_off_defines_the_quirky_cases(ctx, golden_images):
+    """strict_reference = 0: Q8 one stage at Df instead of none, Q11 no right-column seeding,
+    Q12 pixel == 150 solid in the FloodFill mask; everything else unchanged."""
+    img = golden_images["00000"]
+    p = E.default_params(Ds=1e-4, Df=1.0, mode=E.MODE_2PH_SINGLE, strict_reference=0)
+    got = ctx.solve_image(img, p)
+    ref = ctx.solve_image(img, E.default_params(Ds=1e-4, Df=1.0, mode=E.MODE_2PH_BATCH))
+    assert got["nstages"] == 1 and got["iters"] == ref["iters"] and got["deff"] == ref["deff"]
+    # a full-height solid wall with a solid corner pixel: the reference reports PathFlag 1 (Q11)
+    wall = np.zeros((64, 96), np.uint8)
+    wall[:, 40:44] = 255
+    wall[0, 0] = 255
+    for mode in (1, 2):
+        ctx.set_floodfill(mode)
+        ctx.domain_load(wall, 2, E.default_params(Ds=1e-3, Df=1.0))
+        assert ctx.info()["pathflag"] == 1
+        ctx.domain_load(wall, 2, E.default_params(Ds=1e-3, Df=1.0, strict_reference=0))
+        assert ctx.info()["pathflag"] == 0
+    # pixel == 150: open for the reference's FloodFill (> 150), solid in D (< 150 is fluid)
+    grey = np.zeros((32, 48), np.uint8)
+    grey[:, 20:24] = 150
+    for mode in (1, 2):
+        ctx.set_floodfill(mode)
+        ctx.domain_load(grey, 2, E.default_params(Ds=1e-3, Df=1.0))
+        assert ctx.info()["pathflag"] == 1
+        ctx.domain_load(grey, 2, E.default_params(Ds=1e-3, Df=1.0, strict_reference=0))
+        assert ctx.info()["pathflag"] == 0
+    ctx.set_floodfill(0)
+
+
 def test_mesh_amplification_and_custom_cadence(ctx):
     img = blobs(21, (20, 28), levels=(0, 150, 255), fracs=(0.3, 0.4))
     for mode, omode, kw in ((E.MODE_2PH_BATCH, O.MODE_2PH_BATCH, dict(Ds=1e-2, Df=1.0)),
