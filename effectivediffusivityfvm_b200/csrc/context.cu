@@ -99,11 +99,12 @@ static int enqueue_sweeps(deff2d_ctx *c, int64_t n)
     if (c->slab && c->slab_domain) return slab_enqueue_sweeps(c, n);
     while (n > 0) {
         int64_t done = 0;
-        // kernel 0 (default): the TMA tiled kernel from 4096 cells up.  Depth by size (measured,
+        // kernel 0 (default): the TMA tiled kernel from 64 cells up (replayed as CUDA graphs: even a tiny
+        // domain then costs ~0.7 us per sweep instead of one 8 us launch per sweep).  Depth by size (measured,
         // profiles/): 4 sweeps per pass where HBM traffic matters (>= 16 M cells), 6 in between,
         // 8 on small domains, which are bound by per-pass latency; tiny domains stream (K3).
         const int64_t ncell = c->Nx * c->Ny;
-        if (c->kernel == 2 || (c->kernel == 0 && ncell >= 4096)) {
+        if (c->kernel == 2 || (c->kernel == 0 && ncell >= 64)) {
             if (c->kernel == 0) {
                 c->tile_family = 1;
                 c->tblock = ncell >= ((int64_t)1 << 24) ? 4 : (ncell >= ((int64_t)1 << 20) ? 6 : 8);
