@@ -90,7 +90,7 @@ def main():
         p = E.default_params(amp_x=4, amp_y=4)
         ctx = E.Deff2D(local)
         dom = SlabDomain(ctx, img, p, rank, world, weak=True)
-        dom.sweeps(40)
+        dom.sweeps(400)                                       # warm-up incl. the CUDA-graph capture
         dom.flux()
         dist.barrier()
         torch.cuda.synchronize()
@@ -114,7 +114,7 @@ def main():
         p = E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH)
         ctx = E.Deff2D(local)
         dom = SlabDomain(ctx, img, p, rank, world, nphase=2)
-        dom.sweeps(64)
+        dom.sweeps(400)                                       # warm-up incl. the CUDA-graph capture
         dom.flux()
         dist.barrier()
         torch.cuda.synchronize()
