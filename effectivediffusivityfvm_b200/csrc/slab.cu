@@ -2,18 +2,19 @@
 //
 // The reference is single-GPU (cudaSetDevice(0), Deff2D.cuh:908); a 5-point stencil shards
 // naturally into horizontal slabs.  One process (or thread) per GPU owns a contiguous band of
-// rows plus H halo rows of each neighbour (deff2d_domain_load_slab).  One temporally blocked
-// pass of depth T <= H (sweep_tma.cu) leaves the own rows exact and the halo rows stale, so
-// after every pass the H boundary rows travel to the neighbours:
+// rows plus H halo rows of each neighbour (deff2d_domain_load_slab).  A temporally blocked pass
+// of depth T (sweep_tma.cu) leaves the own rows exact and makes T more halo rows stale, so the
+// H boundary rows only travel to the neighbours when the next pass would need more exact halo
+// rows than are left -- with H = 16 and T = 4 once per 4 passes:
 //
-//     main stream:  [pass over BOUNDARY tiles] --evA--> [pass over INTERIOR tiles] --wait evC--> next pass
-//     comm stream:            wait evA -> ncclGroup{Send/Recv up, Send/Recv down} -> evC
+//     [exchange: ncclGroup{Send/Recv up, Send/Recv down}] [pass] [pass] [pass] [pass] [exchange] ...
 //
 // Rows are contiguous (pitch doubles each), so the halo is sent straight from the iterate
-// buffer: no pack kernel.  The interior launch leaves a few SMs free so that the NCCL
-// send/recv kernel can run beside it.  Once per check the two boundary-flux partial sums are
-// all-reduced (ncclAllReduce, 2 doubles) and every rank applies the identical stop rule
-// (cuh:1263-1276 via k_check).
+// buffer: no pack kernel.  Runs of 16 passes with their exchanges are captured into one CUDA
+// graph.  Once per check the two boundary-flux partial sums are all-reduced (ncclAllReduce,
+// 2 doubles) and every rank applies the identical stop rule (cuh:1263-1276 via k_check).
+// DEFF2D_SLAB_SPLIT=1 selects the alternative that exchanges after every pass on a second stream
+// beside the interior tiles (boundary tiles launched first); measured slower, see slab_pass.
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2): a process that already loaded NCCL (e.g.
 // through torch) shares that copy, and single-GPU users need no NCCL at all.
