@@ -437,7 +437,6 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     c->pitch = ((c->Nx + 2 * XOFF) + 15) / 16 * 16;
     c->rows = c->Ny + 2;
     c->ghost_period = Nx + 1;
-    c->prefer_smem_lut = false;
     c->own_first = 0; c->own_rows = c->Ny;
     c->nphase = nphase;
     c->CL = p->CL; c->CR = p->CR;

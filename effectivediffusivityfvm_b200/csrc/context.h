@@ -42,7 +42,6 @@ struct deff2d_ctx {
     DevBuf<uint16_t> idx16;          // per-cell weight-table index derived from `code` (k_build_idx), read by the tiled sweep
     DevBuf<double> lut, dense;
     DevBuf<double> clut;             // compact per-stage weight tables of the tiled sweep (tables.cpp: compact_table)
-    bool prefer_smem_lut = false;    // stage the compact table in shared memory (pays off when most patches are single-phase)
     int lut_stages = 1;              // stages resident in lut / clut (packed batches: all stages of the mode)
     std::vector<uint8_t> h_grid;
 

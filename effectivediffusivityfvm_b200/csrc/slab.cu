@@ -76,7 +76,6 @@ struct SlabGraph {
     const void *x0 = nullptr, *x1 = nullptr, *idx = nullptr, *lut = nullptr;
     double omega = 0;
     uint64_t lists = 0;
-    bool slut = false;
 };
 
 struct SlabState {
@@ -254,8 +253,7 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
         if (c->use_graphs && s->use_graphs && n >= (int64_t)T * SLAB_GRAPH_PASSES) {
             SlabGraph &g = s->graph[c->cur];
             const bool valid = g.exec && g.T == T && g.x0 == c->x[0].p && g.x1 == c->x[1].p && g.idx == c->idx16.p &&
-                               g.lut == c->clut.p && g.omega == c->omega && g.lists == s->lists_version &&
-                               g.slut == (c->prefer_smem_lut && c->lut_stages == 1);
+                               g.lut == c->clut.p && g.omega == c->omega && g.lists == s->lists_version;
             if (!valid) {
                 if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
                 // one direct pass pair first: encodes the tensor maps outside the capture
@@ -278,7 +276,7 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
                 cudaGraphDestroy(graph);
                 if (e != cudaSuccess) { g.exec = nullptr; set_error(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
                 g.T = T; g.x0 = c->x[0].p; g.x1 = c->x[1].p; g.idx = c->idx16.p; g.lut = c->clut.p; g.omega = c->omega;
-                g.lists = s->lists_version; g.slut = (c->prefer_smem_lut && c->lut_stages == 1);
+                g.lists = s->lists_version;
             }
             cudaError_t e = cudaGraphLaunch(s->graph[c->cur].exec, c->stream);
             if (e != cudaSuccess) { set_error(c, "cudaGraphLaunch failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }

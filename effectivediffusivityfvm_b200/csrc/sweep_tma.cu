@@ -106,27 +106,23 @@ struct Cfg {
     static constexpr size_t OUT_BYTES = ((size_t)OW * OH * 8 + 127) / 128 * 128;
     static constexpr size_t OFF_CODE = OFF_OUT + OUT_BYTES;       // CODE[2]
     static constexpr size_t OFF_BAR = OFF_CODE + 2 * CODE_BYTES;  // 2 mbarriers + tile origins
-    static constexpr size_t OFF_LUT = OFF_BAR + 128;              // compact weight table of the stage (SLUT kernels)
-    static constexpr size_t LUT_BYTES = (size_t)DEFF2D_CLUT_ENTRIES * 32;    // four planes of doubles
     static constexpr size_t SMEM = OFF_BAR + 64 + 128;            // + alignment slack
-    static constexpr size_t SMEM_SLUT = OFF_LUT + LUT_BYTES + 128;
     static_assert(OW > 0 && OH > 0, "tile too small for this temporal depth");
     static_assert(TW <= 256 && TH <= 256, "TMA box dimension limit");
 };
 
-// LIST: walk an explicit tile list.  SLUT: every image is in the same continuation stage, so the
-// stage's compact weight table (32 KB) can be staged in shared memory once per CTA
-// (DEFF2D_SMEM_LUT=1).  Measured with the dense planar table: gathers through L1 are faster on
-// both mesh-amplified (704 vs 695 GLUP/s) and interface-rich media (543 vs 513), so this is off
-// by default and kept as a tuning switch.
-template <class C, bool LIST, bool SLUT>
+// LIST: walk an explicit tile list.
+// Measured and removed alternatives: staging the weight table in shared memory (695 vs 704 GLUP/s
+// on config 2, 513 vs 543 in packed batches once the table became dense and planar -- gathers
+// through L1 win); writing the patches straight to global memory with 16-byte stores instead of
+// staging the output box for one bulk tensor store (647 vs 702, 532 vs 547).
+template <class C, bool LIST>
 __global__ void __launch_bounds__(C::NT, 1)
 k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, double om,
-            int tiles_x, int ntiles, const uint32_t *__restrict__ tile_list, const int *__restrict__ stop)
+            int tiles_x, int ntiles, const uint32_t *__restrict__ tile_list)
 {
     constexpr int T = C::T, TE = C::TE, PX = C::PX, PY = C::PY, TW = C::TW, TH = C::TH, OW = C::OW, OH = C::OH;
     constexpr int PW = C::PLANE_W, IW = C::IW;
-    if (stop && *stop) return;
 
     // No integer round trip on the base pointer: the compiler must keep seeing the shared
     // address space (a generic pointer turns every LDS/STS below into a slow generic LD/ST).
@@ -176,13 +172,6 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     __syncthreads();
     int tile = blockIdx.x;
     const double *wtab = lut;
-    if constexpr (SLUT) {
-        double *sl = reinterpret_cast<double *>(smem + C::OFF_LUT);
-        for (int k = tid; k < DEFF2D_CLUT_ENTRIES * 2; k += C::NT)
-            reinterpret_cast<double2 *>(sl)[k] = __ldg(reinterpret_cast<const double2 *>(lut) + k);
-        wtab = sl;
-        __syncthreads();
-    }
     if (tid == 0) {
         if (tile < ntiles) issue_load(tile, 0);
         if (tile + (int)gridDim.x < ntiles) issue_load(tile + gridDim.x, 1);
@@ -252,20 +241,16 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
 #pragma unroll
             for (int py = 0; py < PY; py++)
 #pragma unroll
-                for (int px = 0; px < PX; px++)      // offset into the planar table: stage * 4096 + slot (SLUT: one stage)
-                    idx[py][px] = SLUT ? (idx[py][px] & 0x3ffu) : (((idx[py][px] & 0x3c00u) << 2) | (idx[py][px] & 0x3ffu));
+                for (int px = 0; px < PX; px++)      // offset into the planar table: stage * 4096 + slot
+                    idx[py][px] = ((idx[py][px] & 0x3c00u) << 2) | (idx[py][px] & 0x3ffu);
             // Most patches lie inside one phase (every cell has the same neighbourhood index):
             // one LUT entry then serves all PX*PY cells -- 2 instead of 2*PX*PY 16-byte loads.
             // The LSU data pipe is the busiest unit of this kernel (ncu: ~80 % of peak).
             // warp-wide decision: a mixed warp would execute both paths
             auto fetch = [&](unsigned e, double &w0, double &w1, double &w2, double &w3) {
                 const double *q = wtab + e;
-                if constexpr (SLUT) {
-                    w0 = q[0]; w1 = q[DEFF2D_CLUT_ENTRIES]; w2 = q[2 * DEFF2D_CLUT_ENTRIES]; w3 = q[3 * DEFF2D_CLUT_ENTRIES];
-                } else {
-                    w0 = __ldg(q); w1 = __ldg(q + DEFF2D_CLUT_ENTRIES); w2 = __ldg(q + 2 * DEFF2D_CLUT_ENTRIES);
-                    w3 = __ldg(q + 3 * DEFF2D_CLUT_ENTRIES);
-                }
+                w0 = __ldg(q); w1 = __ldg(q + DEFF2D_CLUT_ENTRIES); w2 = __ldg(q + 2 * DEFF2D_CLUT_ENTRIES);
+                w3 = __ldg(q + 3 * DEFF2D_CLUT_ENTRIES);
             };
             if (__all_sync(0xffffffffu, uniform)) {
                 double a0, a1, a2, a3;
@@ -367,19 +352,11 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
             for (int py = 0; py < PY; py++) {
                 const int r = r0 + py - T;
                 if (r >= 0 && r < OH) {
-                    if constexpr (PX % 2 == 0) {   // c0, TE and OW are even: pairs never straddle the box edge
 #pragma unroll
-                        for (int px = 0; px < PX; px += 2) {
-                            const int c = c0 + px - TE;
-                            if (c >= 0 && c < OW)
-                                *reinterpret_cast<double2 *>(out + r * OW + c) = make_double2(x[py][px], x[py][px + 1]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int px = 0; px < PX; px++) {
-                            const int c = c0 + px - TE;
-                            if (c >= 0 && c < OW) out[r * OW + c] = x[py][px];
-                        }
+                    for (int px = 0; px < PX; px += 2) {   // c0, TE and OW are even: pairs never straddle the box edge
+                        const int c = c0 + px - TE;
+                        if (c >= 0 && c < OW)
+                            *reinterpret_cast<double2 *>(out + r * OW + c) = make_double2(x[py][px], x[py][px + 1]);
                     }
                 }
             }
@@ -407,7 +384,6 @@ struct GraphEntry {
     const uint32_t *list = nullptr;
     const double *lut = nullptr;
     double omega = 0;
-    bool slut = false;
 };
 
 struct TmaState {
@@ -420,7 +396,7 @@ struct TmaState {
     int ow = 0, oh = 0, tiles_x = 0, tiles_y = 0;
     void *key_x0 = nullptr, *key_x1 = nullptr, *key_code = nullptr;
     int64_t key_Nx = 0, key_Ny = 0, key_pitch = 0;
-    bool attr_set[4][3][17] = {{{false}}};
+    bool attr_set[2][3][17] = {{{false}}};
     int cfg_F = -1;
     int max_smem_optin = 0;
 };
@@ -453,23 +429,13 @@ template <int T> struct Family<T, 1> { using type = Cfg<T, 4, 4, 1, 8>; };
 //   family 2: 2 x 4 cells per thread, 2 x 8 warps, 512 threads (more warps, <= 128 registers)
 template <int T> struct Family<T, 2> { using type = Cfg<T, 2, 4, 2, 8>; };
 
-// DEFF2D_SMEM_LUT=0/1 overrides the per-domain choice (tuning)
-static bool smem_lut_wanted(const deff2d_ctx *c)
-{
-    static const int env = [] { const char *e = std::getenv("DEFF2D_SMEM_LUT"); return e ? std::atoi(e) : -1; }();
-    if (c->lut_stages != 1) return false;
-    return env < 0 ? c->prefer_smem_lut : env != 0;
-}
-
 template <int T, int F>
 static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, int count, cudaStream_t stream)
 {
     using C = typename Family<T, F>::type;
-    const bool slut = smem_lut_wanted(c) && ((int)C::SMEM_SLUT <= ts->max_smem_optin);
-    auto kern = list ? (slut ? k_sweep_tma<C, true, true> : k_sweep_tma<C, true, false>)
-                     : (slut ? k_sweep_tma<C, false, true> : k_sweep_tma<C, false, false>);
-    const size_t smem = slut ? C::SMEM_SLUT : C::SMEM;
-    const int variant = (list ? 1 : 0) + (slut ? 2 : 0);
+    auto kern = list ? k_sweep_tma<C, true> : k_sweep_tma<C, false>;
+    const size_t smem = C::SMEM;
+    const int variant = list ? 1 : 0;
     if (!ts->attr_set[variant][F][T]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error(c, "cudaFuncSetAttribute(smem %zu) failed: %s", smem, cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
@@ -480,7 +446,7 @@ static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, 
     int grid = c->prop.multiProcessorCount;
     if (c->grid_limit > 0 && grid > c->grid_limit) grid = c->grid_limit;
     if (grid > ntiles) grid = ntiles;
-    kern<<<grid, C::NT, smem, stream>>>(ts->maps, src, c->clut.p, 1.0 - c->omega, ts->tiles_x, ntiles, list, nullptr);
+    kern<<<grid, C::NT, smem, stream>>>(ts->maps, src, c->clut.p, 1.0 - c->omega, ts->tiles_x, ntiles, list);
     return DEFF2D_OK;
 }
 
@@ -600,11 +566,10 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
             npasses--;
             continue;
         }
-        const bool slut = smem_lut_wanted(c);
         GraphEntry *g = nullptr;
         for (auto &e : ts->graphs)
             if (e.exec && e.version == ts->version && e.T == T && e.fam == c->tile_family && e.src == c->cur && e.list == list &&
-                e.count == count && e.grid_limit == c->grid_limit && e.slut == slut && e.lut == c->clut.p && e.omega == c->omega) { g = &e; break; }
+                e.count == count && e.grid_limit == c->grid_limit && e.lut == c->clut.p && e.omega == c->omega) { g = &e; break; }
         if (!g) {
             // drop stale graphs, then capture GRAPH_PASSES passes
             for (auto &e : ts->graphs)
@@ -627,7 +592,7 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) { slot->exec = nullptr; set_error(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
             slot->version = ts->version; slot->T = T; slot->fam = c->tile_family; slot->src = c->cur; slot->list = list;
-            slot->count = count; slot->grid_limit = c->grid_limit; slot->slut = slut; slot->lut = c->clut.p; slot->omega = c->omega;
+            slot->count = count; slot->grid_limit = c->grid_limit; slot->lut = c->clut.p; slot->omega = c->omega;
             g = slot;
         }
         cudaError_t e = cudaGraphLaunch(g->exec, c->stream);
