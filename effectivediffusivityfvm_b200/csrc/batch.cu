@@ -498,6 +498,9 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     g.W = W; g.H = H; g.amp_x = p->amp_x; g.amp_y = p->amp_y; g.Nx = (int)Nx; g.Ny = (int)Ny; g.GX = GX; g.nphase = nphase;
     g.pitch = c->pitch; g.CL = c->CL; g.CR = c->CR; g.ce = c->check_every; g.nstages = nstages;
 
+    const int old_family = c->tile_family, old_tblock = c->tblock;
+    c->tile_family = DEFF2D_DEFAULT_TILE_FAMILY;
+    if (const char *e = std::getenv("DEFF2D_BATCH_FAMILY")) { const int v = std::atoi(e); if (v >= 0 && v <= 3) c->tile_family = v; }   // tuning
     // tile grids of the pass depths in use (T and the remainders 1..T-1)
     int ow[9], oh[9], tx_n[9], ty_n[9];
     size_t tiles_cap = 0;
@@ -520,8 +523,6 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     std::vector<uint32_t> tl;
     int next_image = 0, nactive = 0, done_images = 0;
     bool active_changed = true;
-    const int old_family = c->tile_family, old_tblock = c->tblock;
-    c->tile_family = 1;
     c->tblock = T;
     auto restore = [&]() {
         c->tile_family = old_family; c->tblock = old_tblock;

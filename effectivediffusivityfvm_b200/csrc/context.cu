@@ -99,15 +99,15 @@ static int enqueue_sweeps(deff2d_ctx *c, int64_t n)
     if (c->slab && c->slab_domain) return slab_enqueue_sweeps(c, n);
     while (n > 0) {
         int64_t done = 0;
-        // kernel 0 (default): the TMA tiled kernel from 64 cells up (replayed as CUDA graphs: even a tiny
-        // domain then costs ~0.7 us per sweep instead of one 8 us launch per sweep).  Depth by size (measured,
-        // profiles/): 4 sweeps per pass where HBM traffic matters (>= 16 M cells), 6 in between,
-        // 8 on small domains, which are bound by per-pass latency; tiny domains stream (K3).
+        // kernel 0 (default): the TMA tiled kernel (square 64 x 64 tiles) from 64 cells up, replayed as CUDA
+        // graphs: even a tiny domain then costs ~0.7 us per sweep instead of one 8 us launch per sweep.
+        // Depth (measured on config 2 with square tiles: 766 / 730 / 772 / 775 GLUP/s at T = 4 / 5 / 6 / 8;
+        // 2048^2: best at 6): 6 sweeps per pass from 1 M cells, 8 on small domains (per-pass latency bound).
         const int64_t ncell = c->Nx * c->Ny;
         if (c->kernel == 2 || (c->kernel == 0 && ncell >= 64)) {
             if (c->kernel == 0) {
-                c->tile_family = 1;
-                c->tblock = ncell >= ((int64_t)1 << 24) ? 4 : (ncell >= ((int64_t)1 << 20) ? 6 : 8);
+                c->tile_family = DEFF2D_DEFAULT_TILE_FAMILY;
+                c->tblock = ncell >= ((int64_t)1 << 20) ? 6 : 8;
             }
             int rc = launch_sweep_tma(c, n, &done);
             if (rc) return rc;
@@ -697,8 +697,8 @@ DEFF2D_EXPORT int deff2d_sync(deff2d_ctx *c)
 
 DEFF2D_EXPORT int deff2d_set_kernel(deff2d_ctx *c, int kernel, int tblock)
 {
-    if (!c || kernel < 0 || kernel > 4 || tblock < 0 || tblock > 16) return DEFF2D_ERR_ARG;
-    c->tile_family = (kernel >= 3) ? kernel - 2 : 0;   // 3, 4: alternative tile geometries of the TMA kernel (tuning)
+    if (!c || kernel < 0 || kernel > 5 || tblock < 0 || tblock > 16) return DEFF2D_ERR_ARG;
+    c->tile_family = (kernel >= 3) ? kernel - 2 : 0;   // 3, 4, 5: alternative tile geometries of the TMA kernel (tuning)
     if (kernel >= 3) kernel = 2;
     c->kernel = kernel;
     c->tblock = tblock > 0 ? tblock : 1;

@@ -10,6 +10,7 @@
 #define DEFF2D_LUT_ENTRIES 2048
 #define DEFF2D_CLUT_ENTRIES 1024        // slots per plane of the compact table of the tiled sweep (see clut_slot)
 #define DEFF2D_CLUT_INERT 1023u         // ghost and pinned cells: all four weights 0
+#define DEFF2D_DEFAULT_TILE_FAMILY 3      // sweep_tma.cu: Family<> (square 64 x 64 tiles); what kernel 0 and the planning helpers use
 #define DEFF2D_XOFF 16            // interior column j lives at padded index j + XOFF
 #define DEFF2D_PHASE_FLUID 0
 #define DEFF2D_PHASE_SOLID 1

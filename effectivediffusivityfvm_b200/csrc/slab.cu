@@ -241,11 +241,11 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
     const int64_t H = std::max(c->halo_above, c->halo_below);
     if (s->nranks > 1 && (H < 1 || c->own_rows < H)) { set_error(c, "slab needs halo rows >= 1 and own rows >= halo rows"); return DEFF2D_ERR_STATE; }
     const int old_family = c->tile_family;
-    c->tile_family = 1;
+    c->tile_family = DEFF2D_DEFAULT_TILE_FAMILY;
     int rc = build_lists(c, s);
     if (rc) { c->tile_family = old_family; return rc; }
     int Tmax = c->tblock > 0 ? c->tblock : 4;
-    if (c->kernel == 0) Tmax = 4;
+    if (c->kernel == 0) Tmax = 8;          // default: 8 sweeps per pass, with H = 16 an exchange every second pass
     if (Tmax > 8) Tmax = 8;
     if (s->nranks > 1 && Tmax > H) Tmax = (int)H;
     while (n > 0 && !rc) {

@@ -623,14 +623,15 @@ def test_tiled_kernel_is_bitwise_identical_to_streaming(ctx, shape, nphase):
     ctx.sweeps(29)
     ref = ctx.get_field()
     dref, _ = ctx.flux()
-    for T in range(1, 9):
-        ctx.set_kernel(2, T)
-        ctx.domain_load(img, nphase, p)
-        ctx.sweeps(29)                     # 29 = k*T + remainder: exercises the tail launches too
-        got = ctx.get_field()
-        assert np.array_equal(got, ref, equal_nan=True), (T, np.nanmax(np.abs(got - ref)))
-        d, _ = ctx.flux()
-        assert d == dref or (np.isnan(d) and np.isnan(dref))
+    for kernel in (2, 3, 5):               # tile families: 2 x 8 patches, 4 x 4 patches with shuffles, square 64 x 64 tiles
+        for T in range(1, 9):
+            ctx.set_kernel(kernel, T)
+            ctx.domain_load(img, nphase, p)
+            ctx.sweeps(29)                 # 29 = k*T + remainder: exercises the tail launches too
+            got = ctx.get_field()
+            assert np.array_equal(got, ref, equal_nan=True), (kernel, T, np.nanmax(np.abs(got - ref)))
+            d, _ = ctx.flux()
+            assert d == dref or (np.isnan(d) and np.isnan(dref))
     ctx.set_kernel(0)
 
 

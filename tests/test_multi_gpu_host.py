@@ -27,7 +27,7 @@ def _boxes(tiles, ow, oh):
 @pytest.mark.parametrize("T", [1, 2, 3, 4, 6, 8])
 def test_tile_geometry(T):
     ow, oh, tw, th = E.tile_geometry(T)
-    assert (tw, th) == (128, 32)
+    assert (tw, th) == (64, 64)             # the default tile family: square tiles, 4 x 4 cells per thread
     assert oh == th - 2 * T and ow == tw - 2 * ((T + 1) // 2 * 2)
     assert ow % 2 == 0                      # TMA needs 16-byte aligned FP64 box origins
 
