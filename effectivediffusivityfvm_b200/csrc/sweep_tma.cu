@@ -204,7 +204,18 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
             const uint16_t *id = reinterpret_cast<const uint16_t *>(CODE0 + b * C::CODE_BYTES) + ((ox - TE + DEFF2D_XOFF) & 7);
 #pragma unroll
             for (int py = 0; py < PY; py++) {
-                if constexpr (PX % 2 == 0) {       // 16-byte loads: conflict-free for PX == 2
+                if constexpr (PX == 4) {
+                    // A lane owns 32 consecutive bytes of the row, so lanes l and l+4 of a quarter warp hit
+                    // the same banks when all read their first 16 bytes.  Lanes with bit 2 set read their
+                    // second half first: every 16-byte load instruction is then conflict-free, and two
+                    // selects per value put the halves back in place.
+                    const bool hs = (lane & 4) != 0;
+                    const double *rp = in + (r0 + py) * TW + c0;
+                    const double2 a = *reinterpret_cast<const double2 *>(rp + (hs ? 2 : 0));
+                    const double2 b2 = *reinterpret_cast<const double2 *>(rp + (hs ? 0 : 2));
+                    x[py][0] = hs ? b2.x : a.x; x[py][1] = hs ? b2.y : a.y;
+                    x[py][2] = hs ? a.x : b2.x; x[py][3] = hs ? a.y : b2.y;
+                } else if constexpr (PX % 2 == 0) {       // 16-byte loads: conflict-free for PX == 2
 #pragma unroll
                     for (int px = 0; px < PX; px += 2) {
                         const double2 v = *reinterpret_cast<const double2 *>(in + (r0 + py) * TW + c0 + px);
@@ -354,11 +365,21 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
             for (int py = 0; py < PY; py++) {
                 const int r = r0 + py - T;
                 if (r >= 0 && r < OH) {
+                    if constexpr (PX == 4) {
+                        // same bank argument as for the patch loads: lanes with bit 2 set store their second half first
+                        const bool hs = (lane & 4) != 0;
+                        const int ca = c0 - TE + (hs ? 2 : 0), cb = c0 - TE + (hs ? 0 : 2);
+                        const double2 va = make_double2(hs ? x[py][2] : x[py][0], hs ? x[py][3] : x[py][1]);
+                        const double2 vb = make_double2(hs ? x[py][0] : x[py][2], hs ? x[py][1] : x[py][3]);
+                        if (ca >= 0 && ca < OW) *reinterpret_cast<double2 *>(out + r * OW + ca) = va;
+                        if (cb >= 0 && cb < OW) *reinterpret_cast<double2 *>(out + r * OW + cb) = vb;
+                    } else {
 #pragma unroll
-                    for (int px = 0; px < PX; px += 2) {   // c0, TE and OW are even: pairs never straddle the box edge
-                        const int c = c0 + px - TE;
-                        if (c >= 0 && c < OW)
-                            *reinterpret_cast<double2 *>(out + r * OW + c) = make_double2(x[py][px], x[py][px + 1]);
+                        for (int px = 0; px < PX; px += 2) {   // c0, TE and OW are even: pairs never straddle the box edge
+                            const int c = c0 + px - TE;
+                            if (c >= 0 && c < OW)
+                                *reinterpret_cast<double2 *>(out + r * OW + c) = make_double2(x[py][px], x[py][px + 1]);
+                        }
                     }
                 }
             }
