@@ -117,7 +117,9 @@ struct Cfg {
 // Measured and removed alternatives: staging the weight table in shared memory (695 vs 704 GLUP/s
 // on config 2, 513 vs 543 in packed batches once the table became dense and planar -- gathers
 // through L1 win); writing the patches straight to global memory with 16-byte stores instead of
-// staging the output box for one bulk tensor store (647 vs 702, 532 vs 547).
+// staging the output box for one bulk tensor store (647 vs 702, 532 vs 547); with two patch rows per
+// warp (square tiles), exchanging the row between them by shuffles instead of shared memory
+// (763 vs 817, 610 vs 650: a 64-bit shuffle costs more LSU time than an 8-byte shared-memory access).
 template <class C, bool LIST>
 __global__ void __launch_bounds__(C::NT, 1)
 k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, double om,
