@@ -101,13 +101,14 @@ static int enqueue_sweeps(deff2d_ctx *c, int64_t n)
         int64_t done = 0;
         // kernel 0 (default): the TMA tiled kernel (square 64 x 64 tiles) from 64 cells up, replayed as CUDA
         // graphs: even a tiny domain then costs ~0.7 us per sweep instead of one 8 us launch per sweep.
-        // Depth (measured on config 2 with square tiles: 766 / 730 / 772 / 775 GLUP/s at T = 4 / 5 / 6 / 8;
-        // 2048^2: best at 6): 6 sweeps per pass from 1 M cells, 8 on small domains (per-pass latency bound).
+        // Depth: 8 sweeps per pass (measured with square tiles on config 2: 811 / 816 / 827 GLUP/s at
+        // T = 4 / 6 / 8; 4096^2 and 2048^2 interface-rich media: best at 8; small domains are bound by
+        // per-pass latency, so the deepest pass wins there too).
         const int64_t ncell = c->Nx * c->Ny;
         if (c->kernel == 2 || (c->kernel == 0 && ncell >= 64)) {
             if (c->kernel == 0) {
                 c->tile_family = DEFF2D_DEFAULT_TILE_FAMILY;
-                c->tblock = ncell >= ((int64_t)1 << 20) ? 6 : 8;
+                c->tblock = 8;
             }
             int rc = launch_sweep_tma(c, n, &done);
             if (rc) return rc;

@@ -12,11 +12,11 @@ from effectivediffusivityfvm_b200.datasets import c3_image  # noqa: E402
 
 ctx = E.Deff2D(0)
 p = E.default_params(Ds=1e-3, Df=1.0)
-for size in (64, 128, 256, 512, 1024, 2048):
+for size in (64, 128, 256, 512, 1024, 2048, 4096):
     img = c3_image(1, size)
     ctx.domain_load(img, 2, p)
     out = []
-    for kernel, T in ((1, 1), (3, 2), (3, 4), (3, 6), (3, 8)):
+    for kernel, T in ((1, 1), (5, 4), (5, 6), (5, 8)):
         ctx.set_kernel(kernel, T)
         n = 4800
         ctx.sweeps_timed(240)
