@@ -75,12 +75,12 @@ class SlabDomain:
     img:     the global 8-bit source image (H x W); with weak=True the global domain is `world`
              vertical copies of `img` (every rank then owns one whole copy).
     halo:    amplified halo rows held of each neighbour.  A pass of depth T consumes T of them, so
-             the exchange runs every halo / T passes (16 rows, T = 4: once per 16 sweeps).
+             the exchange runs every halo / T passes (32 rows, T = 8: once per 4 passes = 32 sweeps).
     pinned:  3-phase only -- the global FloodFill mask (cuh:557-713) at amplified resolution, or
              None to compute it here with the library's host FloodFill.
     """
 
-    def __init__(self, ctx, img, params, rank, world, nphase=3, halo=16, pinned=None, weak=False, nccl_id=None):
+    def __init__(self, ctx, img, params, rank, world, nphase=3, halo=32, pinned=None, weak=False, nccl_id=None):
         img = np.ascontiguousarray(img, dtype=np.uint8)
         Hbase, W = img.shape
         self.ctx, self.rank, self.world = ctx, int(rank), int(world)
