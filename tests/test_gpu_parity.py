@@ -664,3 +664,89 @@ def test_slab_decomposition_matches_single_gpu():
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert '"ok": true' in out.stdout
+
+
+# ----------------------------------------------------------------------------- edge cases and error behaviour
+
+def test_api_error_paths_and_degenerate_inputs(ctx):
+    """Every entry point returns a status instead of crashing (reference quirks Q16, Q24): calls in
+    the wrong order, bad arguments, empty batches, no-sweep solves."""
+    L = ctx._L
+    fresh = E.Deff2D(0)
+    try:
+        with pytest.raises(E.Deff2DError):
+            fresh.sweeps(1)                                    # no domain loaded
+        with pytest.raises(E.Deff2DError):
+            fresh.flux()
+        assert fresh.solve_batch(np.zeros((0, 8, 8), np.uint8), E.default_params(mode=E.MODE_2PH_BATCH)) == []
+    finally:
+        fresh.close()
+    img = blobs(9, (24, 40))
+    with pytest.raises(E.Deff2DError):
+        ctx.solve_image(img, E.default_params(amp_x=0))        # cuh:1672-1675
+    bad = E.default_params()
+    bad.mode = 7
+    with pytest.raises(E.Deff2DError):
+        ctx.solve_image(img, bad)
+    assert L.deff2d_set_kernel(ctx._h, 99, 0) < 0 and L.deff2d_set_floodfill(ctx._h, 5) < 0
+    # tol >= 100: the reference loop body never runs (cuh:1232) -- 0 sweeps, Deff = the initial deffNew
+    p = E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH, tol=100.0)
+    got = ctx.solve_image(img, p)
+    ref = O.solve_image(img, O.make_opts(Ds=1e-3, Df=1.0, nphase=2, tol=100.0), O.MODE_2PH_BATCH)
+    assert got["iters"] == ref["iters"] == [0] and got["deff"] == ref["deff"]
+    # the same inside a batch (falls back to the per-image path) and MaxIter = 1
+    gb = ctx.solve_batch(np.stack([img, img]), p)
+    assert [g["iters"] for g in gb] == [[0], [0]]
+    p1 = E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH, max_iter=1)
+    got = ctx.solve_batch(np.stack([img, img[::-1].copy()]), p1)
+    for k, im in enumerate((img, img[::-1].copy())):
+        ref = O.solve_image(im, O.make_opts(Ds=1e-3, Df=1.0, nphase=2, max_iter=1), O.MODE_2PH_BATCH)
+        assert got[k]["iters"] == ref["iters"] == [1] and rel(got[k]["deff"], ref["deff"]) < 1e-12
+    ctx.domain_load(img, 2, E.default_params(Ds=1e-3, Df=1.0))
+    f0 = ctx.get_field()
+    ctx.sweeps(0)
+    assert np.array_equal(ctx.get_field(), f0)
+
+
+@pytest.mark.parametrize("shape", [(2, 2), (2, 37), (41, 2), (3, 3), (5, 300), (300, 5), (64, 64), (65, 63), (129, 127)])
+def test_small_and_ragged_domains_all_kernels(ctx, shape):
+    """Domains smaller than, equal to and just around one tile, thin strips included: the default
+    (tiled, graph-replayed) path equals the streaming kernel bit for bit and the oracle to 1e-13."""
+    img = blobs(shape[0] * 31 + shape[1], shape, levels=(0, 150, 255), fracs=(0.4, 0.3), smooth=1)
+    for nphase, Ds, Dg in ((2, 1e-2, 0.0), (3, 0.0, 20.0)):
+        p = E.default_params(Ds=Ds, Df=1.0, Dg=Dg, CL=0.1, CR=0.9)
+        D = O.fill_D(img, 1, 1, nphase, Ds, 1.0, Dg)
+        G, _ = O.floodfill(O.grid_mask(img, 1, 1, 200 if nphase == 3 else 150))
+        A, b = O.discretize(D, 0.1, 0.9, G if nphase == 3 else None)
+        ref = O.sweeps(A, b, O.init_x(shape[1], shape[0], 0.1, 0.9), 75)
+        out = {}
+        for kernel in (1, 0):
+            ctx.set_kernel(kernel)
+            ctx.domain_load(img, nphase, p)
+            ctx.sweeps(75)                                     # 2 graph-free + remainder passes at depth 8
+            out[kernel] = ctx.get_field()
+        assert np.array_equal(out[0], out[1], equal_nan=True)
+        assert np.array_equal(np.isnan(out[0]), np.isnan(ref))
+        if not np.all(np.isnan(ref)):
+            assert np.nanmax(np.abs(out[0] - ref)) < 1e-13
+    ctx.set_kernel(0)
+
+
+def test_graph_replay_long_runs_match_streaming(ctx):
+    """Runs long enough to go through the CUDA-graph path (32 passes per graph) with a remainder,
+    interleaved with table changes (new stage) that must not be served by a stale graph."""
+    img = blobs(123, (70, 90), levels=(0, 150, 255), fracs=(0.3, 0.4))
+    p = E.default_params(Ds=0.0, Df=1.0, Dg=10.0)
+    res = {}
+    for kernel in (1, 0):
+        ctx.set_kernel(kernel)
+        ctx.domain_load(img, 3, p)
+        ctx.sweeps(700)
+        ctx.set_D(0.0, 1.0, 1000.0)                            # next continuation stage: same graph shape, new table
+        ctx.sweeps(600)
+        ctx.set_field(np.nan_to_num(ctx.get_field()) * 0.5)     # dead cells (A0 = 0) read back as NaN: do not inject them
+        ctx.sweeps(300)
+        res[kernel] = (ctx.get_field(), ctx.flux())
+    assert np.array_equal(res[0][0], res[1][0], equal_nan=True) and res[0][1] == res[1][1]
+    assert np.isfinite(res[0][1][0])
+    ctx.set_kernel(0)
