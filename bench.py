@@ -218,6 +218,8 @@ def batch_leg(ctx, count, size=256):
 
 
 def run_ours(args):
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
     import torch
     import effectivediffusivityfvm_b200 as E
     rank, local_rank, world = dist_env()
