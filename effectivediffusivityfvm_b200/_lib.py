@@ -75,6 +75,7 @@ def lib():
         "deff2d_default_params": (None, [C.POINTER(Params)]),
         "deff2d_solve_image": (i32, [vp, c_ubyte_p, i32, i32, C.POINTER(Params), C.POINTER(Result), c_double_p]),
         "deff2d_solve_batch": (i32, [vp, c_ubyte_p, i32, i32, i32, C.POINTER(Params), C.POINTER(Result), c_double_p]),
+        "deff2d_solve_image_slabs": (i32, [C.POINTER(vp), i32, c_ubyte_p, i32, i32, C.POINTER(Params), C.POINTER(Result), c_double_p]),
         "deff2d_domain_load": (i32, [vp, c_ubyte_p, i32, i32, i32, C.POINTER(Params)]),
         "deff2d_domain_load_slab": (i32, [vp, c_ubyte_p, i32, i32, i32, C.POINTER(Params), i64, i64, i32, c_ubyte_p]),
         "deff2d_domain_set_D": (i32, [vp, dbl, dbl, dbl]),

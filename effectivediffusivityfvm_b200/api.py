@@ -316,6 +316,26 @@ class Deff2D:
         return d.value
 
 
+def solve_image_slabs(contexts, gray, params, want_field=False):
+    """One image over the GPUs of `contexts` (Deff2D objects on different devices) from this one
+    process: row slabs, one host thread per device inside the library (csrc/multi.cpp)."""
+    gray = np.ascontiguousarray(gray, dtype=np.uint8)
+    H, W = gray.shape
+    res = Result()
+    field = np.empty((H * params.amp_y, W * params.amp_x), dtype=np.float64) if want_field else None
+    arr = (C.c_void_p * len(contexts))(*[c._h for c in contexts])
+    L = _lib.lib()
+    rc = L.deff2d_solve_image_slabs(arr, len(contexts), gray.ctypes.data_as(_lib.c_ubyte_p), W, H, C.byref(params), C.byref(res),
+                                    field.ctypes.data_as(_lib.c_double_p) if want_field else None)
+    if rc:
+        msgs = [L.deff2d_last_error(c._h).decode() for c in contexts]
+        raise Deff2DError("deff2d_solve_image_slabs failed (%d): %s" % (rc, "; ".join(m for m in msgs if m)))
+    out = res.as_dict()
+    if want_field:
+        out["field"] = field
+    return out
+
+
 def nccl_unique_id():
     buf = (C.c_ubyte * _lib.NCCL_ID_BYTES)()
     rc = _lib.lib().deff2d_nccl_unique_id(buf)

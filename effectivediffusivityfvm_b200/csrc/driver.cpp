@@ -90,7 +90,20 @@ DEFF2D_EXPORT int deff2d_run_input_file(deff2d_ctx *ctx, const char *path)
         deff2d_result res;
         std::vector<double> field;
         if (in.print_cmap == 1) field.resize((size_t)W * in.p.amp_x * (size_t)H * in.p.amp_y);
-        rc = deff2d_solve_image(ctx, gray, W, H, &in.p, &res, in.print_cmap == 1 ? field.data() : nullptr);
+        if (in.devices > 1) {
+            // one large image over several GPUs: row slabs, one host thread per device (multi.cpp)
+            std::vector<deff2d_ctx *> ctxs{ctx};
+            for (int d = 1; d < in.devices; d++) {
+                deff2d_ctx *cx = nullptr;
+                if (deff2d_create(&cx, d) != DEFF2D_OK) break;      // fewer GPUs than asked for: use what is there
+                ctxs.push_back(cx);
+            }
+            rc = deff2d_solve_image_slabs(ctxs.data(), (int)ctxs.size(), gray, W, H, &in.p, &res,
+                                          in.print_cmap == 1 ? field.data() : nullptr);
+            for (size_t d = 1; d < ctxs.size(); d++) deff2d_destroy(ctxs[d]);
+        } else {
+            rc = deff2d_solve_image(ctx, gray, W, H, &in.p, &res, in.print_cmap == 1 ? field.data() : nullptr);
+        }
         deff2d_free(gray);
         if (rc) return rc;
         if ((rc = deff2d_write_csv_single(&in, &res))) return rc;   // cuh:1821, cuh:1612

@@ -113,6 +113,13 @@ int deff2d_solve_image(deff2d_ctx *ctx, const uint8_t *gray, int W, int H,
 int deff2d_solve_batch(deff2d_ctx *ctx, const uint8_t *gray, int count, int W, int H,
                        const deff2d_params *p, deff2d_result *results, double *fields);
 
+/* One image over several GPUs from one host process (not in the reference, which is
+ * single-GPU: cudaSetDevice(0), cuh:908): ctxs[0..nctx) are contexts on different devices; the
+ * domain is split into row slabs, one host thread per device, halo exchange and flux all-reduce
+ * over NCCL.  Same driver logic, results and `field` layout as deff2d_solve_image. */
+int deff2d_solve_image_slabs(deff2d_ctx *const *ctxs, int nctx, const uint8_t *gray, int W, int H,
+                             const deff2d_params *p, deff2d_result *res, double *field);
+
 /* ---- device-resident stepping (tests, benchmarks, multi-GPU slabs) ------------------- */
 
 /* Upload an image, threshold/amplify it into the per-cell phase codes, run FloodFill

@@ -750,3 +750,32 @@ def test_graph_replay_long_runs_match_streaming(ctx):
     assert np.array_equal(res[0][0], res[1][0], equal_nan=True) and res[0][1] == res[1][1]
     assert np.isfinite(res[0][1][0])
     ctx.set_kernel(0)
+
+
+def test_single_process_multi_gpu_slabs_match_single_gpu(ctx):
+    """deff2d_solve_image_slabs (csrc/multi.cpp): one host process, one thread per GPU, NCCL halo
+    exchange -- same stage sequence, sweep counts, Deff (1e-12) and field as the single-GPU solve."""
+    import torch
+    n = min(torch.cuda.device_count(), 4)
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    others = [E.Deff2D(d) for d in range(1, n)]
+    try:
+        img3 = blobs(71, (300, 260), levels=(0, 150, 255), fracs=(0.3, 0.4))
+        img2 = blobs(72, (280, 200))
+        cases = [(img3, E.default_params(Ds=0.0, Df=1.0, Dg=300.0, mode=E.MODE_3PH, check_every=400, max_iter=4000, tol=1e-4, amp_y=2)),
+                 (img2, E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH, check_every=500, max_iter=6000, tol=1e-4)),
+                 (img2, E.default_params(Ds=1.0, Df=12000.0, mode=E.MODE_2PH_SINGLE, check_every=500, max_iter=3000, tol=1e-4))]
+        for img, p in cases:
+            one = ctx.solve_image(img, p, want_field=True)
+            many = E.solve_image_slabs([ctx] + others, img, p, want_field=True)
+            for k in ("iters", "nstages", "pathflag", "porosity", "SVF", "LVF", "total_iters", "n_cells", "stage_D"):
+                assert many[k] == one[k], (k, many[k], one[k])
+            assert rel(many["deff"], one["deff"]) < 1e-12 and abs(many["conv"] - one["conv"]) < 1e-12
+            for a, b in zip(many["stage_deff_raw"], one["stage_deff_raw"]):
+                assert rel(a, b) < 1e-12
+            assert np.array_equal(np.isnan(many["field"]), np.isnan(one["field"]))
+            assert np.nanmax(np.abs(many["field"] - one["field"])) < 1e-13
+    finally:
+        for c in others:
+            c.close()
