@@ -92,6 +92,7 @@ def lib():
         "deff2d_set_kernel": (i32, [vp, i32, i32]),
         "deff2d_set_batch_slots": (i32, [vp, i32]),
         "deff2d_set_floodfill": (i32, [vp, i32]),
+        "deff2d_set_graphs": (i32, [vp, i32]),
         "deff2d_kernel_launches": (i64, [vp]),
         "deff2d_stream": (vp, [vp]),
         "deff2d_domain_buffers": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]),

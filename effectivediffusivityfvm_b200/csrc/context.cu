@@ -706,6 +706,13 @@ DEFF2D_EXPORT int deff2d_set_kernel(deff2d_ctx *c, int kernel, int tblock)
     return DEFF2D_OK;
 }
 
+DEFF2D_EXPORT int deff2d_set_graphs(deff2d_ctx *c, int enable)
+{
+    if (!c) return DEFF2D_ERR_ARG;
+    c->use_graphs = enable != 0;
+    return DEFF2D_OK;
+}
+
 DEFF2D_EXPORT int deff2d_set_floodfill(deff2d_ctx *c, int mode)
 {
     if (!c || mode < 0 || mode > 2) return DEFF2D_ERR_ARG;

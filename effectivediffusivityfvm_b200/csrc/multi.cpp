@@ -104,6 +104,9 @@ DEFF2D_EXPORT int deff2d_solve_image_slabs(deff2d_ctx *const *ctxs, int nctx, co
     auto work = [&](int r) {
         RankOut &o = out[(size_t)r];
         deff2d_ctx *c = ctxs[r];
+        // NCCL reports an internal error when send/recv of ranks that are threads of one process are
+        // captured into CUDA graphs (measured, NCCL 2.28): enqueue the passes directly in this mode
+        deff2d_set_graphs(c, 0);
         if ((o.rc = deff2d_nccl_init(c, id, r, n))) return;
         const int s0 = (int)((int64_t)H * r / n), s1 = (int)((int64_t)H * (r + 1) / n);
         const int sa = (r > 0) ? halo_src : 0, sb = (r < n - 1) ? halo_src : 0;
@@ -138,6 +141,7 @@ DEFF2D_EXPORT int deff2d_solve_image_slabs(deff2d_ctx *const *ctxs, int nctx, co
     for (int r = 1; r < n; r++) pool.emplace_back(work, r);
     work(0);
     for (auto &t : pool) t.join();
+    for (int r = 0; r < n; r++) deff2d_set_graphs(ctxs[r], 1);
     for (int r = 0; r < n; r++) if (out[(size_t)r].rc) return out[(size_t)r].rc;
 
     const RankOut &o0 = out[0];

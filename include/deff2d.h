@@ -168,6 +168,9 @@ int deff2d_set_floodfill(deff2d_ctx *ctx, int mode);
  * (0 = library default, sized from the image size); finished images are replaced from the
  * queue.  Tuning / test hook. */
 int deff2d_set_batch_slots(deff2d_ctx *ctx, int max_slots);
+/* CUDA-graph replay of long runs of passes: 1 (default) on, 0 off.  Tuning hook; the single-process
+ * multi-GPU driver switches it off (NCCL cannot capture when its ranks are threads of one process). */
+int deff2d_set_graphs(deff2d_ctx *ctx, int enable);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t deff2d_kernel_launches(const deff2d_ctx *ctx);
 /* The CUDA stream (cudaStream_t as an opaque pointer) all work of the context is enqueued on. */
