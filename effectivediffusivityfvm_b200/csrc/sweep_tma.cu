@@ -119,7 +119,9 @@ struct Cfg {
 // through L1 win); writing the patches straight to global memory with 16-byte stores instead of
 // staging the output box for one bulk tensor store (647 vs 702, 532 vs 547); with two patch rows per
 // warp (square tiles), exchanging the row between them by shuffles instead of shared memory
-// (763 vs 817, 610 vs 650: a 64-bit shuffle costs more LSU time than an 8-byte shared-memory access).
+// (763 vs 817, 610 vs 650: a 64-bit shuffle costs more LSU time than an 8-byte shared-memory access);
+// two 64-thread named barriers per sweep between neighbouring warps instead of one CTA-wide barrier
+// (685 vs 828).
 template <class C, bool LIST>
 __global__ void __launch_bounds__(C::NT, 1)
 k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, double om,
