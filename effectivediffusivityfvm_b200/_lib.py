@@ -23,7 +23,7 @@ class Params(C.Structure):
                 ("max_iter", C.c_int64), ("tol", C.c_double),
                 ("mode", C.c_int), ("check_every", C.c_int),
                 ("omega", C.c_double), ("tblock", C.c_int),
-                ("verbose", C.c_int), ("strict_reference", C.c_int)]
+                ("verbose", C.c_int), ("residual_tol", C.c_double), ("strict_reference", C.c_int)]
 
 
 class Result(C.Structure):

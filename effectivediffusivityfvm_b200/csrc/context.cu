@@ -160,9 +160,19 @@ int solve_loop(deff2d_ctx *c, double tol, int64_t max_iter, bool verbose_checks,
             launch_flux(c->stream, view(c), c->Dphase, c->CL, c->CR, c->NxG, c->own_first, c->own_rows, c->d_state);
             c->launches++;
             if ((rc = slab_allreduce_q(c))) return rc;
-            launch_check(c->stream, c->d_state, c->NyG, c->CL, c->CR, tol, last);
+            // residual mode: the Deff-change test is switched off (tol -1 is never reached; NaN still stops)
+            launch_check(c->stream, c->d_state, c->NyG, c->CL, c->CR, c->residual_tol > 0 ? -1.0 : tol, last);
             c->launches++;
             if ((rc = read_state(c))) return rc;
+            if (c->residual_tol > 0 && !c->h_state->stop) {
+                CU(cudaMemsetAsync(c->d_scalar, 0, sizeof(double), c->stream));
+                launch_residual(c->stream, view(c), c->Dphase, c->CL, c->CR, c->NxG, c->NyG, c->d_scalar);
+                c->launches++;
+                CU(cudaMemcpyAsync(c->h_scalar, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                c->h_state->resid = *c->h_scalar;
+                if (!(*c->h_scalar > c->residual_tol)) { iter = last + 1; stopped = true; break; }
+            }
             if (verbose_checks)     // cuh:1270
                 std::printf("Iteration = %d, Deff = %1.3e, Deff Change = %1.3e\n", (int)last,
                             c->h_state->deff_new / print_div, c->h_state->change);
@@ -197,6 +207,7 @@ static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc,
     c->CL = p->CL; c->CR = p->CR;
     c->omega = (p->omega > 0) ? p->omega : 2.0 / 3.0;
     c->check_every = (p->check_every > 0) ? p->check_every : 10000;
+    c->residual_tol = (p->residual_tol > 0 && !c->slab_domain) ? p->residual_tol : 0;
     c->Dphase[0] = p->Df; c->Dphase[1] = p->Ds; c->Dphase[2] = p->Dg;
     c->cur = 0;
     c->tma_ready = false;

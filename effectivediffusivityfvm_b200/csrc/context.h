@@ -31,6 +31,7 @@ struct deff2d_ctx {
     double Dphase[3] = {1, 0, 0};    // fluid, solid, gas of the current stage
     double CL = 0, CR = 1, omega = 2.0 / 3.0;
     int check_every = 10000;
+    double residual_tol = 0;         // > 0: stop on the residual instead of the Deff change (non-parity mode)
     int cur = 0;                     // x[cur] holds the newest iterate
     int pathflag = 0;
     double porosity = 0;

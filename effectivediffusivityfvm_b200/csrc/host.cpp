@@ -92,6 +92,7 @@ DEFF2D_EXPORT void deff2d_default_params(deff2d_params *p)
     p->omega = 2.0 / 3.0;
     p->tblock = 0;
     p->verbose = 0;
+    p->residual_tol = 0;
     p->strict_reference = 1;
 }
 

@@ -54,6 +54,10 @@ typedef struct {
     double omega;             /* 0 -> 2/3, the reference's damping               cuh:72   */
     int tblock;               /* sweeps fused per HBM pass; 0 -> library default         */
     int verbose;              /* 1: print the reference's per-check / per-stage stdout lines */
+    double residual_tol;      /* > 0: NON-PARITY stop rule -- at every check stop when the reference's (dead) Residual
+                               * (mean |flux imbalance| per cell, cuh:451-494) is <= residual_tol instead of testing
+                               * the relative Deff change (cuh:1232); 0 (default): the reference rule.  Single-GPU domains.
+                               * (That Residual is kept verbatim: it scales every face by dy/dx and so plateaus above 0.) */
     int strict_reference;     /* 1 (default): bit-faithful reference quirks.  0: defined behaviour instead --
                                * 2-phase single with Df < 10 runs one stage at Df (Q8, cuh:1714/1761), FloodFill
                                * seeds the left column only (Q11, cuh:601), pixel == 150 is solid in the

@@ -779,3 +779,25 @@ def test_single_process_multi_gpu_slabs_match_single_gpu(ctx):
     finally:
         for c in others:
             c.close()
+
+
+def test_opt_in_residual_stop_rule(ctx):
+    """residual_tol > 0 (non-parity mode): the loop stops at the first check where the
+    reference's Residual (cuh:451-494) is <= residual_tol, whatever the Deff change does."""
+    img = blobs(55, (48, 64))
+    base = dict(Ds=1e-2, Df=1.0, mode=E.MODE_2PH_BATCH, check_every=250, max_iter=100000)
+    ref = ctx.solve_image(img, E.default_params(tol=1e-9, **base))            # reference rule, tight
+    # the reference's Residual, kept verbatim, scales every face by dy/dx and plateaus (here near 8.4e-4)
+    # instead of vanishing at the solution: the tolerance has to sit above that plateau
+    rtol = 8.45e-4
+    got = ctx.solve_image(img, E.default_params(tol=1e-9, residual_tol=rtol, **base))
+    it = got["iters"][0]
+    assert (it - 1) % 250 == 0 and 1 < it < ref["iters"][0]
+    # the residual at the stopping check is below the tolerance, one check earlier it is not
+    p = E.default_params(**base)
+    ctx.domain_load(img, 2, p)
+    ctx.sweeps(it - 250)
+    assert ctx.residual() > rtol
+    ctx.sweeps(250)
+    assert ctx.residual() <= rtol
+    assert rel(ctx.flux()[0], got["deff_raw"]) < 1e-12
