@@ -801,3 +801,29 @@ def test_opt_in_residual_stop_rule(ctx):
     ctx.sweeps(250)
     assert ctx.residual() <= rtol
     assert rel(ctx.flux()[0], got["deff_raw"]) < 1e-12
+
+
+def test_bundled_00042_stage_checkpoints_from_the_reference(ctx, golden_images):
+    """Shipped input.txt verbatim on the bundled 00042.jpg (2.0 M cells, 3-phase): un-normalised Deff
+    at every check of pre-conditioning stage 1 (DCG = 10, stops at sweep 150 001 because the signed
+    change crosses zero) and at the first 11 checks of stage 2 (DCG = 100), as produced by the
+    reference's own host code + kernel body."""
+    img = golden_images["00042"]
+    p = E.default_params()                                     # Ds 0, Df 1, Dg 1237500, tol 1e-5, MaxIter 5e5
+    ctx.domain_load(img, 3, p)
+    ctx.set_D(0.0, 1.0, 10.0)                                  # cuh:1492-1531
+    r1 = ctx.solve(p.tol * 10, 1000000)                        # cuh:1501-1502
+    stage1 = [9.255802317031, 3.436492926626, 3.377988028260, 3.346242512934, 3.325747837646, 3.311021646843,
+              3.299831844933, 3.291133004473, 3.284350477833, 3.279116522299, 3.275166467026, 3.272294662892,
+              3.270333924566, 3.269144735927, 3.268608828991, 3.268624930899]
+    assert r1["iters"] == 150001 and len(r1["trace"]) == 16
+    for a, b in zip(r1["trace"], stage1):
+        assert rel(a, b) < 1e-9
+    assert abs(r1["conv"] - (-4.926e-06)) < 1e-9
+    ctx.set_D(0.0, 1.0, 100.0)                                 # stage 2, warm start
+    r2 = ctx.solve(p.tol * 10, 100002)
+    stage2 = [28.86247113599, 28.84390816332, 28.81427679676, 28.78700150716, 28.76275598923, 28.74128132848,
+              28.72220433724, 28.70516255849, 28.68982560472, 28.67589684461, 28.66311119152]
+    assert r2["iters"] == 100002 and len(r2["trace"]) == 11
+    for a, b in zip(r2["trace"], stage2):
+        assert rel(a, b) < 1e-9
