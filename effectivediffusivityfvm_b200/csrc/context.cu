@@ -210,7 +210,6 @@ static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc,
     c->residual_tol = (p->residual_tol > 0 && !c->slab_domain) ? p->residual_tol : 0;
     c->Dphase[0] = p->Df; c->Dphase[1] = p->Ds; c->Dphase[2] = p->Dg;
     c->cur = 0;
-    c->tma_ready = false;
     const size_t cells = (size_t)c->rows * (size_t)c->pitch;
     int rc;
     if ((rc = ensure(c, c->x[0], cells))) return rc;

@@ -57,7 +57,6 @@ struct deff2d_ctx {
     int64_t launches = 0;
 
     // TMA tiled sweep state (sweep_tma.cu)
-    bool tma_ready = false;
     void *tma = nullptr;
     int64_t ghost_period = 0;        // every ghost_period-th column (from -1) is a Dirichlet ghost column: Nx + 1
                                      // for one domain, image width + 1 in a packed batch

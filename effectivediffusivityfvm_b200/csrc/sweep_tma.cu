@@ -8,14 +8,20 @@
 //     index of every cell, cp.async.bulk.tensor.2d, mbarrier complete_tx), double buffered so the next tile's
 //     copy overlaps the current tile's sweeps; out-of-range boxes are zero filled by TMA;
 //   * each thread owns a PX x PY patch of cells for the whole tile visit: the patch values
-//     and its 4 x PX x PY sweep weights (looked up once per tile from the per-stage LUT with
-//     the 11-bit phase-neighbourhood index) live in registers;
-//   * T sweeps run on chip; per sweep a thread publishes only its patch boundary to a planar
-//     exchange buffer (column-phase planes -> conflict-free LDS/STS) and reads its 2(PX+PY)
-//     halo values back; one __syncthreads per sweep;
-//   * after T sweeps the (TW-2T) x (TH-2T) interior is written back with one bulk tensor
-//     store through a tensor map that covers only the interior of the domain (so ghost
-//     columns/rows are never overwritten and edge tiles are clipped by the hardware).
+//     and its 4 x PX x PY sweep weights (gathered once per tile from the stage's compact planar
+//     table with the precomputed per-cell slot; one broadcast read when the whole warp's
+//     patches are single-phase) live in registers;
+//   * T sweeps run on chip; per sweep a thread gets its W / E halo from the neighbouring lanes
+//     by warp shuffles (a warp spans the tile width) and publishes only its top and bottom
+//     patch rows to a planar exchange buffer (column-phase planes -> conflict-free LDS/STS),
+//     reading the rows of the patches above and below back; one __syncthreads per sweep;
+//   * after T sweeps the (TW-2*TE) x (TH-2T) interior is staged in shared memory and written
+//     back with one bulk tensor store through a tensor map that covers only the interior of the
+//     domain (so the outer ghost ring is never overwritten and edge tiles are clipped by the hardware);
+//   * long runs of passes are replayed as CUDA graphs (tma_passes).
+//
+// Default geometry: square 64 x 64 tiles (Family 3: 16 lanes side by side, two patch rows per warp,
+// 4 x 4 cells per thread, 256 threads, one CTA per SM), 8 sweeps per pass.
 //
 // Overlapped tiling is algebraically identical to T plain sweeps: a cell at distance >= T
 // from the tile edge only ever sees values that are exact at each intermediate level.

@@ -162,8 +162,11 @@ int deff2d_domain_info(deff2d_ctx *ctx, int64_t *Nx, int64_t *Ny, int *pathflag,
                        double *SVF, double *LVF);
 int deff2d_sync(deff2d_ctx *ctx);
 
-/* Select the sweep kernel: 0 = library default, 1 = plain streaming kernel (one sweep per
- * HBM pass), 2 = TMA-staged tiled kernel with `tblock` sweeps per pass. */
+/* Select the sweep kernel: 0 = library default (TMA-staged tiled kernel, square 64 x 64 tiles, 8
+ * sweeps per pass, CUDA-graph replay), 1 = plain streaming kernel (one sweep per HBM pass), 2..5 =
+ * the tiled kernel with `tblock` (1..8) sweeps per pass in one of its tile geometries (2: 128 x 32
+ * tiles with 2 x 8 cells per thread, 3: 128 x 32 with 4 x 4, 4: 128 x 32 with 2 x 4 and 512 threads,
+ * 5: 64 x 64 with 4 x 4 -- the default's).  All give bit-identical iterates.  Tuning / test hook. */
 int deff2d_set_kernel(deff2d_ctx *ctx, int kernel, int tblock);
 /* Where FloodFill (cuh:557-713) runs for whole-domain loads: 0 = automatic (device from 64 K cells),
  * 1 = host (FIFO flood), 2 = device (label propagation).  Same result either way. */
