@@ -260,3 +260,36 @@ def test_input_file_extension_keys(tmp_path):
     p.write_text("Phases: 3\n")
     inp = E.read_input_file(p)
     assert (inp.devices, inp.field_npy) == (1, 0)
+
+
+def test_jpeg_decoder_random_files_against_reference_decoder(tmp_path):
+    """Freshly encoded grayscale JPEGs (random content, size, quality, baseline / progressive /
+    optimised / restart markers) through the library's decoder and through the reference's own
+    decoder built from /root/reference (oracle/_ref): identical pixels.  Skipped where the
+    reference build or PIL is not available (the committed fixtures cover that case)."""
+    if O.reference("cpu") is None:
+        pytest.skip("oracle/_ref/libref_cpu.so not built")
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(2026)
+    for k in range(14):
+        h, w = int(rng.integers(1, 90)), int(rng.integers(1, 130))
+        kind = k % 3
+        if kind == 0:
+            a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+        elif kind == 1:
+            yy, xx = np.mgrid[0:h, 0:w]
+            a = ((np.sin(xx / 7.0) + np.cos(yy / 5.0) + 2) * 63).astype(np.uint8)
+        else:
+            a = np.where(rng.random((h, w)) < 0.5, 30, 220).astype(np.uint8)
+        kw = dict(quality=int(rng.integers(5, 101)))
+        if k % 2:
+            kw["progressive"] = True
+        if k % 4 == 0:
+            kw["optimize"] = True
+        if k % 5 == 0:
+            kw["restart_marker_blocks"] = int(rng.integers(1, 9))
+        p = tmp_path / ("r%d.jpg" % k)
+        Image.fromarray(a).save(p, "JPEG", **kw)
+        got, ch = E.load_image(p)
+        want, ch2 = O.ref_decode(str(p))
+        assert ch == ch2 == 1 and np.array_equal(got, want), (k, h, w, kw)
