@@ -293,3 +293,25 @@ def test_jpeg_decoder_random_files_against_reference_decoder(tmp_path):
         got, ch = E.load_image(p)
         want, ch2 = O.ref_decode(str(p))
         assert ch == ch2 == 1 and np.array_equal(got, want), (k, h, w, kw)
+
+
+def test_png_decoder_variants_against_reference_decoder(tmp_path):
+    """PNG bit depths and colour types (8/16-bit gray, 1/2/4-bit gray, gray+alpha, palette) through
+    the library's decoder and the reference's: same pixels, same channel count (the drivers accept
+    only channel count 1, cuh:1665-1668)."""
+    if O.reference("cpu") is None:
+        pytest.skip("oracle/_ref/libref_cpu.so not built")
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(1)
+    a8 = rng.integers(0, 256, (37, 53), dtype=np.uint8)
+    a16 = rng.integers(0, 65536, (37, 53), dtype=np.uint16)
+    cases = {"L": (Image.fromarray(a8), {}), "I16": (Image.fromarray(a16), {}), "bit1": (Image.fromarray(a8 > 127), {}),
+             "LA": (Image.fromarray(np.stack([a8, 255 - a8], -1), "LA"), {}), "P": (Image.fromarray(a8).convert("P"), {}),
+             "bit4": (Image.fromarray((a8 >> 4) << 4), {"bits": 4}), "bit2": (Image.fromarray((a8 >> 6) << 6), {"bits": 2})}
+    for name, (im, kw) in cases.items():
+        p = tmp_path / (name + ".png")
+        im.save(p, "PNG", **kw)
+        got, ch = E.load_image(p)
+        want, ch2 = O.ref_decode(str(p))
+        assert ch == ch2, name
+        assert np.array_equal(got, want), name
