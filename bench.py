@@ -394,7 +394,7 @@ def main():
     ap.add_argument("--ref-crop", type=int, default=0, help="use only the first N source rows for the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-cuda-sweeps", type=int, default=1001)
-    ap.add_argument("--batch-images", type=int, default=0, help="also time the packed batch mode on this many config-3 images per GPU")
+    ap.add_argument("--batch-images", type=int, default=64, help="also time the packed batch mode on this many config-3 images per GPU (0: skip)")
     ap.add_argument("--allow-short-warmup", action="store_true")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not poll NVML during the timed region")
     args = ap.parse_args()
