@@ -127,7 +127,7 @@ struct Cfg {
 // warp (square tiles), exchanging the row between them by shuffles instead of shared memory
 // (763 vs 817, 610 vs 650: a 64-bit shuffle costs more LSU time than an 8-byte shared-memory access);
 // two 64-thread named barriers per sweep between neighbouring warps instead of one CTA-wide barrier
-// (685 vs 828).
+// (685 vs 828); two 128-thread CTAs per SM on 64 x 32 tiles (744 at T = 4 vs 827).
 template <class C, bool LIST>
 __global__ void __launch_bounds__(C::NT, 1)
 k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, double om,
