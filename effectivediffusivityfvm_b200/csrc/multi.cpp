@@ -7,8 +7,11 @@
 #include "deff2d_internal.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -101,13 +104,24 @@ DEFF2D_EXPORT int deff2d_solve_image_slabs(deff2d_ctx *const *ctxs, int nctx, co
 
     struct RankOut { int rc = 0; std::vector<int64_t> iters; std::vector<double> deff, ms; double conv = 0; };
     std::vector<RankOut> out((size_t)n);
+    // A rank whose slab failed to load must not leave the others waiting in a halo exchange: all ranks
+    // meet once after loading and give up together if any of them failed.
+    std::mutex mtx;
+    std::condition_variable cv;
+    int arrived = 0;
+    std::atomic<int> failed(0);
+    auto meet = [&]() {
+        std::unique_lock<std::mutex> lk(mtx);
+        if (++arrived == n) cv.notify_all();
+        else cv.wait(lk, [&] { return arrived == n; });
+    };
     auto work = [&](int r) {
         RankOut &o = out[(size_t)r];
         deff2d_ctx *c = ctxs[r];
         // NCCL reports an internal error when send/recv of ranks that are threads of one process are
         // captured into CUDA graphs (measured, NCCL 2.28): enqueue the passes directly in this mode
         deff2d_set_graphs(c, 0);
-        if ((o.rc = deff2d_nccl_init(c, id, r, n))) return;
+        if ((o.rc = deff2d_nccl_init(c, id, r, n))) { failed.store(1); meet(); return; }
         const int s0 = (int)((int64_t)H * r / n), s1 = (int)((int64_t)H * (r + 1) / n);
         const int sa = (r > 0) ? halo_src : 0, sb = (r < n - 1) ? halo_src : 0;
         const int64_t a0 = (int64_t)(s0 - sa) * p->amp_y, a1 = (int64_t)(s1 + sb) * p->amp_y;       // local amplified rows [a0, a1)
@@ -116,7 +130,9 @@ DEFF2D_EXPORT int deff2d_solve_image_slabs(deff2d_ctx *const *ctxs, int nctx, co
         o.rc = deff2d_domain_load_slab(c, gray + (size_t)(s0 - sa) * W, W, s1 - s0, nphase, &q, (int64_t)s0 * p->amp_y, Ny, halo,
                                        nphase == 3 ? grid.data() + (size_t)a0 * Nx : nullptr);
         (void)a1;
-        if (o.rc) return;
+        if (o.rc) failed.store(1);
+        meet();
+        if (failed.load()) { if (!o.rc) o.rc = DEFF2D_ERR_STATE; return; }
         for (const Stage &st : stages) {
             if ((o.rc = deff2d_domain_set_D(c, st.Ds, st.Df, st.Dg))) return;
             int64_t it = 0;
