@@ -315,3 +315,40 @@ def test_png_decoder_variants_against_reference_decoder(tmp_path):
         want, ch2 = O.ref_decode(str(p))
         assert ch == ch2, name
         assert np.array_equal(got, want), name
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/deff2d.h is the drop-in boundary: it must compile as C (no C++ or CUDA types in any
+    signature) and a plain C program must link against libdeff2d.so and call the host-side entry
+    points without a GPU."""
+    src = tmp_path / "use_abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "deff2d.h"
+int main(void) {
+    deff2d_params p;
+    deff2d_default_params(&p);
+    if (deff2d_version() != DEFF2D_VERSION || p.Dg != 1237500.0 || p.mode != DEFF2D_MODE_3PH) return 2;
+    unsigned char grid[12] = {0,0,1,0, 0,1,1,0, 0,0,0,0};
+    int pf = deff2d_floodfill(grid, 4, 3);
+    static double lut[2048 * 4];
+    static unsigned char dead[2048];
+    if (deff2d_build_tables(0.0, 1.0, 5.0, 8, 8, 0.0, 1.0, 0.0, lut, dead) != DEFF2D_OK) return 3;
+    int ow, oh, tw, th;
+    if (deff2d_tile_geometry(8, &ow, &oh, &tw, &th) != DEFF2D_OK) return 4;
+    printf("%d %d %dx%d %dx%d %zu %zu %zu\n", pf, (int)dead[1 | 1 << 2 | 1 << 4 | 1 << 6 | 1 << 8], ow, oh, tw, th,
+           sizeof(deff2d_result), sizeof(deff2d_params), sizeof(deff2d_input));
+    return 0;
+}
+''')
+    exe = tmp_path / "use_abi"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-ldeff2d", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert out[0] == "1"                      # the open path along the bottom row reaches the last column
+    assert out[1] == "1"                      # an all-solid neighbourhood with Ds = 0 has A0 = 0 (quirk Q13)
+    assert out[2] == "48x48" and out[3] == "64x64"
+    # the ctypes mirror matches the C layout
+    assert [int(v) for v in out[4:7]] == [C.sizeof(_lib.Result), C.sizeof(_lib.Params), C.sizeof(_lib.Input)]
