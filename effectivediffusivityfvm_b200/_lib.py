@@ -110,6 +110,7 @@ def lib():
         "deff2d_read_input_file": (i32, [C.c_char_p, C.POINTER(Input)]),
         "deff2d_write_csv_single": (i32, [C.POINTER(Input), C.POINTER(Result)]),
         "deff2d_write_csv_batch": (i32, [C.POINTER(Input), C.POINTER(Result), i32]),
+        "deff2d_append_csv_batch_row": (i32, [C.POINTER(Input), i32, C.POINTER(Result)]),
         "deff2d_write_cmap": (i32, [C.c_char_p, c_double_p, i64, i64]),
         "deff2d_write_field_npy": (i32, [C.c_char_p, c_double_p, i64, i64]),
         "deff2d_run_input_file": (i32, [vp, C.c_char_p]),

@@ -196,7 +196,8 @@ DEFF2D_EXPORT int deff2d_run_input_file(deff2d_ctx *ctx, const char *path)
         return deff2d_write_csv_batch(&in, results.data(), in.num_images);
     }
     // one image at a time: keeps the reference's per-image stdout order (Verbose: 1) and handles
-    // images of different sizes
+    // images of different sizes; every row is appended as soon as its image is solved
+    if ((rc = deff2d_append_csv_batch_row(&in, -1, nullptr))) return rc;
     for (int k = 0; k < in.num_images; k++) {
         const int W = Ws[(size_t)k], H = Hs[(size_t)k];
         std::vector<double> field;
@@ -204,11 +205,12 @@ DEFF2D_EXPORT int deff2d_run_input_file(deff2d_ctx *ctx, const char *path)
         deff2d_params p = in.p;
         rc = deff2d_solve_batch(ctx, singles[(size_t)k].data(), 1, W, H, &p, &results[(size_t)k], cmap ? field.data() : nullptr);
         if (rc) return rc;
+        if ((rc = deff2d_append_csv_batch_row(&in, k, &results[(size_t)k]))) return rc;
         if (cmap) {
             char cm[100];
             std::snprintf(cm, sizeof(cm), "CMAP_%05d.csv", k);      // cuh:2396
             if ((rc = deff2d_write_cmap(cm, field.data(), (int64_t)W * in.p.amp_x, (int64_t)H * in.p.amp_y))) return rc;
         }
     }
-    return deff2d_write_csv_batch(&in, results.data(), in.num_images);
+    return DEFF2D_OK;
 }

@@ -165,26 +165,48 @@ DEFF2D_EXPORT int deff2d_write_csv_single(const deff2d_input *in, const deff2d_r
     return DEFF2D_OK;
 }
 
-// outputBatch (cuh:204-217) / outputBatch3Phase (cuh:219-232).
+// outputBatch (cuh:204-217) / outputBatch3Phase (cuh:219-232): header and rows.  The reference
+// buffers all rows and writes them when the last image is done ("if the code is interrupted,
+// all progress is lost", doc 3.6); the row-wise entry point lets the driver append each row
+// as soon as its image has finished -- the finished file is byte-identical.
+static void csv_batch_header(FILE *o, const deff2d_input *in)
+{
+    if (in->nphase == 3) std::fprintf(o, "imgNum,SVF,LVF,PathFlag,Deff,Time,nElements,converge,ds,df,dg\n");
+    else std::fprintf(o, "imgNum,porosity,PathFlag,Deff,Time,nElements,converge,ds,df\n");
+}
+
+static void csv_batch_row(FILE *o, const deff2d_input *in, int i, const deff2d_result *r)
+{
+    if (in->nphase == 3)
+        std::fprintf(o, "%d,%f,%f,%d,%1.5e,%f,%d,%1.5e,%1.5e,%1.5e,%1.5e\n", i, r->SVF, r->LVF, r->pathflag, r->deff,
+                     r->solve_ms / 1000, (int)r->n_cells, r->conv, in->p.Ds, r->last_df, in->p.Dg);
+    else
+        std::fprintf(o, "%d,%f,%d,%f,%f,%d,%f,%f,%f\n", i, r->porosity, r->pathflag, r->deff, r->solve_ms / 1000,
+                     (int)r->n_cells, r->conv, in->p.Ds, r->last_df);
+}
+
 DEFF2D_EXPORT int deff2d_write_csv_batch(const deff2d_input *in, const deff2d_result *r, int count)
 {
     if (!in || (!r && count > 0)) return DEFF2D_ERR_ARG;
     FILE *o = std::fopen(in->output_name, "a+");
     if (!o) return DEFF2D_ERR_IO;
-    if (in->nphase == 3) {
-        std::fprintf(o, "imgNum,SVF,LVF,PathFlag,Deff,Time,nElements,converge,ds,df,dg\n");
-        for (int i = 0; i < count; i++)
-            std::fprintf(o, "%d,%f,%f,%d,%1.5e,%f,%d,%1.5e,%1.5e,%1.5e,%1.5e\n", i, r[i].SVF, r[i].LVF,
-                         r[i].pathflag, r[i].deff, r[i].solve_ms / 1000, (int)r[i].n_cells, r[i].conv,
-                         in->p.Ds, r[i].last_df, in->p.Dg);
-    } else {
-        std::fprintf(o, "imgNum,porosity,PathFlag,Deff,Time,nElements,converge,ds,df\n");
-        for (int i = 0; i < count; i++)
-            std::fprintf(o, "%d,%f,%d,%f,%f,%d,%f,%f,%f\n", i, r[i].porosity, r[i].pathflag, r[i].deff,
-                         r[i].solve_ms / 1000, (int)r[i].n_cells, r[i].conv, in->p.Ds, r[i].last_df);
-    }
+    csv_batch_header(o, in);
+    for (int i = 0; i < count; i++) csv_batch_row(o, in, i, r + i);
     std::fclose(o);
     return DEFF2D_OK;
+}
+
+// Crash-safe variant: index < 0 appends the header, index >= 0 appends (and flushes) row `index`.
+DEFF2D_EXPORT int deff2d_append_csv_batch_row(const deff2d_input *in, int index, const deff2d_result *r)
+{
+    if (!in || (index >= 0 && !r)) return DEFF2D_ERR_ARG;
+    FILE *o = std::fopen(in->output_name, "a+");
+    if (!o) return DEFF2D_ERR_IO;
+    if (index < 0) csv_batch_header(o, in);
+    else csv_batch_row(o, in, index, r);
+    const bool ok = std::fflush(o) == 0;
+    std::fclose(o);
+    return ok ? DEFF2D_OK : DEFF2D_ERR_IO;
 }
 
 // createCMAP / createCMAPBatch, cuh:497-554: "X,Y,C" then "%d,%d,%1.3e" per cell, y outer,

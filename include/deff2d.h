@@ -246,6 +246,9 @@ int deff2d_read_input_file(const char *path, deff2d_input *in);
 /* CSV / CMAP writers with the reference's exact formats (cuh:177-232, 497-554). */
 int deff2d_write_csv_single(const deff2d_input *in, const deff2d_result *r);
 int deff2d_write_csv_batch(const deff2d_input *in, const deff2d_result *r, int count);
+/* The same file row by row (index < 0: the header): lets a driver append every image's row as soon
+ * as it is solved instead of losing everything on an interruption (reference doc 3.6, cuh:2051). */
+int deff2d_append_csv_batch_row(const deff2d_input *in, int index, const deff2d_result *r);
 int deff2d_write_cmap(const char *path, const double *field, int64_t Nx, int64_t Ny);
 /* The same map as a NumPy .npy file (float64, shape (Ny, Nx)): binary companion of the CMAP text. */
 int deff2d_write_field_npy(const char *path, const double *field, int64_t Nx, int64_t Ny);

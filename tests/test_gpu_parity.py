@@ -514,6 +514,30 @@ def test_drop_in_executable_packed_batch(tmp_path):
         assert f[7] == "%f" % 0.01 and f[8] == "%f" % 1.0
 
 
+def test_drop_in_executable_batch_per_image_path_streams_rows(tmp_path):
+    """RunBatch: 1 with Verbose: 1 (the reference's per-image stdout order is kept, so images are
+    solved one at a time) and images of two sizes: rows are appended as each image finishes and the
+    finished CSV equals what the packed path writes for the same inputs."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(E.LIB_PATH), "deff2d")
+    imgs = [blobs(500 + k, (40, 56) if k != 2 else (48, 40), fracs=(0.55,)) for k in range(4)]
+    for k, im in enumerate(imgs):
+        (tmp_path / ("%05d.jpg" % k)).write_bytes(b"P5\n%d %d\n255\n" % (im.shape[1], im.shape[0]) + im.tobytes())
+    (tmp_path / "input.txt").write_text(
+        "Phases: 2\nDs: 0.01\nDf: 1\nDg: 0\nMeshAmpX: 1\nMeshAmpY: 1\nInputName: unused.jpg\nCR: 1\nCL: 0\n"
+        "OutputName: rows.csv\nprintCMap: 0\nCMapName: unused.csv\nConvergence: 1e-4\nMaxIter: 100000\nVerbose: 1\n"
+        "RunBatch: 1\nNumImages: 4\n")
+    out = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("Iterations taken = ") == 4
+    rows = (tmp_path / "rows.csv").read_text().strip().splitlines()
+    assert rows[0].startswith("imgNum,porosity") and len(rows) == 5
+    for k, im in enumerate(imgs):
+        ref = O.solve_image(im, O.make_opts(Ds=0.01, Df=1.0, nphase=2, tol=1e-4, max_iter=100000), O.MODE_2PH_BATCH)
+        f = rows[1 + k].split(",")
+        assert f[0] == str(k) and f[1] == "%f" % ref["porosity"] and f[3] == "%f" % ref["deff"] and f[5] == str(im.size)
+
+
 # ----------------------------------------------------------------------------- full-size properties
 
 def test_full_size_properties_config2(ctx, golden_images):

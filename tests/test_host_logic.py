@@ -352,3 +352,32 @@ int main(void) {
     assert out[2] == "48x48" and out[3] == "64x64"
     # the ctypes mirror matches the C layout
     assert [int(v) for v in out[4:7]] == [C.sizeof(_lib.Result), C.sizeof(_lib.Params), C.sizeof(_lib.Input)]
+
+
+def test_csv_batch_rows_streamed_equal_bulk_write(tmp_path):
+    """deff2d_append_csv_batch_row (header, then one flushed row per image) produces the same bytes
+    as deff2d_write_csv_batch, for both phase counts."""
+    L = _lib.lib()
+    rng = np.random.default_rng(4)
+    for nphase in (2, 3):
+        res = (_lib.Result * 3)()
+        for k in range(3):
+            res[k].porosity, res[k].SVF, res[k].LVF = rng.random(3)
+            res[k].deff, res[k].conv, res[k].solve_ms = rng.random() * 10.0 ** rng.integers(-3, 6), rng.normal() * 1e-6, rng.random() * 1e4
+            res[k].pathflag, res[k].n_cells, res[k].last_df = int(rng.integers(0, 2)), 65536, 1.0
+        files = []
+        for mode in ("bulk", "rows"):
+            inp = _lib.Input()
+            L.deff2d_default_params(C.byref(inp.p))
+            inp.nphase = nphase
+            inp.p.Ds, inp.p.Df, inp.p.Dg = 1e-3, 1.0, 1237500.0
+            path = tmp_path / ("%s%d.csv" % (mode, nphase))
+            inp.output_name = str(path).encode()
+            if mode == "bulk":
+                assert L.deff2d_write_csv_batch(C.byref(inp), res, 3) == 0
+            else:
+                assert L.deff2d_append_csv_batch_row(C.byref(inp), -1, None) == 0
+                for k in range(3):
+                    assert L.deff2d_append_csv_batch_row(C.byref(inp), k, C.byref(res[k])) == 0
+            files.append(path.read_bytes())
+        assert files[0] == files[1] and files[0].count(b"\n") == 4
