@@ -499,6 +499,10 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     g.pitch = c->pitch; g.CL = c->CL; g.CR = c->CR; g.ce = c->check_every; g.nstages = nstages;
 
     const int old_family = c->tile_family, old_tblock = c->tblock;
+    struct Restore {                                      // every exit path puts the caller's kernel selection back
+        deff2d_ctx *c; int fam, tb;
+        ~Restore() { c->tile_family = fam; c->tblock = tb; c->tile_list = nullptr; c->tile_count = 0; }
+    } restore_guard{c, old_family, old_tblock};
     c->tile_family = DEFF2D_DEFAULT_TILE_FAMILY;
     if (const char *e = std::getenv("DEFF2D_BATCH_FAMILY")) { const int v = std::atoi(e); if (v >= 0 && v <= 3) c->tile_family = v; }   // tuning
     // tile grids of the pass depths in use (T and the remainders 1..T-1)

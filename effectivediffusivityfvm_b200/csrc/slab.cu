@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "context.h"
@@ -44,16 +45,14 @@ struct NcclApi {
     std::string error;
 };
 
-static NcclApi *nccl_api()
+static void nccl_bind(NcclApi &api)
 {
-    static NcclApi api;
-    if (api.handle || !api.error.empty()) return &api;
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char *n : names) {
         api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
         if (api.handle) break;
     }
-    if (!api.handle) { api.error = std::string("cannot load libnccl.so.2: ") + dlerror(); return &api; }
+    if (!api.handle) { api.error = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
     bool ok = true;
     auto sym = [&](const char *name) { void *p = dlsym(api.handle, name); if (!p) ok = false; return p; };
     api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
@@ -66,6 +65,14 @@ static NcclApi *nccl_api()
     api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
     if (!ok) { api.error = "libnccl.so.2 lacks a required symbol"; api.handle = nullptr; }
+}
+
+// bound once per process, also when several device threads ask at the same time (multi.cpp)
+static NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] { nccl_bind(api); });
     return &api;
 }
 
