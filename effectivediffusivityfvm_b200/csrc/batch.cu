@@ -376,6 +376,7 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
                        deff2d_result *results, double *fields, const BatchStages &stages, const double *stageD,
                        int nstages)
 {
+    CUB(cudaSetDevice(c->device));                       // before anything is created: the caller's thread may sit on another device
     BatchState *b = static_cast<BatchState *>(c->batch);
     if (!b) {
         b = new BatchState();

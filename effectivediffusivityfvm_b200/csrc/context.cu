@@ -496,6 +496,7 @@ DEFF2D_EXPORT int deff2d_solve_image(deff2d_ctx *c, const uint8_t *gray, int W, 
                                      deff2d_result *res, double *field)
 {
     if (!c) return DEFF2D_ERR_ARG;
+    CU(cudaSetDevice(c->device));
     c->in_batch = false;
     return solve_image_impl(c, gray, W, H, p, res, field, 0);
 }
@@ -505,6 +506,7 @@ DEFF2D_EXPORT int deff2d_solve_batch(deff2d_ctx *c, const uint8_t *gray, int cou
 {
     if (!c) return DEFF2D_ERR_ARG;
     if (count < 0 || (count > 0 && (!gray || !results)) || !p) { set_error(c, "solve_batch: invalid argument"); return DEFF2D_ERR_ARG; }
+    CU(cudaSetDevice(c->device));
     int rc = batch_resident_solve(c, gray, count, W, H, p, results, fields);
     if (rc != 1) return rc;          // 1: the resident batch kernel does not cover this case
     c->in_batch = true;
@@ -556,6 +558,7 @@ DEFF2D_EXPORT int deff2d_domain_set_D(deff2d_ctx *c, double Ds, double Df, doubl
 {
     if (!c) return DEFF2D_ERR_ARG;
     if (!c->loaded) { set_error(c, "no domain loaded"); return DEFF2D_ERR_STATE; }
+    CU(cudaSetDevice(c->device));
     c->Dphase[0] = Df; c->Dphase[1] = Ds; c->Dphase[2] = Dg;
     return upload_tables(c);
 }
