@@ -464,7 +464,8 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     if ((rc = grow(c->img, npix * count))) return rc;
     if (nphase == 3 && (rc = grow(c->grid, (size_t)cells * count))) return rc;
     if ((rc = grow(c->lut, (size_t)nstages * DEFF2D_LUT_ENTRIES * 4)) || (rc = grow(c->dead, (size_t)nstages * DEFF2D_LUT_ENTRIES)) ||
-        (rc = grow(c->clut, (size_t)nstages * DEFF2D_CLUT_ENTRIES * 4))) return rc;
+        (rc = grow(c->clut, (size_t)nstages * DEFF2D_CLUT_ENTRIES * 4)) ||
+        (rc = grow(c->clut_aos, (size_t)nstages * DEFF2D_CLUT_ENTRIES * 4))) return rc;
     c->lut_stages = nstages;
     if (fields && (rc = grow(c->dense, (size_t)cells))) return rc;
     if ((rc = dev_ensure(c, b->slots, (size_t)nslots)) || (rc = dev_ensure(c, b->outs, (size_t)count)) ||
@@ -483,12 +484,14 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     {
         std::vector<double> lut((size_t)nstages * DEFF2D_LUT_ENTRIES * 4);
         std::vector<uint8_t> dead((size_t)nstages * DEFF2D_LUT_ENTRIES);
-        std::vector<double> clut((size_t)nstages * DEFF2D_CLUT_ENTRIES * 4);
+        std::vector<double> clut((size_t)nstages * DEFF2D_CLUT_ENTRIES * 4), aos((size_t)nstages * DEFF2D_CLUT_ENTRIES * 4);
         for (int k = 0; k < nstages; k++) {
             build_tables(stages.s[k].D, Nx, Ny, c->CL, c->CR, c->omega, lut.data() + (size_t)k * DEFF2D_LUT_ENTRIES * 4,
                          dead.data() + (size_t)k * DEFF2D_LUT_ENTRIES);
             compact_table(lut.data() + (size_t)k * DEFF2D_LUT_ENTRIES * 4, clut.data() + (size_t)k * DEFF2D_CLUT_ENTRIES * 4, nphase);
+            interleave_table(clut.data() + (size_t)k * DEFF2D_CLUT_ENTRIES * 4, aos.data() + (size_t)k * DEFF2D_CLUT_ENTRIES * 4);
         }
+        CUB(cudaMemcpyAsync(c->clut_aos.p, aos.data(), aos.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         CUB(cudaMemcpyAsync(c->clut.p, clut.data(), clut.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         CUB(cudaMemcpyAsync(c->lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         CUB(cudaMemcpyAsync(c->dead.p, dead.data(), dead.size(), cudaMemcpyHostToDevice, s));
@@ -504,8 +507,7 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
         deff2d_ctx *c; int fam, tb;
         ~Restore() { c->tile_family = fam; c->tblock = tb; c->tile_list = nullptr; c->tile_count = 0; }
     } restore_guard{c, old_family, old_tblock};
-    c->tile_family = DEFF2D_DEFAULT_TILE_FAMILY;
-    if (const char *e = std::getenv("DEFF2D_BATCH_FAMILY")) { const int v = std::atoi(e); if (v >= 0 && v <= 3) c->tile_family = v; }   // tuning
+    c->tile_family = 0;                                  // the default thread layout
     // tile grids of the pass depths in use (T and the remainders 1..T-1)
     int ow[9], oh[9], tx_n[9], ty_n[9];
     size_t tiles_cap = 0;

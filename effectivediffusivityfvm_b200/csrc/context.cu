@@ -81,11 +81,15 @@ static int upload_tables(deff2d_ctx *c)
     int rc;
     std::vector<double> clut((size_t)DEFF2D_CLUT_ENTRIES * 4);
     compact_table(lut.data(), clut.data(), c->nphase);
+    std::vector<double> aos(clut.size());
+    interleave_table(clut.data(), aos.data());
     if ((rc = ensure(c, c->lut, lut.size()))) return rc;
     if ((rc = ensure(c, c->clut, clut.size()))) return rc;
+    if ((rc = ensure(c, c->clut_aos, aos.size()))) return rc;
     if ((rc = ensure(c, c->dead, dead.size()))) return rc;
     c->lut_stages = 1;
     CU(cudaMemcpyAsync(c->clut.p, clut.data(), clut.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->clut_aos.p, aos.data(), aos.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     // pageable source: the copy is staged before the call returns, the vectors may die
     CU(cudaMemcpyAsync(c->lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->dead.p, dead.data(), dead.size(), cudaMemcpyHostToDevice, c->stream));
@@ -106,11 +110,7 @@ static int enqueue_sweeps(deff2d_ctx *c, int64_t n)
         // per-pass latency, so the deepest pass wins there too).
         const int64_t ncell = c->Nx * c->Ny;
         if (c->kernel == 2 || (c->kernel == 0 && ncell >= 64)) {
-            if (c->kernel == 0) {
-                c->tile_family = DEFF2D_DEFAULT_TILE_FAMILY;
-                c->tblock = 8;
-            }
-            int rc = launch_sweep_tma(c, n, &done);
+            int rc = launch_sweep_tma(c, n, c->kernel == 0 ? c->k2_default_depth : c->tblock, &done);
             if (rc) return rc;
         }
         if (done == 0) {
@@ -458,6 +458,9 @@ DEFF2D_EXPORT int deff2d_create(deff2d_ctx **out, int device)
     std::memset(c->h_state, 0, sizeof(SolveState));
     c->kernel = 0;
     c->tblock = 1;
+    if (const char *e = std::getenv("DEFF2D_K2_VAR")) c->k2_variant = std::atoi(e) & 3;          // tuning (A/B runs)
+    if (const char *e = std::getenv("DEFF2D_K2_FAM")) c->k2_default_family = std::atoi(e) == 4 ? 4 : 3;
+    if (const char *e = std::getenv("DEFF2D_K2_DEPTH")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) c->k2_default_depth = v; }
     *out = c;
     return DEFF2D_OK;
 }
@@ -477,6 +480,7 @@ DEFF2D_EXPORT void deff2d_destroy(deff2d_ctx *c)
     if (c->grid.p) cudaFree(c->grid.p);
     if (c->lut.p) cudaFree(c->lut.p);
     if (c->clut.p) cudaFree(c->clut.p);
+    if (c->clut_aos.p) cudaFree(c->clut_aos.p);
     if (c->dead.p) cudaFree(c->dead.p);
     if (c->dense.p) cudaFree(c->dense.p);
     if (c->dense8.p) cudaFree(c->dense8.p);
@@ -711,8 +715,8 @@ DEFF2D_EXPORT int deff2d_sync(deff2d_ctx *c)
 
 DEFF2D_EXPORT int deff2d_set_kernel(deff2d_ctx *c, int kernel, int tblock)
 {
-    if (!c || kernel < 0 || kernel > 5 || tblock < 0 || tblock > 16) return DEFF2D_ERR_ARG;
-    c->tile_family = (kernel >= 3) ? kernel - 2 : 0;   // 3, 4, 5: alternative tile geometries of the TMA kernel (tuning)
+    if (!c || kernel < 0 || kernel > 4 || tblock < 0 || tblock > 16) return DEFF2D_ERR_ARG;
+    c->tile_family = (kernel >= 3) ? kernel : 0;       // 3, 4: the two thread layouts of the tiled kernel by name; 0, 2: the default layout
     if (kernel >= 3) kernel = 2;
     c->kernel = kernel;
     c->tblock = tblock > 0 ? tblock : 1;

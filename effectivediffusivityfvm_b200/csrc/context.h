@@ -42,7 +42,8 @@ struct deff2d_ctx {
     DevBuf<uint8_t> code, img, grid, dead, dense8;
     DevBuf<uint16_t> idx16;          // per-cell weight-table index derived from `code` (k_build_idx), read by the tiled sweep
     DevBuf<double> lut, dense;
-    DevBuf<double> clut;             // compact per-stage weight tables of the tiled sweep (tables.cpp: compact_table)
+    DevBuf<double> clut;             // compact per-stage weight tables of the tiled sweep (tables.cpp: compact_table), four planes
+    DevBuf<double> clut_aos;         // the same entries as [slot][4] (two 16-byte loads per cell)
     int lut_stages = 1;              // stages resident in lut / clut (packed batches: all stages of the mode)
     std::vector<uint8_t> h_grid;
 
@@ -53,7 +54,10 @@ struct deff2d_ctx {
     // kernel selection
     int kernel = 0;                  // 0 default, 1 simple, 2 TMA tiled
     int tblock = 1;
-    int tile_family = 0;             // sweep_tma.cu tile geometry (tuning)
+    int tile_family = 0;             // sweep_tma.cu thread layout: 3 = 4 x 4 patches, 4 = 2 x 8 patches, else the default
+    int k2_variant = 0;              // sweep_tma.cu: bit 0 [slot][4] weight table, bit 1 split-phase sweep barrier
+    int k2_default_family = DEFF2D_DEFAULT_TILE_FAMILY;
+    int k2_default_depth = 8;        // sweeps per HBM pass of kernel 0
     int64_t launches = 0;
 
     // TMA tiled sweep state (sweep_tma.cu)
@@ -89,7 +93,7 @@ int solve_image_impl(deff2d_ctx *c, const uint8_t *gray, int W, int H, const def
 
 // sweep_tma.cu: enqueue up to min(n, tblock) sweeps with the TMA tiled kernel; *done = sweeps
 // enqueued (0: this domain is not eligible, caller falls back to the streaming kernel).
-int launch_sweep_tma(deff2d_ctx *c, int64_t n, int64_t *done);
+int launch_sweep_tma(deff2d_ctx *c, int64_t n, int T, int64_t *done);
 // one pass of depth T over an explicit tile list on `stream`, without flipping c->cur
 int tma_pass(deff2d_ctx *c, int T, const uint32_t *list, int count, cudaStream_t stream);
 // npasses passes of depth T on c->stream, flipping c->cur after each (CUDA graphs for long runs)

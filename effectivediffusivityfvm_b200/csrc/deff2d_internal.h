@@ -48,6 +48,8 @@ DEFF2D_HD inline unsigned clut_slot(unsigned p, unsigned w, unsigned e, unsigned
     return 243u + p * 256u + (w | (e << 2) | (s << 4) | (n << 6));
 }
 void compact_table(const double *lut, double *clut, int nphase);
+// planar compact table (4 x DEFF2D_CLUT_ENTRIES) -> [slot][4]
+void interleave_table(const double *clut, double *aos);
 
 // FloodFill (cuh:557-713) on a byte grid; returns PathFlag.
 // reference_quirk: keep the right-column seeding of cuh:601 (quirk Q11); false = flood from the left column only

@@ -248,7 +248,7 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
     const int64_t H = std::max(c->halo_above, c->halo_below);
     if (s->nranks > 1 && (H < 1 || c->own_rows < H)) { set_error(c, "slab needs halo rows >= 1 and own rows >= halo rows"); return DEFF2D_ERR_STATE; }
     const int old_family = c->tile_family;
-    c->tile_family = DEFF2D_DEFAULT_TILE_FAMILY;
+    c->tile_family = 0;                    // the default thread layout
     int rc = build_lists(c, s);
     if (rc) { c->tile_family = old_family; return rc; }
     int Tmax = c->tblock > 0 ? c->tblock : 4;

@@ -51,6 +51,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;
@@ -128,13 +132,16 @@ struct Cfg {
 // (763 vs 817, 610 vs 650: a 64-bit shuffle costs more LSU time than an 8-byte shared-memory access);
 // two 64-thread named barriers per sweep between neighbouring warps instead of one CTA-wide barrier
 // (685 vs 828); two 128-thread CTAs per SM on 64 x 32 tiles (744 at T = 4 vs 827).
-template <class C, bool LIST>
+template <class C, bool LIST, int VAR>
 __global__ void __launch_bounds__(C::NT, 1)
 k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, double om,
             int tiles_x, int ntiles, const uint32_t *__restrict__ tile_list)
 {
     constexpr int T = C::T, TE = C::TE, PX = C::PX, PY = C::PY, TW = C::TW, TH = C::TH, OW = C::OW, OH = C::OH;
     constexpr int PW = C::PLANE_W, IW = C::IW;
+    constexpr bool AOS = (VAR & 1) != 0;      // weight table as [slot][4] (two 16-byte loads per cell) instead of four planes
+    constexpr bool SPLIT = (VAR & 2) != 0;    // split-phase sweep barrier (mbarrier arrive / wait) with the published rows computed first
+    static_assert(C::NWX == 1, "a warp spans the tile width (W / E halo by shuffles)");
 
     // No integer round trip on the base pointer: the compiler must keep seeing the shared
     // address space (a generic pointer turns every LDS/STS below into a slow generic LD/ST).
@@ -145,6 +152,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     uint8_t *const CODE0 = smem + C::OFF_CODE;
     uint64_t *const bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
     int *const org = reinterpret_cast<int *>(smem + C::OFF_BAR + 16);   // output-box origin of the tile in buffer b: org[2b], org[2b+1]
+    uint64_t *const swbar = bar + 4;            // SPLIT: the sweep barrier (one arrival per warp)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wx = warp % C::NWX, wy = warp / C::NWX;
@@ -179,6 +187,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         prefetch_tmap(map_in); prefetch_tmap(map_out); prefetch_tmap(&maps.idx);
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
+        if constexpr (SPLIT) mbar_init(swbar, C::NT / 32);
         fence_barrier_init();
     }
     __syncthreads();
@@ -190,11 +199,10 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     }
 
     // clamped neighbour positions (tile-edge patches produce halo garbage that is never stored)
-    const int gW = (g > 0) ? g - 1 : g;                       // plane PX-1, column gW
-    const int gE = (g < PW - 1) ? g + 1 : g;                  // plane 0,    column gE
     const int rN = (r0 > 0) ? r0 - 1 : r0;
     const int rS = (r0 + PY < TH) ? r0 + PY : r0 + PY - 1;
 
+    uint32_t sw_phase = 0;                     // SPLIT: parity of the sweep barrier's current phase
     int k = 0;
     for (; tile < ntiles; tile += gridDim.x, k++) {
         const int b = k & 1;
@@ -264,16 +272,21 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
 #pragma unroll
             for (int py = 0; py < PY; py++)
 #pragma unroll
-                for (int px = 0; px < PX; px++)      // offset into the planar table: stage * 4096 + slot
-                    idx[py][px] = ((idx[py][px] & 0x3c00u) << 2) | (idx[py][px] & 0x3ffu);
+                for (int px = 0; px < PX; px++)      // offset into the table: (stage * 1024 + slot) [* 4 doubles] / stage * 4096 + slot (planar)
+                    idx[py][px] = AOS ? ((idx[py][px] & 0x3fffu) << 2) : (((idx[py][px] & 0x3c00u) << 2) | (idx[py][px] & 0x3ffu));
             // Most patches lie inside one phase (every cell has the same neighbourhood index):
             // one LUT entry then serves all PX*PY cells -- 2 instead of 2*PX*PY 16-byte loads.
-            // The LSU data pipe is the busiest unit of this kernel (ncu: ~80 % of peak).
             // warp-wide decision: a mixed warp would execute both paths
             auto fetch = [&](unsigned e, double &w0, double &w1, double &w2, double &w3) {
                 const double *q = wtab + e;
-                w0 = __ldg(q); w1 = __ldg(q + DEFF2D_CLUT_ENTRIES); w2 = __ldg(q + 2 * DEFF2D_CLUT_ENTRIES);
-                w3 = __ldg(q + 3 * DEFF2D_CLUT_ENTRIES);
+                if constexpr (AOS) {
+                    const double2 a = __ldg(reinterpret_cast<const double2 *>(q));
+                    const double2 c2 = __ldg(reinterpret_cast<const double2 *>(q) + 1);
+                    w0 = a.x; w1 = a.y; w2 = c2.x; w3 = c2.y;
+                } else {
+                    w0 = __ldg(q); w1 = __ldg(q + DEFF2D_CLUT_ENTRIES); w2 = __ldg(q + 2 * DEFF2D_CLUT_ENTRIES);
+                    w3 = __ldg(q + 3 * DEFF2D_CLUT_ENTRIES);
+                }
             };
             if (__all_sync(0xffffffffu, uniform)) {
                 double a0, a1, a2, a3;
@@ -293,78 +306,119 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
             }
         }
 
-        // XSHFL (one warp spans the tile width): the W / E halo comes from the neighbouring lanes by
-        // warp shuffles, so only the top and bottom patch rows go through shared memory
-        constexpr bool XSHFL = (C::NWX == 1);
-        auto publish = [&](double *pb) {
+        // The W / E halo comes from the neighbouring lanes by warp shuffles (a warp spans the tile
+        // width), so only the top and bottom patch rows go through shared memory.
+        auto publish_rows = [&](double *pb, const double (&top)[PX], const double (&bot)[PX]) {
 #pragma unroll
-            for (int py = 0; py < PY; py++)
-#pragma unroll
-                for (int px = 0; px < PX; px++) {
-                    const bool edge = XSHFL ? ((py == 0) || (py == PY - 1))
-                                            : ((px == 0) || (px == PX - 1) || (py == 0) || (py == PY - 1));
-                    if (edge) pb[(px * TH + r0 + py) * PW + g] = x[py][px];
-                }
+            for (int px = 0; px < PX; px++) {
+                pb[(px * TH + r0) * PW + g] = top[px];
+                pb[(px * TH + r0 + PY - 1) * PW + g] = bot[px];
+            }
         };
-        publish(P0);
-        // the OUT box of the previous tile must have been read by its bulk store before this
-        // tile's last sweep overwrites it (the wait is ordered before the writes by S1)
-        if (tid == 0) tma_wait_read0();
-        __syncthreads();                       // S1: IN[b], CODE[b] fully consumed; P[0] visible
+        // x' = (1-w) x + wW xW + wE xE + wS xS + wN xN   (cuh:76-89, A and b folded into w): one patch row
+        auto row_update = [&](int py, double hw, double he, const double (&upv)[PX], const double (&dnv)[PX],
+                              const double (&cur)[PX], double (&out)[PX]) {
+            double left = hw;
+#pragma unroll
+            for (int px = 0; px < PX; px++) {
+                const double c = cur[px];
+                const double right = (px == PX - 1) ? he : cur[px + 1];
+                double r = omc[px] * c;
+                r = fma(w[py][px][0], left, r);
+                r = fma(w[py][px][1], right, r);
+                r = fma(w[py][px][2], dnv[px], r);
+                r = fma(w[py][px][3], upv[px], r);
+                out[px] = r;
+                left = c;
+            }
+        };
+        uint32_t &sph = sw_phase;
+        auto sw_arrive = [&]() { __syncwarp(); if (lane == 0) mbar_arrive(swbar); };
+        auto sw_wait = [&]() { mbar_wait(swbar, sph); sph ^= 1u; };
 
-        // prefetch the tile after next into the buffer just consumed: loads run two tiles ahead
-        if (tid == 0) {
-            const int nt = tile + 2 * (int)gridDim.x;
-            if (nt < ntiles) issue_load(nt, b);
+        if constexpr (SPLIT) {
+            // the end-of-tile barrier of the previous tile (its OUT box is staged; every warp has left its last sweep)
+            if (k > 0) sw_wait();
+        }
+        publish_rows(P0, x[0], x[PY - 1]);
+        // the OUT box of the previous tile must have been read by its bulk store before this
+        // tile's last sweep overwrites it (the wait is ordered before the writes by the barrier)
+        if (tid == 0) tma_wait_read0();
+        if constexpr (SPLIT) sw_arrive();
+        else {
+            __syncthreads();                   // S1: IN[b], CODE[b] fully consumed; P[0] visible
+            // prefetch the tile after next into the buffer just consumed: loads run two tiles ahead
+            if (tid == 0) {
+                const int nt = tile + 2 * (int)gridDim.x;
+                if (nt < ntiles) issue_load(nt, b);
+            }
         }
 
         // ---- T sweeps on chip --------------------------------------------------------------
 #pragma unroll
         for (int s = 1; s <= T; s++) {
+            if constexpr (SPLIT) {
+                sw_wait();                     // level s-1 rows of every warp are in P[(s-1)&1]
+                if (s == 1 && tid == 0) {      // IN[b], CODE[b] fully consumed: prefetch the tile after next into them
+                    const int nt = tile + 2 * (int)gridDim.x;
+                    if (nt < ntiles) issue_load(nt, b);
+                }
+            }
             const double *pr = P0 + ((s - 1) & 1) * C::CELLS;
             double hW[PY], hE[PY], hN[PX], hS[PX];
 #pragma unroll
             for (int py = 0; py < PY; py++) {
-                if constexpr (XSHFL) {
-                    // lanes 0 / 31 sit on the tile edge: they get their own value back (halo garbage, never stored)
-                    hW[py] = __shfl_up_sync(0xffffffffu, x[py][PX - 1], 1, C::LX);
-                    hE[py] = __shfl_down_sync(0xffffffffu, x[py][0], 1, C::LX);
-                } else {
-                    hW[py] = pr[((PX - 1) * TH + r0 + py) * PW + gW];
-                    hE[py] = pr[(0 * TH + r0 + py) * PW + gE];
-                }
+                // the lanes on the tile edge get their own value back (halo garbage, never stored)
+                hW[py] = __shfl_up_sync(0xffffffffu, x[py][PX - 1], 1, C::LX);
+                hE[py] = __shfl_down_sync(0xffffffffu, x[py][0], 1, C::LX);
             }
 #pragma unroll
             for (int px = 0; px < PX; px++) {
                 hN[px] = pr[(px * TH + rN) * PW + g];
                 hS[px] = pr[(px * TH + rS) * PW + g];
             }
-            // in-place update; `up[px]` carries the old value of the row above
-            double up[PX];
-#pragma unroll
-            for (int px = 0; px < PX; px++) up[px] = hN[px];
-#pragma unroll
-            for (int py = 0; py < PY; py++) {
-                double left = hW[py];
-#pragma unroll
-                for (int px = 0; px < PX; px++) {
-                    const double c = x[py][px];
-                    const double right = (px == PX - 1) ? hE[py] : x[py][px + 1];
-                    const double down = (py == PY - 1) ? hS[px] : x[py + 1][px];
-                    // x' = (1-w) x + wW xW + wE xE + wS xS + wN xN   (cuh:76-89, A and b folded into w)
-                    double r = omc[px] * c;
-                    r = fma(w[py][px][0], left, r);
-                    r = fma(w[py][px][1], right, r);
-                    r = fma(w[py][px][2], down, r);
-                    r = fma(w[py][px][3], up[px], r);
-                    x[py][px] = r;
-                    left = c;
-                    up[px] = c;
+            if constexpr (SPLIT) {
+                // the two published rows first, so that the other warps' wait overlaps the inner rows
+                double n0[PX], nL[PX];
+                row_update(0, hW[0], hE[0], hN, x[1], x[0], n0);
+                row_update(PY - 1, hW[PY - 1], hE[PY - 1], x[PY - 2], hS, x[PY - 1], nL);
+                if (s < T) {
+                    publish_rows(P0 + (s & 1) * C::CELLS, n0, nL);
+                    sw_arrive();
                 }
-            }
-            if (s < T) {
-                publish(P0 + (s & 1) * C::CELLS);
-                __syncthreads();
+                double up[PX];
+#pragma unroll
+                for (int px = 0; px < PX; px++) up[px] = x[0][px];
+#pragma unroll
+                for (int py = 1; py < PY - 1; py++) {
+                    double cur[PX];
+#pragma unroll
+                    for (int px = 0; px < PX; px++) cur[px] = x[py][px];
+                    row_update(py, hW[py], hE[py], up, x[py + 1], cur, x[py]);
+#pragma unroll
+                    for (int px = 0; px < PX; px++) up[px] = cur[px];
+                }
+#pragma unroll
+                for (int px = 0; px < PX; px++) { x[0][px] = n0[px]; x[PY - 1][px] = nL[px]; }
+            } else {
+                // in-place update; `up[px]` carries the old value of the row above
+                double up[PX];
+#pragma unroll
+                for (int px = 0; px < PX; px++) up[px] = hN[px];
+#pragma unroll
+                for (int py = 0; py < PY; py++) {
+                    double cur[PX];
+#pragma unroll
+                    for (int px = 0; px < PX; px++) cur[px] = x[py][px];
+                    if (py == PY - 1) row_update(py, hW[py], hE[py], up, hS, cur, x[py]);
+                    else row_update(py, hW[py], hE[py], up, x[py + 1], cur, x[py]);
+#pragma unroll
+                    for (int px = 0; px < PX; px++) up[px] = cur[px];
+                }
+                if (s < T) {
+                    publish_rows(P0 + (s & 1) * C::CELLS, x[0], x[PY - 1]);
+                    __syncthreads();
+                }
             }
         }
 
@@ -395,7 +449,10 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
             }
         }
         fence_proxy_async();                   // generic-proxy writes -> visible to the TMA engine
-        __syncthreads();
+        if constexpr (SPLIT) {
+            sw_arrive();
+            if (tid == 0) mbar_wait(swbar, sph);    // every thread consumes this phase at the top of its next tile
+        } else __syncthreads();
         if (tid == 0) {
             tma_store_2d(map_out, ox, oy, OUT);
             tma_commit();
@@ -415,7 +472,7 @@ struct GraphEntry {
     uint64_t version = 0;        // tensor-map generation the graph was captured with
     int T = 0, fam = 0, src = 0, count = 0, grid_limit = 0;
     const uint32_t *list = nullptr;
-    const double *lut = nullptr;
+    const double *lut = nullptr, *lut2 = nullptr;
     double omega = 0;
 };
 
@@ -429,8 +486,7 @@ struct TmaState {
     int ow = 0, oh = 0, tiles_x = 0, tiles_y = 0;
     void *key_x0 = nullptr, *key_x1 = nullptr, *key_code = nullptr;
     int64_t key_Nx = 0, key_Ny = 0, key_pitch = 0;
-    bool attr_set[2][4][17] = {{{false}}};
-    int cfg_F = -1;
+    std::vector<const void *> attr_fns;   // kernels whose dynamic shared-memory limit has been raised
     int max_smem_optin = 0;
 };
 
@@ -453,36 +509,38 @@ static int encode_2d(deff2d_ctx *c, TmaState *ts, CUtensorMap *m, CUtensorMapDat
     return DEFF2D_OK;
 }
 
-// tile geometries (all 128 x 32 cells, 256 threads, 16 cells per thread):
-//   family 0: 2 x 8 cells per thread, 2 x 4 warps   (16-byte patch rows: conflict-free staging)
-//   family 1: 4 x 4 cells per thread, 1 x 8 warps   (fewest exchange operations per sweep)
+// tile geometries: square 64 x 64 tiles, 256 threads, 16 cells per thread, one warp per 8 tile rows
+//   family 3: 4 x 4 cells per thread, 16 lanes side by side, two patch rows per warp
+//   family 4: 2 x 8 cells per thread, 32 lanes side by side: half the shared-memory row exchange of family 3 per
+//             sweep (2 + 2 values published and read per thread instead of 4 + 4) for twice the W / E shuffles
 template <int T, int F> struct Family;
-template <int T> struct Family<T, 0> { using type = Cfg<T, 2, 8, 2, 4>; };
-template <int T> struct Family<T, 1> { using type = Cfg<T, 4, 4, 1, 8>; };
-//   family 2: 2 x 4 cells per thread, 2 x 8 warps, 512 threads (more warps, <= 128 registers)
-template <int T> struct Family<T, 2> { using type = Cfg<T, 2, 4, 2, 8>; };
-//   family 3: 4 x 4 cells per thread, 16 lanes per patch row, 1 x 8 warps: square 64 x 64 tiles -- the
-//             halo ring of a square costs fewer redundant cells (T = 4: 76.6 % useful instead of 70.3 %)
 template <int T> struct Family<T, 3> { using type = Cfg<T, 4, 4, 1, 8, 16>; };
+template <int T> struct Family<T, 4> { using type = Cfg<T, 2, 8, 1, 8, 32>; };
 
-template <int T, int F>
+static bool attr_done(TmaState *ts, const void *fn)
+{
+    for (const void *f : ts->attr_fns) if (f == fn) return true;
+    ts->attr_fns.push_back(fn);
+    return false;
+}
+
+template <int T, int F, int VAR>
 static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, int count, cudaStream_t stream)
 {
     using C = typename Family<T, F>::type;
-    auto kern = list ? k_sweep_tma<C, true> : k_sweep_tma<C, false>;
+    auto kern = list ? k_sweep_tma<C, true, VAR> : k_sweep_tma<C, false, VAR>;
     const size_t smem = C::SMEM;
-    const int variant = list ? 1 : 0;
-    if (!ts->attr_set[variant][F][T]) {
+    if (!attr_done(ts, (const void *)kern)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error(c, "cudaFuncSetAttribute(smem %zu) failed: %s", smem, cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
-        ts->attr_set[variant][F][T] = true;
     }
     const int ntiles = list ? count : ts->tiles_x * ts->tiles_y;
     if (ntiles < 1) return DEFF2D_OK;
     int grid = c->prop.multiProcessorCount;
     if (c->grid_limit > 0 && grid > c->grid_limit) grid = c->grid_limit;
     if (grid > ntiles) grid = ntiles;
-    kern<<<grid, C::NT, smem, stream>>>(ts->maps, src, c->clut.p, 1.0 - c->omega, ts->tiles_x, ntiles, list);
+    const double *table = (VAR & 1) ? c->clut_aos.p : c->clut.p;
+    kern<<<grid, C::NT, smem, stream>>>(ts->maps, src, table, 1.0 - c->omega, ts->tiles_x, ntiles, list);
     return DEFF2D_OK;
 }
 
@@ -491,7 +549,8 @@ static int prepare_T(deff2d_ctx *c, TmaState *ts)
 {
     using C = typename Family<T, F>::type;
     if ((int)C::SMEM > ts->max_smem_optin) { set_error(c, "tile needs %zu B smem > %d", C::SMEM, ts->max_smem_optin); return DEFF2D_ERR_STATE; }
-    const bool same = ts->cfg_T == T && ts->cfg_F == F && ts->key_x0 == c->x[0].p && ts->key_x1 == c->x[1].p && ts->key_code == c->idx16.p &&
+    // both families share the tile geometry, so the tensor maps depend on T only
+    const bool same = ts->cfg_T == T && ts->key_x0 == c->x[0].p && ts->key_x1 == c->x[1].p && ts->key_code == c->idx16.p &&
                       ts->key_Nx == c->Nx && ts->key_Ny == c->Ny && ts->key_pitch == c->pitch;
     if (same) return DEFF2D_OK;
     int rc;
@@ -507,7 +566,6 @@ static int prepare_T(deff2d_ctx *c, TmaState *ts)
                         (uint64_t)c->rows, (uint64_t)c->pitch * 2, C::IW, C::TH))) return rc;
     ts->version++;
     ts->cfg_T = T;
-    ts->cfg_F = F;
     ts->ow = C::OW; ts->oh = C::OH;
     ts->tiles_x = (int)((c->Nx + C::OW - 1) / C::OW);
     ts->tiles_y = (int)((c->Ny + C::OH - 1) / C::OH);
@@ -534,15 +592,16 @@ static TmaState *tma_state(deff2d_ctx *c)
     return ts;
 }
 
-// Output-box size of the tiles of temporal depth T in the context's tile family.
+// Output-box size of the tiles of temporal depth T (64 x 64 tiles in both families).
 void tma_tile_geometry(const deff2d_ctx *c, int T, int *ow, int *oh)
 {
+    (void)c;
     const int te = (T + 1) & ~1;
-    const int fam = c ? c->tile_family : DEFF2D_DEFAULT_TILE_FAMILY;
-    const int tw = (fam == 3) ? 64 : 128, th = (fam == 3) ? 64 : 32;     // Family<> above
-    *ow = tw - 2 * te;
-    *oh = th - 2 * T;
+    *ow = 64 - 2 * te;
+    *oh = 64 - 2 * T;
 }
+
+static int k2_family(const deff2d_ctx *c) { return c->tile_family == 4 ? 4 : (c->tile_family == 3 ? 3 : c->k2_default_family); }
 
 // One pass of depth T (1..8) from x[src] into x[src ^ 1] over the tiles of `list` (NULL: the whole
 // tile grid) on `stream`.
@@ -552,27 +611,28 @@ static int pass_from(deff2d_ctx *c, int T, int src, const uint32_t *list, int co
     if (!ts->encode) { set_error(c, "cuTensorMapEncodeTiled is not available from this driver"); return DEFF2D_ERR_CUDA; }
     if (T < 1 || T > 8) { set_error(c, "temporal depth %d out of range", T); return DEFF2D_ERR_ARG; }
     int rc = DEFF2D_OK;
-    const int fam = c->tile_family;
+    const int fam = k2_family(c);
+    const int var = c->k2_variant & 3;
+#define DEFF2D_VAR(TT, FF)                                                                                     \
+    {                                                                                                          \
+        if ((rc = prepare_T<TT, FF>(c, ts))) return rc;                                                        \
+        switch (var) {                                                                                         \
+        case 0: rc = launch_T<TT, FF, 0>(c, ts, src, list, count, stream); break;                              \
+        case 1: rc = launch_T<TT, FF, 1>(c, ts, src, list, count, stream); break;                              \
+        case 2: rc = launch_T<TT, FF, 2>(c, ts, src, list, count, stream); break;                              \
+        default: rc = launch_T<TT, FF, 3>(c, ts, src, list, count, stream); break;                             \
+        }                                                                                                      \
+        if (rc) return rc;                                                                                     \
+    }
 #define DEFF2D_CASE(TT)                                                                   \
     case TT:                                                                              \
-        if (fam == 1) {                                                                   \
-            if ((rc = prepare_T<TT, 1>(c, ts))) return rc;                                \
-            if ((rc = launch_T<TT, 1>(c, ts, src, list, count, stream))) return rc;       \
-        } else if (fam == 3) {                                                            \
-            if ((rc = prepare_T<TT, 3>(c, ts))) return rc;                                \
-            if ((rc = launch_T<TT, 3>(c, ts, src, list, count, stream))) return rc;       \
-        } else if (fam == 2) {                                                            \
-            if ((rc = prepare_T<TT, 2>(c, ts))) return rc;                                \
-            if ((rc = launch_T<TT, 2>(c, ts, src, list, count, stream))) return rc;       \
-        } else {                                                                          \
-            if ((rc = prepare_T<TT, 0>(c, ts))) return rc;                                \
-            if ((rc = launch_T<TT, 0>(c, ts, src, list, count, stream))) return rc;       \
-        }                                                                                 \
+        if (fam == 4) DEFF2D_VAR(TT, 4) else DEFF2D_VAR(TT, 3)                            \
         break;
     switch (T) {
         DEFF2D_CASE(1) DEFF2D_CASE(2) DEFF2D_CASE(3) DEFF2D_CASE(4) DEFF2D_CASE(5) DEFF2D_CASE(6) DEFF2D_CASE(7) DEFF2D_CASE(8)
     }
 #undef DEFF2D_CASE
+#undef DEFF2D_VAR
     return DEFF2D_OK;
 }
 
@@ -597,7 +657,7 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
     int rc;
     while (npasses >= GRAPH_PASSES && c->use_graphs) {
         // make sure the tensor maps are current before looking a graph up (re-encoding bumps the version)
-        if (ts->cfg_T != T || ts->cfg_F != c->tile_family || ts->key_x0 != c->x[0].p || ts->key_x1 != c->x[1].p ||
+        if (ts->cfg_T != T || ts->key_x0 != c->x[0].p || ts->key_x1 != c->x[1].p ||
             ts->key_code != c->idx16.p || ts->key_Nx != c->Nx || ts->key_Ny != c->Ny || ts->key_pitch != c->pitch) {
             // a direct pass re-encodes the maps; then the graphs of the old maps are dropped below
             if ((rc = tma_pass(c, T, list, count, c->stream))) return rc;
@@ -607,8 +667,8 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
         }
         GraphEntry *g = nullptr;
         for (auto &e : ts->graphs)
-            if (e.exec && e.version == ts->version && e.T == T && e.fam == c->tile_family && e.src == c->cur && e.list == list &&
-                e.count == count && e.grid_limit == c->grid_limit && e.lut == c->clut.p && e.omega == c->omega) { g = &e; break; }
+            if (e.exec && e.version == ts->version && e.T == T && e.fam == (k2_family(c) * 8 + (c->k2_variant & 3)) && e.src == c->cur && e.list == list &&
+                e.count == count && e.grid_limit == c->grid_limit && e.lut == c->clut.p && e.lut2 == c->clut_aos.p && e.omega == c->omega) { g = &e; break; }
         if (!g) {
             // drop stale graphs, then capture GRAPH_PASSES passes
             for (auto &e : ts->graphs)
@@ -630,8 +690,8 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
             e = cudaGraphInstantiate(&slot->exec, graph, 0);
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) { slot->exec = nullptr; set_error(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
-            slot->version = ts->version; slot->T = T; slot->fam = c->tile_family; slot->src = c->cur; slot->list = list;
-            slot->count = count; slot->grid_limit = c->grid_limit; slot->lut = c->clut.p; slot->omega = c->omega;
+            slot->version = ts->version; slot->T = T; slot->fam = k2_family(c) * 8 + (c->k2_variant & 3); slot->src = c->cur; slot->list = list;
+            slot->count = count; slot->grid_limit = c->grid_limit; slot->lut = c->clut.p; slot->lut2 = c->clut_aos.p; slot->omega = c->omega;
             g = slot;
         }
         cudaError_t e = cudaGraphLaunch(g->exec, c->stream);
@@ -649,10 +709,9 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
 
 // Up to n sweeps with the context's tile list and depth: whole passes of depth tblock (through
 // tma_passes), or one shallower pass for the remainder.  *done = sweeps enqueued.
-int launch_sweep_tma(deff2d_ctx *c, int64_t n, int64_t *done)
+int launch_sweep_tma(deff2d_ctx *c, int64_t n, int T, int64_t *done)
 {
     *done = 0;
-    int T = c->tblock;
     if (T < 1) T = 1;
     if (T > 8) T = 8;
     int rc;
