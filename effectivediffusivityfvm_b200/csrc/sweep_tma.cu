@@ -51,10 +51,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     uint32_t ok;
@@ -139,8 +135,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
 {
     constexpr int T = C::T, TE = C::TE, PX = C::PX, PY = C::PY, TW = C::TW, TH = C::TH, OW = C::OW, OH = C::OH;
     constexpr int PW = C::PLANE_W, IW = C::IW;
-    constexpr bool AOS = (VAR & 1) != 0;      // weight table as [slot][4] (two 16-byte loads per cell) instead of four planes
-    constexpr bool SPLIT = (VAR & 2) != 0;    // split-phase sweep barrier (mbarrier arrive / wait) with the published rows computed first
+    constexpr bool ROWEX = (VAR & 1) != 0 && PX == 2;   // N / S row exchange row-major with 16-byte accesses instead of planar 8-byte ones
     static_assert(C::NWX == 1, "a warp spans the tile width (W / E halo by shuffles)");
 
     // No integer round trip on the base pointer: the compiler must keep seeing the shared
@@ -152,7 +147,6 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     uint8_t *const CODE0 = smem + C::OFF_CODE;
     uint64_t *const bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
     int *const org = reinterpret_cast<int *>(smem + C::OFF_BAR + 16);   // output-box origin of the tile in buffer b: org[2b], org[2b+1]
-    uint64_t *const swbar = bar + 4;            // SPLIT: the sweep barrier (one arrival per warp)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wx = warp % C::NWX, wy = warp / C::NWX;
@@ -187,7 +181,6 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         prefetch_tmap(map_in); prefetch_tmap(map_out); prefetch_tmap(&maps.idx);
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
-        if constexpr (SPLIT) mbar_init(swbar, C::NT / 32);
         fence_barrier_init();
     }
     __syncthreads();
@@ -202,7 +195,6 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     const int rN = (r0 > 0) ? r0 - 1 : r0;
     const int rS = (r0 + PY < TH) ? r0 + PY : r0 + PY - 1;
 
-    uint32_t sw_phase = 0;                     // SPLIT: parity of the sweep barrier's current phase
     int k = 0;
     for (; tile < ntiles; tile += gridDim.x, k++) {
         const int b = k & 1;
@@ -273,20 +265,14 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
             for (int py = 0; py < PY; py++)
 #pragma unroll
                 for (int px = 0; px < PX; px++)      // offset into the table: (stage * 1024 + slot) [* 4 doubles] / stage * 4096 + slot (planar)
-                    idx[py][px] = AOS ? ((idx[py][px] & 0x3fffu) << 2) : (((idx[py][px] & 0x3c00u) << 2) | (idx[py][px] & 0x3ffu));
+                    idx[py][px] = ((idx[py][px] & 0x3c00u) << 2) | (idx[py][px] & 0x3ffu);
             // Most patches lie inside one phase (every cell has the same neighbourhood index):
             // one LUT entry then serves all PX*PY cells -- 2 instead of 2*PX*PY 16-byte loads.
             // warp-wide decision: a mixed warp would execute both paths
             auto fetch = [&](unsigned e, double &w0, double &w1, double &w2, double &w3) {
                 const double *q = wtab + e;
-                if constexpr (AOS) {
-                    const double2 a = __ldg(reinterpret_cast<const double2 *>(q));
-                    const double2 c2 = __ldg(reinterpret_cast<const double2 *>(q) + 1);
-                    w0 = a.x; w1 = a.y; w2 = c2.x; w3 = c2.y;
-                } else {
-                    w0 = __ldg(q); w1 = __ldg(q + DEFF2D_CLUT_ENTRIES); w2 = __ldg(q + 2 * DEFF2D_CLUT_ENTRIES);
-                    w3 = __ldg(q + 3 * DEFF2D_CLUT_ENTRIES);
-                }
+                w0 = __ldg(q); w1 = __ldg(q + DEFF2D_CLUT_ENTRIES); w2 = __ldg(q + 2 * DEFF2D_CLUT_ENTRIES);
+                w3 = __ldg(q + 3 * DEFF2D_CLUT_ENTRIES);
             };
             if (__all_sync(0xffffffffu, uniform)) {
                 double a0, a1, a2, a3;
@@ -309,10 +295,15 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         // The W / E halo comes from the neighbouring lanes by warp shuffles (a warp spans the tile
         // width), so only the top and bottom patch rows go through shared memory.
         auto publish_rows = [&](double *pb, const double (&top)[PX], const double (&bot)[PX]) {
+            if constexpr (ROWEX) {
+                *reinterpret_cast<double2 *>(pb + r0 * TW + c0) = make_double2(top[0], top[1]);
+                *reinterpret_cast<double2 *>(pb + (r0 + PY - 1) * TW + c0) = make_double2(bot[0], bot[1]);
+            } else {
 #pragma unroll
-            for (int px = 0; px < PX; px++) {
-                pb[(px * TH + r0) * PW + g] = top[px];
-                pb[(px * TH + r0 + PY - 1) * PW + g] = bot[px];
+                for (int px = 0; px < PX; px++) {
+                    pb[(px * TH + r0) * PW + g] = top[px];
+                    pb[(px * TH + r0 + PY - 1) * PW + g] = bot[px];
+                }
             }
         };
         // x' = (1-w) x + wW xW + wE xE + wS xS + wN xN   (cuh:76-89, A and b folded into w): one patch row
@@ -332,38 +323,22 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
                 left = c;
             }
         };
-        uint32_t &sph = sw_phase;
-        auto sw_arrive = [&]() { __syncwarp(); if (lane == 0) mbar_arrive(swbar); };
-        auto sw_wait = [&]() { mbar_wait(swbar, sph); sph ^= 1u; };
 
-        if constexpr (SPLIT) {
-            // the end-of-tile barrier of the previous tile (its OUT box is staged; every warp has left its last sweep)
-            if (k > 0) sw_wait();
-        }
         publish_rows(P0, x[0], x[PY - 1]);
         // the OUT box of the previous tile must have been read by its bulk store before this
-        // tile's last sweep overwrites it (the wait is ordered before the writes by the barrier)
+        // tile's last sweep overwrites it (the wait is ordered before the writes by S1)
         if (tid == 0) tma_wait_read0();
-        if constexpr (SPLIT) sw_arrive();
-        else {
-            __syncthreads();                   // S1: IN[b], CODE[b] fully consumed; P[0] visible
-            // prefetch the tile after next into the buffer just consumed: loads run two tiles ahead
-            if (tid == 0) {
-                const int nt = tile + 2 * (int)gridDim.x;
-                if (nt < ntiles) issue_load(nt, b);
-            }
+        __syncthreads();                       // S1: IN[b], CODE[b] fully consumed; P[0] visible
+
+        // prefetch the tile after next into the buffer just consumed: loads run two tiles ahead
+        if (tid == 0) {
+            const int nt = tile + 2 * (int)gridDim.x;
+            if (nt < ntiles) issue_load(nt, b);
         }
 
         // ---- T sweeps on chip --------------------------------------------------------------
 #pragma unroll
         for (int s = 1; s <= T; s++) {
-            if constexpr (SPLIT) {
-                sw_wait();                     // level s-1 rows of every warp are in P[(s-1)&1]
-                if (s == 1 && tid == 0) {      // IN[b], CODE[b] fully consumed: prefetch the tile after next into them
-                    const int nt = tile + 2 * (int)gridDim.x;
-                    if (nt < ntiles) issue_load(nt, b);
-                }
-            }
             const double *pr = P0 + ((s - 1) & 1) * C::CELLS;
             double hW[PY], hE[PY], hN[PX], hS[PX];
 #pragma unroll
@@ -372,53 +347,34 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
                 hW[py] = __shfl_up_sync(0xffffffffu, x[py][PX - 1], 1, C::LX);
                 hE[py] = __shfl_down_sync(0xffffffffu, x[py][0], 1, C::LX);
             }
-#pragma unroll
-            for (int px = 0; px < PX; px++) {
-                hN[px] = pr[(px * TH + rN) * PW + g];
-                hS[px] = pr[(px * TH + rS) * PW + g];
-            }
-            if constexpr (SPLIT) {
-                // the two published rows first, so that the other warps' wait overlaps the inner rows
-                double n0[PX], nL[PX];
-                row_update(0, hW[0], hE[0], hN, x[1], x[0], n0);
-                row_update(PY - 1, hW[PY - 1], hE[PY - 1], x[PY - 2], hS, x[PY - 1], nL);
-                if (s < T) {
-                    publish_rows(P0 + (s & 1) * C::CELLS, n0, nL);
-                    sw_arrive();
-                }
-                double up[PX];
-#pragma unroll
-                for (int px = 0; px < PX; px++) up[px] = x[0][px];
-#pragma unroll
-                for (int py = 1; py < PY - 1; py++) {
-                    double cur[PX];
-#pragma unroll
-                    for (int px = 0; px < PX; px++) cur[px] = x[py][px];
-                    row_update(py, hW[py], hE[py], up, x[py + 1], cur, x[py]);
-#pragma unroll
-                    for (int px = 0; px < PX; px++) up[px] = cur[px];
-                }
-#pragma unroll
-                for (int px = 0; px < PX; px++) { x[0][px] = n0[px]; x[PY - 1][px] = nL[px]; }
+            if constexpr (ROWEX) {
+                const double2 n2 = *reinterpret_cast<const double2 *>(pr + rN * TW + c0);
+                const double2 s2 = *reinterpret_cast<const double2 *>(pr + rS * TW + c0);
+                hN[0] = n2.x; hN[1] = n2.y; hS[0] = s2.x; hS[1] = s2.y;
             } else {
-                // in-place update; `up[px]` carries the old value of the row above
-                double up[PX];
 #pragma unroll
-                for (int px = 0; px < PX; px++) up[px] = hN[px];
-#pragma unroll
-                for (int py = 0; py < PY; py++) {
-                    double cur[PX];
-#pragma unroll
-                    for (int px = 0; px < PX; px++) cur[px] = x[py][px];
-                    if (py == PY - 1) row_update(py, hW[py], hE[py], up, hS, cur, x[py]);
-                    else row_update(py, hW[py], hE[py], up, x[py + 1], cur, x[py]);
-#pragma unroll
-                    for (int px = 0; px < PX; px++) up[px] = cur[px];
+                for (int px = 0; px < PX; px++) {
+                    hN[px] = pr[(px * TH + rN) * PW + g];
+                    hS[px] = pr[(px * TH + rS) * PW + g];
                 }
-                if (s < T) {
-                    publish_rows(P0 + (s & 1) * C::CELLS, x[0], x[PY - 1]);
-                    __syncthreads();
-                }
+            }
+            // in-place update; `up[px]` carries the old value of the row above
+            double up[PX];
+#pragma unroll
+            for (int px = 0; px < PX; px++) up[px] = hN[px];
+#pragma unroll
+            for (int py = 0; py < PY; py++) {
+                double cur[PX];
+#pragma unroll
+                for (int px = 0; px < PX; px++) cur[px] = x[py][px];
+                if (py == PY - 1) row_update(py, hW[py], hE[py], up, hS, cur, x[py]);
+                else row_update(py, hW[py], hE[py], up, x[py + 1], cur, x[py]);
+#pragma unroll
+                for (int px = 0; px < PX; px++) up[px] = cur[px];
+            }
+            if (s < T) {
+                publish_rows(P0 + (s & 1) * C::CELLS, x[0], x[PY - 1]);
+                __syncthreads();
             }
         }
 
@@ -449,10 +405,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
             }
         }
         fence_proxy_async();                   // generic-proxy writes -> visible to the TMA engine
-        if constexpr (SPLIT) {
-            sw_arrive();
-            if (tid == 0) mbar_wait(swbar, sph);    // every thread consumes this phase at the top of its next tile
-        } else __syncthreads();
+        __syncthreads();
         if (tid == 0) {
             tma_store_2d(map_out, ox, oy, OUT);
             tma_commit();
@@ -486,6 +439,7 @@ struct TmaState {
     int ow = 0, oh = 0, tiles_x = 0, tiles_y = 0;
     void *key_x0 = nullptr, *key_x1 = nullptr, *key_code = nullptr;
     int64_t key_Nx = 0, key_Ny = 0, key_pitch = 0;
+    int cfg_TH = 0;              // tile height the maps were encoded for
     std::vector<const void *> attr_fns;   // kernels whose dynamic shared-memory limit has been raised
     int max_smem_optin = 0;
 };
@@ -516,6 +470,7 @@ static int encode_2d(deff2d_ctx *c, TmaState *ts, CUtensorMap *m, CUtensorMapDat
 template <int T, int F> struct Family;
 template <int T> struct Family<T, 3> { using type = Cfg<T, 4, 4, 1, 8, 16>; };
 template <int T> struct Family<T, 4> { using type = Cfg<T, 2, 8, 1, 8, 32>; };
+// (nine warps on 64 x 72 tiles do not work: registers are allocated per four warps, so 288 threads get 168 each)
 
 static bool attr_done(TmaState *ts, const void *fn)
 {
@@ -539,7 +494,7 @@ static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, 
     int grid = c->prop.multiProcessorCount;
     if (c->grid_limit > 0 && grid > c->grid_limit) grid = c->grid_limit;
     if (grid > ntiles) grid = ntiles;
-    const double *table = (VAR & 1) ? c->clut_aos.p : c->clut.p;
+    const double *table = c->clut.p;
     kern<<<grid, C::NT, smem, stream>>>(ts->maps, src, table, 1.0 - c->omega, ts->tiles_x, ntiles, list);
     return DEFF2D_OK;
 }
@@ -549,8 +504,7 @@ static int prepare_T(deff2d_ctx *c, TmaState *ts)
 {
     using C = typename Family<T, F>::type;
     if ((int)C::SMEM > ts->max_smem_optin) { set_error(c, "tile needs %zu B smem > %d", C::SMEM, ts->max_smem_optin); return DEFF2D_ERR_STATE; }
-    // both families share the tile geometry, so the tensor maps depend on T only
-    const bool same = ts->cfg_T == T && ts->key_x0 == c->x[0].p && ts->key_x1 == c->x[1].p && ts->key_code == c->idx16.p &&
+    const bool same = ts->cfg_T == T && ts->cfg_TH == C::TH && ts->key_x0 == c->x[0].p && ts->key_x1 == c->x[1].p && ts->key_code == c->idx16.p &&
                       ts->key_Nx == c->Nx && ts->key_Ny == c->Ny && ts->key_pitch == c->pitch;
     if (same) return DEFF2D_OK;
     int rc;
@@ -566,6 +520,7 @@ static int prepare_T(deff2d_ctx *c, TmaState *ts)
                         (uint64_t)c->rows, (uint64_t)c->pitch * 2, C::IW, C::TH))) return rc;
     ts->version++;
     ts->cfg_T = T;
+    ts->cfg_TH = C::TH;
     ts->ow = C::OW; ts->oh = C::OH;
     ts->tiles_x = (int)((c->Nx + C::OW - 1) / C::OW);
     ts->tiles_y = (int)((c->Ny + C::OH - 1) / C::OH);
@@ -595,13 +550,13 @@ static TmaState *tma_state(deff2d_ctx *c)
 // Output-box size of the tiles of temporal depth T (64 x 64 tiles in both families).
 void tma_tile_geometry(const deff2d_ctx *c, int T, int *ow, int *oh)
 {
-    (void)c;
     const int te = (T + 1) & ~1;
     *ow = 64 - 2 * te;
+    (void)c;
     *oh = 64 - 2 * T;
 }
 
-static int k2_family(const deff2d_ctx *c) { return c->tile_family == 4 ? 4 : (c->tile_family == 3 ? 3 : c->k2_default_family); }
+static int k2_family(const deff2d_ctx *c) { return (c->tile_family >= 3 && c->tile_family <= 4) ? c->tile_family : c->k2_default_family; }
 
 // One pass of depth T (1..8) from x[src] into x[src ^ 1] over the tiles of `list` (NULL: the whole
 // tile grid) on `stream`.
@@ -616,12 +571,8 @@ static int pass_from(deff2d_ctx *c, int T, int src, const uint32_t *list, int co
 #define DEFF2D_VAR(TT, FF)                                                                                     \
     {                                                                                                          \
         if ((rc = prepare_T<TT, FF>(c, ts))) return rc;                                                        \
-        switch (var) {                                                                                         \
-        case 0: rc = launch_T<TT, FF, 0>(c, ts, src, list, count, stream); break;                              \
-        case 1: rc = launch_T<TT, FF, 1>(c, ts, src, list, count, stream); break;                              \
-        case 2: rc = launch_T<TT, FF, 2>(c, ts, src, list, count, stream); break;                              \
-        default: rc = launch_T<TT, FF, 3>(c, ts, src, list, count, stream); break;                             \
-        }                                                                                                      \
+        if (var & 1) rc = launch_T<TT, FF, 1>(c, ts, src, list, count, stream);                                \
+        else rc = launch_T<TT, FF, 0>(c, ts, src, list, count, stream);                                        \
         if (rc) return rc;                                                                                     \
     }
 #define DEFF2D_CASE(TT)                                                                   \
@@ -657,7 +608,7 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
     int rc;
     while (npasses >= GRAPH_PASSES && c->use_graphs) {
         // make sure the tensor maps are current before looking a graph up (re-encoding bumps the version)
-        if (ts->cfg_T != T || ts->key_x0 != c->x[0].p || ts->key_x1 != c->x[1].p ||
+        if (ts->cfg_T != T || ts->cfg_TH != 64 || ts->key_x0 != c->x[0].p || ts->key_x1 != c->x[1].p ||
             ts->key_code != c->idx16.p || ts->key_Nx != c->Nx || ts->key_Ny != c->Ny || ts->key_pitch != c->pitch) {
             // a direct pass re-encodes the maps; then the graphs of the old maps are dropped below
             if ((rc = tma_pass(c, T, list, count, c->stream))) return rc;

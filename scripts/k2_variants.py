@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of the tiled sweep's thread layouts and variants (GPU box only):
-   python scripts/k2_variants.py [sweeps]
+   python scripts/k2_variants.py [sweeps] [fam:var,...] [T,...]
 For every (family, variant): bit-identity against the streaming kernel on a small 3-phase domain for
 T = 1..8, then GLUP/s on config 2 (00042.jpg x4), a 4096^2 blob medium and a 2048^2 site-percolation
 medium (every cell its own weights)."""
@@ -27,9 +27,10 @@ small = np.where(z < q1, 0, np.where(z < q2, 150, 255)).astype(np.uint8)
 blob = c4_image(4096)
 perc = c5_image()
 out = {}
-combos = [(3, 0), (3, 1), (3, 2), (3, 3), (4, 0), (4, 1), (4, 2), (4, 3)]
+combos = [(3, 0), (4, 0), (4, 1)]
 if len(sys.argv) > 2:
     combos = [tuple(int(v) for v in c.split(":")) for c in sys.argv[2].split(",")]
+depths = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [4, 5, 6, 7, 8]
 for fam, var in combos:
     os.environ["DEFF2D_K2_VAR"] = str(var)
     os.environ["DEFF2D_K2_FAM"] = str(fam)
@@ -55,7 +56,7 @@ for fam, var in combos:
                                 ("perc2048", perc, 2, E.default_params(Ds=1e-4, Df=1.0, mode=E.MODE_2PH_BATCH))):
         ctx.domain_load(img, nph, par)
         cells = img.size * par.amp_x * par.amp_y
-        for T in (4, 6, 8):
+        for T in depths:
             ctx.set_kernel(2, T)
             n = sweeps // T * T
             ctx.sweeps_timed(4 * T)
