@@ -17,6 +17,17 @@ e2e: the same metric through the C ABI with HOST buffers: every step uploads the
 (deff2d_domain_load: H2D, threshold + amplification, FloodFill, tables), runs the reference loop
 for check_every + 1 sweeps (deff2d_domain_solve: two checks) and reads Deff back.
 
+The same JSON line carries every BASELINE.json config under "configs", each with a `parity` field:
+  c1  bundled 00000.jpg, shipped input.txt defaults, full solve (N = 1): sweeps per stage and Deff against the
+      reference's own result (140 007 sweeps, Deff 224 673.610442892); plus the 2-phase run
+  c2  the headline domain: Deff after `--cpu-sweeps` sweeps against the CPU oracle on the full 4008 x 8028 domain
+  c3  `--batch-images` (512) distinct synthetic 256 x 256 images per GPU (image index rank*count + k), packed batch
+      mode, images/s end to end; 4 images of rank 0 re-solved by the CPU oracle (sweep counts equal, Deff <= 1e-4)
+  c4  one 16384 x 16384 two-phase domain, MaxIter 10 001 (two checks), row slabs over all N GPUs (strong scaling);
+      Deff must be identical for every N (compare the SCALE lines); N > 1 also runs a slab-vs-single-GPU self-check
+  c5  2048 x 2048 site percolation, Ds/Df = 1e-4, full solve to the reference stop rule (N = 1); the first
+      `--c5-oracle-sweeps` sweeps are checked against the CPU oracle
+
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                   [--sweeps-per-step S] [--kernel 0|1|2] [--tblock T]
 """
@@ -181,7 +192,8 @@ def cpu_baseline(img, sweeps, three_phase=True):
     secs = O.oracle().orc_time_sweeps(O._up(img), img.shape[1], img.shape[0], o, 1 if three_phase else 0, sweeps, O._dp(d))
     cells = img.shape[0] * img.shape[1] * AMP * AMP
     n = O.oracle().orc_num_threads()
-    return {"value": cells * sweeps / secs / 1e9, "unit": "GLUP/s", "cores": n, "kind": "port",
+    return {"value": cells * sweeps / secs / 1e9, "unit": "GLUP/s", "cores": n, "kind": "port", "deff_raw": float(d[0]),
+            "sweeps": int(sweeps),
             "sample": "%d sweeps of the oracle's restatement of updateX_SOR (A[n][5]+b, 80 B/LUP) on the full "
                       "%dx%d domain, %d OpenMP threads, %.1f s" % (sweeps, img.shape[1] * AMP, img.shape[0] * AMP, n, secs)}
 
@@ -202,19 +214,213 @@ def ref_cuda_baseline(img, sweeps):
                       "%dx%d cells, its own cudaEvent time %.1f ms" % (r["iters"], Nx, Ny, r["ms"])}
 
 
-def batch_leg(ctx, count, size=256):
-    """Deff images/s of the packed batch mode on config 3 inputs (host images in, Deff out)."""
+def rel_err(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+def leg_c1(ctx):
+    """configs[0]: bundled 00000.jpg at native resolution, shipped input.txt defaults (3-phase, 7 continuation
+    stages) through the whole-path call, against the reference's own run (BASELINE.md section 2 / tests/golden)."""
+    import effectivediffusivityfvm_b200 as E
+    img = np.load(os.path.join(ROOT, "tests", "golden", "images.npz"))["img00000"]
+    want_iters, want_deff = [80001, 10001, 10001, 10001, 10001, 10001, 10001], 224673.610442892
+    ctx.solve_image(img, E.default_params(max_iter=11))                       # warm-up: allocations, graphs
+    t0 = time.perf_counter()
+    r = ctx.solve_image(img, E.default_params())
+    dt = time.perf_counter() - t0
+    out = {"workload": "00000.jpg 128x128, shipped input.txt defaults (3-phase, Ds 0, Df 1, Dg 1237500, tol 1e-5, MaxIter 5e5)",
+           "iters": r["iters"], "total_sweeps": r["total_iters"], "deff": r["deff"], "reference_deff": want_deff,
+           "deff_rel_err": rel_err(r["deff"], want_deff), "seconds": dt, "solve_ms": r["solve_ms"],
+           "glups": 128 * 128 * r["total_iters"] / dt / 1e9, "us_per_sweep": dt * 1e6 / max(r["total_iters"], 1)}
+    out["parity"] = bool(r["iters"] == want_iters and out["deff_rel_err"] <= 1e-4)
+    t0 = time.perf_counter()
+    r2 = ctx.solve_image(img, E.default_params(Ds=1e-4, Df=1.0, mode=E.MODE_2PH_BATCH))
+    dt2 = time.perf_counter() - t0
+    out["two_phase"] = {"workload": "same image, Phases 2, Ds 1e-4, Df 1", "iters": r2["iters"], "deff": r2["deff"],
+                        "reference_deff": 0.1816910277372, "deff_rel_err": rel_err(r2["deff"], 0.1816910277372), "seconds": dt2,
+                        "parity": bool(r2["iters"] == [100001] and rel_err(r2["deff"], 0.1816910277372) <= 1e-4)}
+    out["parity"] = bool(out["parity"] and out["two_phase"]["parity"])
+    return out
+
+
+def leg_c2_parity(ctx, img, p, base):
+    """configs[1] parity at full size: Deff after the same number of sweeps from x0 as the CPU oracle ran."""
+    n = int(base["sweeps"])
+    ctx.domain_load(img, 3, p)
+    ctx.sweeps(n)
+    d = ctx.flux()[0]
+    e = rel_err(d, base["deff_raw"])
+    return {"sweeps": n, "deff_raw": d, "oracle_deff_raw": base["deff_raw"], "deff_rel_err": e, "parity": bool(e <= 1e-4),
+            "note": "un-normalised Deff of the full 4008x8028 domain after %d sweeps from x0, library vs CPU oracle" % n}
+
+
+def leg_c3(ctx, rank, world, count, size=256, oracle_checks=4):
+    """configs[2]: `count` distinct images per GPU (image index rank*count + k) through the packed batch mode,
+    host images in, Deff out; per-image sweep histogram; `oracle_checks` images of rank 0 re-solved by the CPU oracle."""
     import effectivediffusivityfvm_b200 as E
     from effectivediffusivityfvm_b200.datasets import c3_image
-    imgs = np.stack([c3_image(k, size) for k in range(count)])
+    first = rank * count
+    imgs = np.stack([c3_image(first + k, size) for k in range(count)])
     p = E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH, tol=1e-5, max_iter=500000)
     ctx.solve_batch(imgs[:2], E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH, max_iter=50))
     t0 = time.perf_counter()
     res = ctx.solve_batch(imgs, p)
     dt = time.perf_counter() - t0
-    sweeps = float(sum(r["total_iters"] for r in res))
-    return {"workload": "configs[2] sample: %d synthetic two-phase %dx%d images, Ds 1e-3, Df 1, tol 1e-5, MaxIter 5e5" % (count, size, size),
-            "images": count, "seconds": dt, "images_per_s": count / dt, "glups": sweeps * size * size / dt / 1e9}
+    iters = np.array([r["total_iters"] for r in res], dtype=np.int64)
+    hist = {}
+    for v in iters:
+        hist[int(v)] = hist.get(int(v), 0) + 1
+    out = {"workload": "%d distinct synthetic two-phase %dx%d images per GPU (c3_image(rank*%d + k)), Ds 1e-3, Df 1, tol 1e-5, "
+                       "MaxIter 5e5, packed batch mode" % (count, size, size, count),
+           "images": count, "seconds": dt, "images_per_s": count / dt, "glups": float(iters.sum()) * size * size / dt / 1e9,
+           "sweeps_total": int(iters.sum()), "sweep_histogram": {str(k): hist[k] for k in sorted(hist)},
+           "pathflag_sum": int(sum(r["pathflag"] for r in res))}
+    if rank == 0 and oracle_checks > 0:
+        import _oracle as O
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        O.oracle().orc_set_num_threads(int(ncpu))
+        # the cheapest images for the oracle (it runs ~1 GLUP/s): smallest sweep counts, ties by index
+        pick = [int(k) for k in np.argsort(iters, kind="stable")[:oracle_checks]]
+        checks, ok = [], True
+        t1 = time.perf_counter()
+        for k in pick:
+            ref = O.solve_image(imgs[k], O.make_opts(Ds=1e-3, Df=1.0, nphase=2), O.MODE_2PH_BATCH)
+            e = rel_err(res[k]["deff"], ref["deff"])
+            good = bool(res[k]["iters"] == ref["iters"] and e <= 1e-4 and res[k]["pathflag"] == ref["pathflag"])
+            ok = ok and good
+            checks.append({"image": first + k, "iters": res[k]["iters"], "oracle_iters": ref["iters"], "deff": res[k]["deff"],
+                           "oracle_deff": ref["deff"], "deff_rel_err": e, "ok": good})
+        out["oracle_checks"] = checks
+        out["oracle_seconds"] = time.perf_counter() - t1
+        out["parity"] = ok
+    return out
+
+
+def leg_c4(ctx, rank, local_rank, world, size=16384, sweeps=10001):
+    """configs[3]: one size x size two-phase domain, the reference loop with MaxIter `sweeps` (checks at sweeps 1 and
+    10 001), row slabs over all ranks with NCCL halo exchange and flux all-reduce.  Strong scaling: fixed total work."""
+    import torch
+    import effectivediffusivityfvm_b200 as E
+    from effectivediffusivityfvm_b200.datasets import c4_image
+    img = np.tile(c4_image(4096), (size // 4096, size // 4096))          # periodic generator: a seamless medium
+    p = E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    if world > 1:
+        import torch.distributed as dist
+        from effectivediffusivityfvm_b200 import slab as slabmod
+        dom = slabmod.SlabDomain(ctx, img, p, rank, world, nphase=2)
+        load = dom.reload
+        solve = dom.solve
+    else:
+        def load():
+            ctx.domain_load(img, 2, p)
+        solve = ctx.solve
+        load()
+    solve(1e-30, 401)                                                     # warm-up incl. CUDA-graph capture
+    load()
+    ctx.sync()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    r = solve(1e-30, sweeps)
+    e1.record(stream)
+    ctx.sync()
+    ms = e0.elapsed_time(e1)
+    t0 = time.perf_counter()
+    load()
+    r2 = solve(1e-30, sweeps)
+    ctx.sync()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0].item()), float(t[1].item())
+    cells = size * size
+    return {"workload": "one %dx%d two-phase domain (sigma 8 px blobs, porosity 0.6), Ds 1e-3, Df 1, MaxIter %d: "
+                        "%s" % (size, size, sweeps, "single GPU" if world == 1 else "%d row slabs, NCCL halo exchange + flux all-reduce" % world),
+            "scaling": "strong", "cells": cells, "sweeps": int(r["iters"]), "ms": ms, "glups": cells * r["iters"] / (ms * 1e-3) / 1e9,
+            "e2e_seconds": e2e_s, "e2e_glups": cells * r2["iters"] / e2e_s / 1e9,
+            "deff_raw": r["deff_raw"], "deff_raw_hex": float(r["deff_raw"]).hex(),
+            "parity": bool(r["iters"] == sweeps and np.isfinite(r["deff_raw"]) and r["deff_raw"] == r2["deff_raw"]),
+            "note": "deff_raw must be identical at every N (bitwise: compare deff_raw_hex across the SCALE lines); "
+                    "e2e = slab upload from host buffers + assembly + the same solve"}
+
+
+def leg_slab_parity(rank, local_rank, world):
+    """N > 1: a small 3-phase and a 2-phase domain decomposed into `world` row slabs against the undecomposed run on
+    this rank's own GPU: own rows bit for bit after 1 / 4 / 203 sweeps, Deff, and the full reference loop."""
+    import torch
+    import torch.distributed as dist
+    import effectivediffusivityfvm_b200 as E
+    from effectivediffusivityfvm_b200.slab import SlabDomain
+    rng = np.random.default_rng(11)
+    z = rng.random((300, 500))
+    for _ in range(3):
+        z = (z + np.roll(z, 1, 0) + np.roll(z, -1, 0) + np.roll(z, 1, 1) + np.roll(z, -1, 1)) / 5
+    q1, q2 = np.quantile(z, [0.3, 0.7])
+    img = np.where(z < q1, 0, np.where(z < q2, 150, 255)).astype(np.uint8)
+    ok, worst = True, 0.0
+    for nphase, halo in ((3, 16), (2, 32)):
+        p = E.default_params(Ds=0.0 if nphase == 3 else 1e-3, Df=1.0, Dg=80.0, CL=0.25, CR=1.5, check_every=400)
+        ref, ctx = E.Deff2D(local_rank), E.Deff2D(local_rank)
+        ref.domain_load(img, nphase, p)
+        dom = SlabDomain(ctx, img, p, rank, world, nphase=nphase, halo=halo)
+        L = dom.layout
+        for n in (1, 4, 203):
+            ref.sweeps(n)
+            dom.sweeps(n)
+            same = np.array_equal(dom.own_field(), ref.get_field()[L.row0:L.row0 + L.own_rows], equal_nan=True)
+            e = rel_err(dom.flux(), ref.flux()[0])
+            worst = max(worst, e)
+            ok = ok and same and e < 1e-12
+        ref.domain_load(img, nphase, p)
+        a = ref.solve(1e-4, 6000)
+        dom.reload()
+        b = dom.solve(1e-4, 6000)
+        e = rel_err(b["deff_raw"], a["deff_raw"])
+        worst = max(worst, e)
+        ok = ok and a["iters"] == b["iters"] and e < 1e-12
+        ref.close()
+        ctx.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return {"parity": bool(flag.item()), "worst_deff_rel_err_rank0": worst,
+            "what": "300x500 domain, 3-phase (halo 16) and 2-phase (halo 32), %d slabs vs one GPU: own rows bitwise after 1/4/203 sweeps, "
+                    "Deff <= 1e-12, same sweep count of the full loop; all ranks agree" % world}
+
+
+def leg_c5(ctx, oracle_sweeps):
+    """configs[4]: 2048 x 2048 site percolation just above threshold, Ds/Df = 1e-4, full solve to the reference stop
+    rule; the first `oracle_sweeps` sweeps against the CPU oracle (the full solve is ~35 CPU-minutes)."""
+    import effectivediffusivityfvm_b200 as E
+    from effectivediffusivityfvm_b200.datasets import c5_image
+    img = c5_image()
+    p = E.default_params(Ds=1e-4, Df=1.0, mode=E.MODE_2PH_BATCH, tol=1e-5, max_iter=500000)
+    ctx.solve_image(img, E.default_params(Ds=1e-4, Df=1.0, mode=E.MODE_2PH_BATCH, max_iter=401))
+    t0 = time.perf_counter()
+    r = ctx.solve_image(img, p)
+    dt = time.perf_counter() - t0
+    out = {"workload": "2048x2048 site percolation p = 0.60, Ds 1e-4, Df 1, tol 1e-5, MaxIter 5e5, full solve",
+           "iters": r["iters"], "deff": r["deff"], "conv": r["conv"], "pathflag": r["pathflag"], "seconds": dt, "solve_ms": r["solve_ms"],
+           "glups": 2048 * 2048 * r["total_iters"] / dt / 1e9}
+    ok = bool(np.isfinite(r["deff"]) and r["deff"] > 0 and (r["total_iters"] - 1) % 10000 == 0 or r["total_iters"] == 500000)
+    if oracle_sweeps > 0:
+        import _oracle as O
+        ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        O.oracle().orc_set_num_threads(int(ncpu))
+        o = O.make_opts(Ds=1e-4, Df=1.0, Dg=0.0, nphase=2)
+        d = np.zeros(1)
+        O.oracle().orc_time_sweeps(O._up(np.ascontiguousarray(img)), 2048, 2048, o, 0, oracle_sweeps, O._dp(d))
+        ctx.domain_load(img, 2, p)
+        ctx.sweeps(oracle_sweeps)
+        mine = ctx.flux()[0]
+        e = rel_err(mine, float(d[0]))
+        out["oracle_prefix"] = {"sweeps": oracle_sweeps, "deff_raw": mine, "oracle_deff_raw": float(d[0]), "deff_rel_err": e}
+        ok = ok and e <= 1e-4
+    out["parity"] = bool(ok)
+    return out
 
 
 def run_ours(args):
@@ -284,13 +490,14 @@ def run_ours(args):
 
     # roofline of the dominant kernel (the sweep): live CUDA-event time of sweep launches only
     sweep_ms = ctx.sweeps_timed(S) if not slab_mode else ms / args.steps
-    # slab mode: the timed step also holds the halo exchanges; one sweep launch = 8 sweeps over the local slab
-    sweep_launches_per_step = (launches / args.steps) - 2 if not slab_mode else S / 8.0
+    # slab mode: the timed step also holds the halo exchanges; one sweep launch = `depth` sweeps over the local slab
+    depth = args.tblock if args.kernel == 2 and args.tblock > 0 else ctx.default_depth
+    sweep_launches_per_step = (launches / args.steps) - 2 if not slab_mode else S / float(depth)
     peak, peak_src = measured_peaks()
     local_cells = cells // world
     achieved = ALG_BYTES_PER_LUP * local_cells * S / (sweep_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "sweep (K%d, tblock %d)" % (args.kernel, args.tblock),
+                "traffic": None, "peak_source": peak_src, "kernel": "k_sweep_tma (tiled sweep, %d sweeps per HBM pass)" % depth if args.kernel != 1 else "k_sweep_simple",
                 "alg_bytes_per_launch": ALG_BYTES_PER_LUP * local_cells * (S / max(sweep_launches_per_step or S, 1)),
                 "avg_launch_us": sweep_ms * 1e3 / max(sweep_launches_per_step or S, 1)}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -354,26 +561,45 @@ def run_ours(args):
                        "cells": cells, "sweeps_per_step": S, "l2_policy": "working set 2x%.0f MB > 126 MB L2, no flush needed" % (Nx * Ny * 8 / 1e6),
                        "kernel": args.kernel, "tblock": args.tblock},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "deff_raw": deff}
+    configs = {}
     if args.batch_images > 0:
-        # image batches shard with no communication: every rank solves its own slice
-        bl = batch_leg(ctx, args.batch_images)
+        # image batches shard with no communication: every rank solves its own, distinct slice
+        bl = leg_c3(ctx, rank, world, args.batch_images, oracle_checks=args.c3_oracle_checks)
         if world > 1:
-            t = torch.tensor([bl["seconds"]], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            bl["seconds"] = float(t.item())
+            t = torch.tensor([bl["seconds"], float(bl["sweeps_total"])], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)
+            dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+            bl["seconds"] = float(t[0].item())
             bl["images"] = args.batch_images * world
             bl["images_per_s"] = bl["images"] / bl["seconds"]
-            bl["glups"] = None
-        line["batch"] = bl
+            bl["sweeps_total"] = int(t[1].item())
+            bl["glups"] = bl["sweeps_total"] * 65536 / bl["seconds"] / 1e9
+            bl["note"] = "images, seconds (max over ranks) and sweeps are whole-job; histogram and oracle checks are rank 0's slice"
+        configs["c3"] = bl
+        line["batch"] = {k: bl[k] for k in ("workload", "images", "seconds", "images_per_s", "glups")}
+    if not args.no_c4:
+        configs["c4"] = leg_c4(ctx, rank, local_rank, world, size=args.c4_size)
+    if world > 1:
+        line["slab_parity"] = leg_slab_parity(rank, local_rank, world)
+    if world == 1:
+        if not args.no_c1:
+            configs["c1"] = leg_c1(ctx)
+        if not args.no_c5:
+            configs["c5"] = leg_c5(ctx, args.c5_oracle_sweeps)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(img, args.cpu_sweeps)
+            configs["c2"] = leg_c2_parity(ctx, img, p, line["cpu_baseline"])
             try:
                 rc = ref_cuda_baseline(img, args.ref_cuda_sweeps)
             except Exception as e:      # a reported baseline must not take the bench line down
                 rc = {"unavailable": "%s: %s" % (type(e).__name__, e)}
             if rc:
                 line["ref_cuda_baseline"] = rc
+        line["configs"] = configs
+        line["parity"] = {k: v.get("parity") for k, v in configs.items()}
+        if "slab_parity" in line:
+            line["parity"]["slab_vs_single_gpu"] = line["slab_parity"]["parity"]
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
@@ -394,7 +620,13 @@ def main():
     ap.add_argument("--ref-crop", type=int, default=0, help="use only the first N source rows for the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-cuda-sweeps", type=int, default=1001)
-    ap.add_argument("--batch-images", type=int, default=64, help="also time the packed batch mode on this many config-3 images per GPU (0: skip)")
+    ap.add_argument("--batch-images", type=int, default=512, help="config 3: images per GPU through the packed batch mode (0: skip)")
+    ap.add_argument("--c3-oracle-checks", type=int, default=4, help="config 3: images of rank 0 re-solved by the CPU oracle")
+    ap.add_argument("--c4-size", type=int, default=16384)
+    ap.add_argument("--c5-oracle-sweeps", type=int, default=60)
+    ap.add_argument("--no-c1", action="store_true")
+    ap.add_argument("--no-c4", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
     ap.add_argument("--allow-short-warmup", action="store_true")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostic: do not poll NVML during the timed region")
     args = ap.parse_args()

@@ -90,6 +90,8 @@ def lib():
         "deff2d_domain_info": (i32, [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32), c_double_p, c_double_p, c_double_p]),
         "deff2d_sync": (i32, [vp]),
         "deff2d_set_kernel": (i32, [vp, i32, i32]),
+        "deff2d_set_resident": (i32, [vp, i32]),
+        "deff2d_default_depth": (i32, [vp]),
         "deff2d_set_batch_slots": (i32, [vp, i32]),
         "deff2d_set_floodfill": (i32, [vp, i32]),
         "deff2d_set_graphs": (i32, [vp, i32]),

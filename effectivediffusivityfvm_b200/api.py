@@ -286,6 +286,10 @@ class Deff2D:
     def set_kernel(self, kernel, tblock=0):
         self._ck(self._L.deff2d_set_kernel(self._h, int(kernel), int(tblock)))
 
+    def set_resident(self, mode):
+        """0: domains / batch images of up to 256 x 256 cells run cluster-resident (default), 1: never."""
+        self._ck(self._L.deff2d_set_resident(self._h, int(mode)))
+
     def set_floodfill(self, mode):
         """0 automatic, 1 host FloodFill, 2 device FloodFill (same result)."""
         self._ck(self._L.deff2d_set_floodfill(self._h, int(mode)))
@@ -293,6 +297,11 @@ class Deff2D:
     def set_batch_slots(self, max_slots):
         """Cap the images resident at a time in packed batch mode (0 = library default)."""
         self._ck(self._L.deff2d_set_batch_slots(self._h, int(max_slots)))
+
+    @property
+    def default_depth(self):
+        """Sweeps per HBM pass of the default tiled kernel."""
+        return int(self._L.deff2d_default_depth(self._h))
 
     @property
     def kernel_launches(self):

@@ -531,6 +531,7 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     int next_image = 0, nactive = 0, done_images = 0;
     bool active_changed = true;
     c->tblock = T;
+    const bool use_resident = c->resident_mode == 0 && resident_eligible(c, Nx, Ny);
     auto restore = [&]() {
         c->tile_family = old_family; c->tblock = old_tblock;
         c->tile_list = nullptr; c->tile_count = 0;
@@ -592,10 +593,15 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
         }
         if (n < 1) { restore(); set_error(c, "packed batch: internal scheduling error"); return DEFF2D_ERR_STATE; }
         CUB(cudaEventRecord(b->e0, s));
-        if (n >= T && (rc = tma_passes(c, T, n / T, b->tiles.p + tile_off[T], tile_cnt[T]))) { restore(); return rc; }
-        if (const int t = (int)(n % T)) {
-            if ((rc = tma_pass(c, t, b->tiles.p + tile_off[t], tile_cnt[t], s))) { restore(); return rc; }
-            c->cur ^= 1;
+        if (use_resident) {
+            // images of up to 256 x 256 cells: one cluster per image keeps it on chip for all n sweeps (resident.cu)
+            if ((rc = resident_sweeps(c, n, Nx, Ny, GX, b->active.p, nactive))) { restore(); return rc; }
+        } else {
+            if (n >= T && (rc = tma_passes(c, T, n / T, b->tiles.p + tile_off[T], tile_cnt[T]))) { restore(); return rc; }
+            if (const int t = (int)(n % T)) {
+                if ((rc = tma_pass(c, t, b->tiles.p + tile_off[t], tile_cnt[t], s))) { restore(); return rc; }
+                c->cur ^= 1;
+            }
         }
         k_batch_check<<<nactive, 1024, 0, s>>>(g, stages, b->slots.p, b->outs.p, b->active.p, n, c->x[c->cur].p, c->code.p, c->idx16.p);
         c->launches++;

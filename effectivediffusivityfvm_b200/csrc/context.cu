@@ -103,12 +103,17 @@ static int enqueue_sweeps(deff2d_ctx *c, int64_t n)
     if (c->slab && c->slab_domain) return slab_enqueue_sweeps(c, n);
     while (n > 0) {
         int64_t done = 0;
-        // kernel 0 (default): the TMA tiled kernel (square 64 x 64 tiles) from 64 cells up, replayed as CUDA
-        // graphs: even a tiny domain then costs ~0.7 us per sweep instead of one 8 us launch per sweep.
-        // Depth: 8 sweeps per pass (measured with square tiles on config 2: 811 / 816 / 827 GLUP/s at
-        // T = 4 / 6 / 8; 4096^2 and 2048^2 interface-rich media: best at 8; small domains are bound by
-        // per-pass latency, so the deepest pass wins there too).
+        // kernel 0 (default): the TMA tiled kernel (64 x 64 tiles, 2 x 8 cells per thread) from 64 cells up, replayed
+        // as CUDA graphs.  Depth: 6 sweeps per pass -- measured on B200 with the 2 x 8 layout at T = 4 / 5 / 6 / 7 / 8:
+        // config 2 861 / 839 / 878 / 848 / 838 GLUP/s, 4096^2 blob medium 720 / 784 / 825 / 793 / 789, 2048^2 site
+        // percolation 562 / 582 / 644 / 650 / 626 (the 4 x 4 layout of round 1: 802 / 776 / 814 / 823 / 822 on config 2).
         const int64_t ncell = c->Nx * c->Ny;
+        // up to 256 x 256 cells: the whole domain stays on chip for all n sweeps (resident.cu), one launch
+        if (c->kernel == 0 && c->resident_mode == 0 && ncell >= 64 && !c->tile_list && resident_eligible(c, c->Nx, c->Ny)) {
+            int rc = resident_sweeps(c, n, c->Nx, c->Ny, 1, nullptr, 1);
+            if (rc) return rc;
+            break;
+        }
         if (c->kernel == 2 || (c->kernel == 0 && ncell >= 64)) {
             int rc = launch_sweep_tma(c, n, c->kernel == 0 ? c->k2_default_depth : c->tblock, &done);
             if (rc) return rc;
@@ -472,6 +477,7 @@ DEFF2D_EXPORT void deff2d_destroy(deff2d_ctx *c)
     cudaStreamSynchronize(c->stream);
     slab_destroy(c);
     batch_destroy(c);
+    resident_destroy(c);
     tma_destroy(c);
     for (int k = 0; k < 2; k++) if (c->x[k].p) cudaFree(c->x[k].p);
     if (c->code.p) cudaFree(c->code.p);
@@ -737,12 +743,21 @@ DEFF2D_EXPORT int deff2d_set_floodfill(deff2d_ctx *c, int mode)
     return DEFF2D_OK;
 }
 
+DEFF2D_EXPORT int deff2d_set_resident(deff2d_ctx *c, int mode)
+{
+    if (!c || mode < 0 || mode > 1) return DEFF2D_ERR_ARG;
+    c->resident_mode = mode;
+    return DEFF2D_OK;
+}
+
 DEFF2D_EXPORT int deff2d_set_batch_slots(deff2d_ctx *c, int max_slots)
 {
     if (!c || max_slots < 0) return DEFF2D_ERR_ARG;
     c->batch_max_slots = max_slots;
     return DEFF2D_OK;
 }
+
+DEFF2D_EXPORT int deff2d_default_depth(const deff2d_ctx *c) { return c ? c->k2_default_depth : DEFF2D_DEFAULT_DEPTH; }
 
 DEFF2D_EXPORT int64_t deff2d_kernel_launches(const deff2d_ctx *c) { return c ? c->launches : 0; }
 

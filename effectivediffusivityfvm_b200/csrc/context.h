@@ -57,7 +57,7 @@ struct deff2d_ctx {
     int tile_family = 0;             // sweep_tma.cu thread layout: 3 = 4 x 4 patches, 4 = 2 x 8 patches, else the default
     int k2_variant = 0;              // sweep_tma.cu: bit 0 [slot][4] weight table, bit 1 split-phase sweep barrier
     int k2_default_family = DEFF2D_DEFAULT_TILE_FAMILY;
-    int k2_default_depth = 8;        // sweeps per HBM pass of kernel 0
+    int k2_default_depth = DEFF2D_DEFAULT_DEPTH;   // sweeps per HBM pass of kernel 0
     int64_t launches = 0;
 
     // TMA tiled sweep state (sweep_tma.cu)
@@ -66,6 +66,10 @@ struct deff2d_ctx {
                                      // for one domain, image width + 1 in a packed batch
     const uint32_t *tile_list = nullptr;   // device: ty << 16 | tx of the tiles to sweep (NULL: the whole tile grid)
     int tile_count = 0;
+
+    // cluster-resident sweeps (resident.cu)
+    void *resident = nullptr;
+    int resident_mode = 0;           // 0: domains / batch images of up to 256 x 256 cells run cluster-resident, 1: never
 
     // packed-batch state (batch.cu)
     void *batch = nullptr;
@@ -106,6 +110,11 @@ int slab_allreduce_q(deff2d_ctx *c);     // no-op unless the resident domain is 
 int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n);
 void slab_destroy(deff2d_ctx *c);
 void batch_destroy(deff2d_ctx *c);
+
+// resident.cu: cluster-resident sweeps (K5) of images of up to 256 x 256 cells
+bool resident_eligible(deff2d_ctx *c, int64_t Nx, int64_t Ny);
+int resident_sweeps(deff2d_ctx *c, int64_t n, int64_t Nx, int64_t Ny, int GX, const int *active, int nactive);
+void resident_destroy(deff2d_ctx *c);
 
 // floodfill.cu: FloodFill (cuh:557-713) by label propagation on the device; blocks
 int floodfill_device(deff2d_ctx *c, const uint8_t *img, int W, int amp_x, int amp_y, int thr, uint8_t *st, int64_t Nx,

@@ -10,7 +10,8 @@
 #define DEFF2D_LUT_ENTRIES 2048
 #define DEFF2D_CLUT_ENTRIES 1024        // slots per plane of the compact table of the tiled sweep (see clut_slot)
 #define DEFF2D_CLUT_INERT 1023u         // ghost and pinned cells: all four weights 0
-#define DEFF2D_DEFAULT_TILE_FAMILY 3      // sweep_tma.cu: Family<> (square 64 x 64 tiles); what kernel 0 and the planning helpers use
+#define DEFF2D_DEFAULT_TILE_FAMILY 4      // sweep_tma.cu: Family<> (2 x 8 cells per thread, 32 lanes across a 64 x 64 tile): what kernel 0 uses
+#define DEFF2D_DEFAULT_DEPTH 6            // sweeps per HBM pass of kernel 0 (measured on B200, see enqueue_sweeps)
 #define DEFF2D_XOFF 16            // interior column j lives at padded index j + XOFF
 #define DEFF2D_PHASE_FLUID 0
 #define DEFF2D_PHASE_SOLID 1

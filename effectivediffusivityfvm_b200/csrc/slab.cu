@@ -252,7 +252,7 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
     int rc = build_lists(c, s);
     if (rc) { c->tile_family = old_family; return rc; }
     int Tmax = c->tblock > 0 ? c->tblock : 4;
-    if (c->kernel == 0) Tmax = 8;          // default: 8 sweeps per pass, with H = 16 an exchange every second pass
+    if (c->kernel == 0) Tmax = c->k2_default_depth;   // default depth; with 32 halo rows an exchange every fifth pass
     if (Tmax > 8) Tmax = 8;
     if (s->nranks > 1 && Tmax > H) Tmax = (int)H;
     while (n > 0 && !rc) {

@@ -171,6 +171,12 @@ int deff2d_set_kernel(deff2d_ctx *ctx, int kernel, int tblock);
 /* Where FloodFill (cuh:557-713) runs for whole-domain loads: 0 = automatic (device from 64 K cells),
  * 1 = host (FIFO flood), 2 = device (label propagation).  Same result either way. */
 int deff2d_set_floodfill(deff2d_ctx *ctx, int mode);
+/* Sweeps per HBM pass of the default kernel (kernel 0). */
+int deff2d_default_depth(const deff2d_ctx *ctx);
+/* Cluster-resident sweeps (csrc/resident.cu): 0 = domains and batch images of up to 256 x 256 cells stay on chip
+ * for a whole check interval (default), 1 = never (the tiled kernel runs instead).  Same iterates bit for bit.
+ * Tuning / test hook. */
+int deff2d_set_resident(deff2d_ctx *ctx, int mode);
 /* Packed batch mode (deff2d_solve_batch): at most `max_slots` images resident at a time
  * (0 = library default, sized from the image size); finished images are replaced from the
  * queue.  Tuning / test hook. */
