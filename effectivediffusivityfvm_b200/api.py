@@ -287,7 +287,7 @@ class Deff2D:
         self._ck(self._L.deff2d_set_kernel(self._h, int(kernel), int(tblock)))
 
     def set_resident(self, mode):
-        """0: domains / batch images of up to 256 x 256 cells run cluster-resident (default), 1: never."""
+        """0: single domains of up to 256 x 256 cells run cluster-resident (default), 1: never, 2: packed batches too."""
         self._ck(self._L.deff2d_set_resident(self._h, int(mode)))
 
     def set_floodfill(self, mode):

@@ -109,7 +109,7 @@ static int enqueue_sweeps(deff2d_ctx *c, int64_t n)
         // percolation 562 / 582 / 644 / 650 / 626 (the 4 x 4 layout of round 1: 802 / 776 / 814 / 823 / 822 on config 2).
         const int64_t ncell = c->Nx * c->Ny;
         // up to 256 x 256 cells: the whole domain stays on chip for all n sweeps (resident.cu), one launch
-        if (c->kernel == 0 && c->resident_mode == 0 && ncell >= 64 && !c->tile_list && resident_eligible(c, c->Nx, c->Ny)) {
+        if (c->kernel == 0 && c->resident_mode != 1 && ncell >= 64 && !c->tile_list && resident_eligible(c, c->Nx, c->Ny)) {
             int rc = resident_sweeps(c, n, c->Nx, c->Ny, 1, nullptr, 1);
             if (rc) return rc;
             break;
@@ -745,7 +745,7 @@ DEFF2D_EXPORT int deff2d_set_floodfill(deff2d_ctx *c, int mode)
 
 DEFF2D_EXPORT int deff2d_set_resident(deff2d_ctx *c, int mode)
 {
-    if (!c || mode < 0 || mode > 1) return DEFF2D_ERR_ARG;
+    if (!c || mode < 0 || mode > 2) return DEFF2D_ERR_ARG;
     c->resident_mode = mode;
     return DEFF2D_OK;
 }

@@ -69,7 +69,7 @@ struct deff2d_ctx {
 
     // cluster-resident sweeps (resident.cu)
     void *resident = nullptr;
-    int resident_mode = 0;           // 0: domains / batch images of up to 256 x 256 cells run cluster-resident, 1: never
+    int resident_mode = 0;           // 0: single domains of up to 256 x 256 cells run cluster-resident, 1: never, 2: packed batches too
 
     // packed-batch state (batch.cu)
     void *batch = nullptr;

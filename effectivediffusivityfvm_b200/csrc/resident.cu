@@ -61,6 +61,10 @@ __device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
 }
+__device__ __forceinline__ void bar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
+}
 __device__ __forceinline__ void bar_expect(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
@@ -109,8 +113,8 @@ k_resident(double *__restrict__ x, const uint16_t *__restrict__ idx16, const dou
     for (int k = tid; k < P_DOUBLES; k += 256) P[k] = 0.0;
     for (int k = tid; k < 2 * H_DOUBLES; k += 256) HW[k] = 1.0;             // HW and HE are contiguous
     if (tid == 0) {
-        bar_init(&bar[0], 1);
-        bar_init(&bar[1], 1);
+        bar_init(&bar[0], 8);
+        bar_init(&bar[1], 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -154,8 +158,6 @@ k_resident(double *__restrict__ x, const uint16_t *__restrict__ idx16, const dou
     const bool sendW = (lane == 0) && hasW, sendE = (lane == 31) && hasE;
     if (sendW) { rWE_addr = map_rank(s32(HE + r0), rankW); rWE_bar = map_rank(lbar, rankW); }   // my column 0 -> its column 64
     if (sendE) { rWE_addr = map_rank(s32(HW + r0), rankE); rWE_bar = map_rank(lbar, rankE); }   // my column 63 -> its column -1
-    const bool edge_lane = (lane == 0) || (lane == 31);
-    const double *const hcol = (lane == 0) ? HW : HE;
 
     // level-s rows and columns that other threads need: the top row is published as soon as it exists, the rest at
     // the end of the sweep.  Local neighbours read the planar buffer P, the neighbouring CTAs get st.async pushes.
@@ -180,14 +182,24 @@ k_resident(double *__restrict__ x, const uint16_t *__restrict__ idx16, const dou
 #pragma unroll
             for (int px = 0; px < RPX; px++) st_async_f64(rS_addr + poff + px * (RROWS * RPW * 8), xv[RPY - 1][px], rS_bar + boff);
         }
-        if (tid == 0) bar_expect(&bar[par], expect);
-    };
-    // lanes 0 / 31: one row of the tile's edge column to the neighbouring CTA, as soon as the row is final
-    auto send_col = [&](auto par_c, int py) {
-        constexpr int par = decltype(par_c)::value;
-        constexpr uint32_t hoff = (uint32_t)par * (RT * 8), boff = (uint32_t)par * 8;
-        const double v = (lane == 0) ? xv[py][0] : xv[py][RPX - 1];
-        if (sendW || sendE) st_async_f64(rWE_addr + hoff + py * 8, v, rWE_bar + boff);
+        // lanes 0 / 31: the tile's edge column to the neighbouring CTA, straight from the patch registers (8-byte
+        // pushes need no staging moves; two-row 16-byte pushes with per-lane selects measured 1310 cycles per sweep)
+        constexpr uint32_t hoff = (uint32_t)par * (RT * 8);
+        if (sendW) {
+#pragma unroll
+            for (int py = 0; py < RPY; py++) st_async_f64(rWE_addr + hoff + py * 8, xv[py][0], rWE_bar + boff);
+        }
+        if (sendE) {
+#pragma unroll
+            for (int py = 0; py < RPY; py++) st_async_f64(rWE_addr + hoff + py * 8, xv[py][RPX - 1], rWE_bar + boff);
+        }
+        // one arrival per warp once its rows are in P (thread 0's also announces the bytes the neighbouring CTAs push):
+        // the wait at the top of the next sweep then covers the local exchange and the remote one -- no CTA barrier
+        __syncwarp();
+        if (lane == 0) {
+            if (warp == 0) bar_expect(&bar[par], expect);
+            else bar_arrive(&bar[par]);
+        }
     };
     using Par0 = std::integral_constant<int, 0>;
     using Par1 = std::integral_constant<int, 1>;
@@ -202,10 +214,7 @@ k_resident(double *__restrict__ x, const uint16_t *__restrict__ idx16, const dou
     }
     if (nsweeps > 0) {
         publish_top(Par0{});
-#pragma unroll
-        for (int py = 0; py < RPY; py++) send_col(Par0{}, py);
         publish_rest(Par0{});
-        __syncthreads();
     }
     const int rowN = r0, rowS = r0 + RPY + 1;          // exchange-row indices of the rows above / below the patch
     // one sweep: level s-1 (exchange buffers of parity `par`) -> level s; publishes level s unless it is the last
@@ -214,21 +223,23 @@ k_resident(double *__restrict__ x, const uint16_t *__restrict__ idx16, const dou
         using Next = std::integral_constant<int, 1 - par>;
         const bool pub = s < nsweeps;
         double hN[RPX], hS[RPX];
-        bar_wait(&bar[par], (uint32_t)(((s - 1) >> 1) & 1));              // the neighbours' level s-1 edges have landed
+        bar_wait(&bar[par], (uint32_t)(((s - 1) >> 1) & 1));              // level s-1: every warp's rows are in P, the neighbours' edges have landed
         const double *pr = P + par * (RPX * RROWS * RPW);
 #pragma unroll
         for (int px = 0; px < RPX; px++) {
             hN[px] = pr[(px * RROWS + rowN) * RPW + lane];
             hS[px] = pr[(px * RROWS + rowS) * RPW + lane];
         }
-        if (edge_lane) {                               // lanes 0 / 31: the halo column comes from the neighbouring CTA
-            const double2 *hp = reinterpret_cast<const double2 *>(hcol + par * RT + r0);
+        // lanes 0 / 31: the halo column comes from the neighbouring CTA (or holds the Dirichlet ghost value)
+        if (lane == 0) {
+            const double2 *hp = reinterpret_cast<const double2 *>(HW + par * RT + r0);
 #pragma unroll
-            for (int py = 0; py < RPY; py += 2) {
-                const double2 v = hp[py >> 1];
-                if (lane == 0) { hW[py] = v.x; hW[py + 1] = v.y; }
-                else { hE[py] = v.x; hE[py + 1] = v.y; }
-            }
+            for (int py = 0; py < RPY; py += 2) { const double2 v = hp[py >> 1]; hW[py] = v.x; hW[py + 1] = v.y; }
+        }
+        if (lane == 31) {
+            const double2 *hp = reinterpret_cast<const double2 *>(HE + par * RT + r0);
+#pragma unroll
+            for (int py = 0; py < RPY; py += 2) { const double2 v = hp[py >> 1]; hE[py] = v.x; hE[py + 1] = v.y; }
         }
         // in-place update; `up[px]` carries the old value of the row above (same FMA order as K2 / K3)
         double up[RPX];
@@ -253,15 +264,9 @@ k_resident(double *__restrict__ x, const uint16_t *__restrict__ idx16, const dou
             }
             hW[py] = __shfl_up_sync(0xffffffffu, xv[py][RPX - 1], 1);
             hE[py] = __shfl_down_sync(0xffffffffu, xv[py][0], 1);
-            if (pub) {
-                if (py == 0) publish_top(Next{});
-                send_col(Next{}, py);
-            }
+            if (py == 0 && pub) publish_top(Next{});
         }
-        if (pub) {
-            publish_rest(Next{});
-            __syncthreads();
-        }
+        if (pub) publish_rest(Next{});
     };
     {
         long long s = 1;

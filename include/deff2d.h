@@ -173,9 +173,9 @@ int deff2d_set_kernel(deff2d_ctx *ctx, int kernel, int tblock);
 int deff2d_set_floodfill(deff2d_ctx *ctx, int mode);
 /* Sweeps per HBM pass of the default kernel (kernel 0). */
 int deff2d_default_depth(const deff2d_ctx *ctx);
-/* Cluster-resident sweeps (csrc/resident.cu): 0 = domains and batch images of up to 256 x 256 cells stay on chip
- * for a whole check interval (default), 1 = never (the tiled kernel runs instead).  Same iterates bit for bit.
- * Tuning / test hook. */
+/* Cluster-resident sweeps (csrc/resident.cu): 0 = a single domain of up to 256 x 256 cells stays on chip for a
+ * whole check interval (default), 1 = never (the tiled kernel runs instead), 2 = the images of a packed batch
+ * too (measured slower than the tiled kernel on B200, kept selectable).  Same iterates bit for bit. */
 int deff2d_set_resident(deff2d_ctx *ctx, int mode);
 /* Packed batch mode (deff2d_solve_batch): at most `max_slots` images resident at a time
  * (0 = library default, sized from the image size); finished images are replaced from the

@@ -633,6 +633,108 @@ def test_full_size_config4_properties(ctx):
     ctx.domain_load(blobs(1, (16, 16)), 2, p)                   # release nothing, but leave a small domain resident
 
 
+
+# ----------------------------------------------------------------------------- config sizes against the oracle
+
+def test_config2_full_size_20_sweeps_vs_oracle(ctx, golden_images):
+    """BASELINE config 2 at full size (4008 x 8028 cells, 3-phase shipped defaults): codes, pinned mask and the field
+    after 20 sweeps against the CPU oracle on the whole domain."""
+    img = golden_images["00042"]
+    p = E.default_params(amp_x=4, amp_y=4)
+    D = O.fill_D(img, 4, 4, 3, 0.0, 1.0, 1237500.0)
+    G, pf = O.floodfill(O.grid_mask(img, 4, 4, 200))
+    A, b = O.discretize(D, 0.0, 1.0, G)
+    ref = O.sweeps(A, b, O.init_x(4008, 8028, 0.0, 1.0), 20)
+    del A, b
+    ctx.set_kernel(0)
+    ctx.domain_load(img, 3, p)
+    assert ctx.info()["pathflag"] == pf
+    codes = ctx.get_codes()
+    assert np.array_equal((codes & 4) != 0, (G == 1) | (G == 2))
+    ctx.sweeps(20)
+    f = ctx.get_field()
+    assert np.array_equal(np.isnan(f), np.isnan(ref))
+    assert np.nanmax(np.abs(f - ref)) < 1e-12
+    assert rel(ctx.flux()[0], O.flux_deff(ref, D, 0.0, 1.0)) < 1e-11
+
+
+def test_packed_batch_of_config3_images_vs_oracle(ctx):
+    """Eight BASELINE config 3 images (256 x 256, sigma 3 px, Ds/Df = 1e-3) through the packed batch mode against the
+    CPU oracle image by image: sweep counts, PathFlag, porosity, Deff; MaxIter 30 001 bounds the oracle's time."""
+    from effectivediffusivityfvm_b200.datasets import c3_image
+    imgs = np.stack([c3_image(k) for k in range(8)])
+    p = E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH, tol=1e-5, max_iter=30001)
+    got = ctx.solve_batch(imgs, p, want_fields=True)
+    for k in range(8):
+        ref = O.solve_image(imgs[k], O.make_opts(Ds=1e-3, Df=1.0, nphase=2, max_iter=30001), O.MODE_2PH_BATCH, want_field=(k == 3))
+        assert got[k]["iters"] == ref["iters"]
+        assert got[k]["pathflag"] == ref["pathflag"] and got[k]["porosity"] == ref["porosity"]
+        assert rel(got[k]["deff"], ref["deff"]) < DEFF_RTOL_TIGHT
+        if k == 3:
+            assert np.max(np.abs(got[k]["field"] - ref["field"])) < FIELD_ATOL
+
+
+def test_stop_rule_at_the_tolerance_boundary(ctx):
+    """cuh:1232 continues while `tol < fabs(change)`: a tolerance equal to |change| of a check stops there, the next
+    representable smaller tolerance does not.  Both against the oracle's loop."""
+    img = blobs(31, (64, 96))
+    opts = dict(Ds=1e-2, Df=1.0, mode=E.MODE_2PH_BATCH, check_every=500, max_iter=100000)
+    ctx.domain_load(img, 2, E.default_params(**opts))
+    probe = ctx.solve(1e-30, 6001)                       # Deff at sweeps 1, 501, ..., 6001
+    tr = probe["trace"]
+    k = 6                                                # the check after sweep 3001
+    change = abs((tr[k - 1] - tr[k]) / tr[k - 1])
+    for tol, want in ((change, k * 500 + 1), (np.nextafter(change, 0.0), None)):
+        got = ctx.solve_image(img, E.default_params(tol=tol, **opts))
+        ref = O.solve_image(img, O.make_opts(Ds=1e-2, Df=1.0, nphase=2, check_every=500, max_iter=100000, tol=tol), O.MODE_2PH_BATCH)
+        assert got["iters"] == ref["iters"]
+        assert rel(got["deff"], ref["deff"]) < DEFF_RTOL_TIGHT
+        if want is not None:
+            assert got["iters"] == [want]
+        else:
+            assert got["iters"][0] > k * 500 + 1
+
+
+# ----------------------------------------------------------------------------- K5 (cluster-resident) == K3 (streaming)
+
+@pytest.mark.parametrize("shape", [(64, 64), (24, 16), (100, 130), (65, 64), (64, 65), (200, 70), (129, 255), (256, 256)])
+@pytest.mark.parametrize("nphase", [2, 3])
+def test_resident_kernel_is_bitwise_identical_to_streaming(ctx, shape, nphase):
+    """A domain of up to 256 x 256 cells stays on chip for all sweeps of a call (one launch, a cluster of up to 4 x 4
+    CTAs exchanging edges through distributed shared memory): same arithmetic as K2 / K3, so the same bits."""
+    img = blobs(shape[0] * 7 + nphase, shape, levels=(0, 150, 255), fracs=(0.3, 0.4), smooth=2)
+    p = E.default_params(Ds=0.0 if nphase == 3 else 1e-3, Df=1.0, Dg=80.0, CL=0.25, CR=1.5)
+    for n in (1, 2, 3, 29, 400):
+        ctx.set_kernel(1)
+        ctx.domain_load(img, nphase, p)
+        ctx.sweeps(n)
+        ref, dref = ctx.get_field(), ctx.flux()[0]
+        ctx.set_kernel(0)
+        ctx.set_resident(0)
+        ctx.domain_load(img, nphase, p)
+        l0 = ctx.kernel_launches
+        ctx.sweeps(n)
+        assert ctx.kernel_launches - l0 == 1
+        assert np.array_equal(ctx.get_field(), ref, equal_nan=True)
+        d = ctx.flux()[0]
+        assert d == dref or (np.isnan(d) and np.isnan(dref))
+    ctx.set_kernel(0)
+
+
+def test_resident_packed_batch_matches_tiled_packed_batch(ctx):
+    from effectivediffusivityfvm_b200.datasets import c3_image
+    imgs = np.stack([c3_image(100 + k, 192) for k in range(12)])
+    p = E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH, max_iter=40001)
+    out = {}
+    for mode in (1, 2):
+        ctx.set_resident(mode)
+        ctx.set_batch_slots(5)                           # slots are refilled while others are still running
+        out[mode] = ctx.solve_batch(imgs, p)
+    ctx.set_resident(0)
+    ctx.set_batch_slots(0)
+    for a, b in zip(out[1], out[2]):
+        assert a["iters"] == b["iters"] and a["deff"] == b["deff"] and a["conv"] == b["conv"] and a["pathflag"] == b["pathflag"]
+
 # ----------------------------------------------------------------------------- K2 (TMA tiled) == K3 (streaming)
 
 @pytest.mark.parametrize("shape", [(40, 300), (131, 257), (64, 120), (24, 16), (300, 1000)])
@@ -744,16 +846,18 @@ def test_small_and_ragged_domains_all_kernels(ctx, shape):
         A, b = O.discretize(D, 0.1, 0.9, G if nphase == 3 else None)
         ref = O.sweeps(A, b, O.init_x(shape[1], shape[0], 0.1, 0.9), 75)
         out = {}
-        for kernel in (1, 0):
+        for kernel, resident in ((1, 0), (0, 0), (0, 1)):      # streaming; default (cluster-resident at these sizes); tiled
             ctx.set_kernel(kernel)
+            ctx.set_resident(resident)
             ctx.domain_load(img, nphase, p)
-            ctx.sweeps(75)                                     # 2 graph-free + remainder passes at depth 8
-            out[kernel] = ctx.get_field()
-        assert np.array_equal(out[0], out[1], equal_nan=True)
-        assert np.array_equal(np.isnan(out[0]), np.isnan(ref))
+            ctx.sweeps(75)                                     # tiled: whole passes at the default depth + a remainder pass
+            out[(kernel, resident)] = ctx.get_field()
+        assert np.array_equal(out[(0, 0)], out[(1, 0)], equal_nan=True) and np.array_equal(out[(0, 1)], out[(1, 0)], equal_nan=True)
+        assert np.array_equal(np.isnan(out[(0, 0)]), np.isnan(ref))
         if not np.all(np.isnan(ref)):
-            assert np.nanmax(np.abs(out[0] - ref)) < 1e-13
+            assert np.nanmax(np.abs(out[(0, 0)] - ref)) < 1e-13
     ctx.set_kernel(0)
+    ctx.set_resident(0)
 
 
 def test_graph_replay_long_runs_match_streaming(ctx):
@@ -762,6 +866,7 @@ def test_graph_replay_long_runs_match_streaming(ctx):
     img = blobs(123, (70, 90), levels=(0, 150, 255), fracs=(0.3, 0.4))
     p = E.default_params(Ds=0.0, Df=1.0, Dg=10.0)
     res = {}
+    ctx.set_resident(1)                                        # a 70 x 90 domain would otherwise run cluster-resident
     for kernel in (1, 0):
         ctx.set_kernel(kernel)
         ctx.domain_load(img, 3, p)
@@ -771,6 +876,7 @@ def test_graph_replay_long_runs_match_streaming(ctx):
         ctx.set_field(np.nan_to_num(ctx.get_field()) * 0.5)     # dead cells (A0 = 0) read back as NaN: do not inject them
         ctx.sweeps(300)
         res[kernel] = (ctx.get_field(), ctx.flux())
+    ctx.set_resident(0)
     assert np.array_equal(res[0][0], res[1][0], equal_nan=True) and res[0][1] == res[1][1]
     assert np.isfinite(res[0][1][0])
     ctx.set_kernel(0)
