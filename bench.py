@@ -492,7 +492,7 @@ def run_ours(args):
     sweep_ms = ctx.sweeps_timed(S) if not slab_mode else ms / args.steps
     # slab mode: the timed step also holds the halo exchanges; one sweep launch = `depth` sweeps over the local slab
     depth = args.tblock if args.kernel == 2 and args.tblock > 0 else ctx.default_depth
-    sweep_launches_per_step = (launches / args.steps) - 2 if not slab_mode else S / float(depth)
+    sweep_launches_per_step = (launches / args.steps) - 1 if not slab_mode else S / float(depth)   # - 1: the flux launch
     peak, peak_src = measured_peaks()
     local_cells = cells // world
     achieved = ALG_BYTES_PER_LUP * local_cells * S / (sweep_ms * 1e-3) / 1e9

@@ -22,7 +22,7 @@ class Params(C.Structure):
                 ("CL", C.c_double), ("CR", C.c_double),
                 ("max_iter", C.c_int64), ("tol", C.c_double),
                 ("mode", C.c_int), ("check_every", C.c_int),
-                ("omega", C.c_double), ("tblock", C.c_int),
+                ("omega", C.c_double), ("solver", C.c_int),
                 ("verbose", C.c_int), ("residual_tol", C.c_double), ("strict_reference", C.c_int)]
 
 
@@ -95,6 +95,7 @@ def lib():
         "deff2d_set_batch_slots": (i32, [vp, i32]),
         "deff2d_set_floodfill": (i32, [vp, i32]),
         "deff2d_set_graphs": (i32, [vp, i32]),
+        "deff2d_get_graphs": (i32, [vp]),
         "deff2d_kernel_launches": (i64, [vp]),
         "deff2d_stream": (vp, [vp]),
         "deff2d_domain_buffers": (i32, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)]),
@@ -102,6 +103,9 @@ def lib():
         "deff2d_nccl_init": (i32, [vp, c_ubyte_p, i32, i32]),
         "deff2d_slab_sweeps": (i32, [vp, i64]),
         "deff2d_slab_flux": (i32, [vp, c_double_p]),
+        "deff2d_slab_abort": (i32, [vp]),
+        "deff2d_domain_load_slab_global": (i32, [vp, c_ubyte_p, i32, i32, i32, C.POINTER(Params), i64, i64, i32]),
+        "deff2d_accumulate_fraction": (dbl, [i64, i64]),
         "deff2d_build_tables": (i32, [dbl, dbl, dbl, i64, i64, dbl, dbl, dbl, c_double_p, c_ubyte_p]),
         "deff2d_floodfill": (i32, [c_ubyte_p, i64, i64]),
         "deff2d_tile_geometry": (i32, [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),

@@ -21,7 +21,7 @@ def default_params(**overrides):
     """Shipped input.txt defaults (Deff2DGPU/input.txt:2-18) with keyword overrides.
 
     Accepts the struct field names (Ds, Df, Dg, amp_x, amp_y, CL, CR, max_iter, tol, mode,
-    check_every, omega, tblock, verbose)."""
+    check_every, omega, solver, verbose, residual_tol, strict_reference)."""
     p = Params()
     _lib.lib().deff2d_default_params(C.byref(p))
     for k, v in overrides.items():
@@ -225,6 +225,14 @@ class Deff2D:
         self._ck(self._L.deff2d_domain_load_slab(self._h, gray.ctypes.data_as(_lib.c_ubyte_p), W, int(own_src_rows),
                                                  int(nphase), C.byref(params), int(row0), int(ny_global),
                                                  int(halo_rows), pp))
+
+    def domain_load_slab_global(self, gray, nphase, params, row0, own_rows, halo_rows):
+        """This rank's slab from the WHOLE source image: device FloodFill over the whole domain, no host mask."""
+        gray = np.ascontiguousarray(gray, dtype=np.uint8)
+        H, W = gray.shape
+        self._keep = (gray,)
+        self._ck(self._L.deff2d_domain_load_slab_global(self._h, gray.ctypes.data_as(_lib.c_ubyte_p), W, H, int(nphase),
+                                                        C.byref(params), int(row0), int(own_rows), int(halo_rows)))
 
     def set_D(self, Ds, Df, Dg=0.0):
         self._ck(self._L.deff2d_domain_set_D(self._h, Ds, Df, Dg))

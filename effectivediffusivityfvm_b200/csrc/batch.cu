@@ -239,6 +239,9 @@ struct BatchState {
     DevBuf<BatchJob> jobs;
     DevBuf<int> active;
     DevBuf<uint32_t> tiles;
+    DevBuf<int> ff_flags;
+    int *h_ff_flags = nullptr;
+    size_t h_ff_flags_cap = 0;
     BatchSlot *h_slots = nullptr;
     BatchJob *h_jobs = nullptr;
     int *h_active = nullptr;
@@ -290,6 +293,8 @@ void batch_destroy(deff2d_ctx *c)
     if (b->jobs.p) cudaFree(b->jobs.p);
     if (b->active.p) cudaFree(b->active.p);
     if (b->tiles.p) cudaFree(b->tiles.p);
+    if (b->ff_flags.p) cudaFree(b->ff_flags.p);
+    if (b->h_ff_flags) cudaFreeHost(b->h_ff_flags);
     if (b->h_slots) cudaFreeHost(b->h_slots);
     if (b->h_jobs) cudaFreeHost(b->h_jobs);
     if (b->h_active) cudaFreeHost(b->h_active);
@@ -309,32 +314,20 @@ void batch_destroy(deff2d_ctx *c)
         }                                                                                    \
     } while (0)
 
-// The stage sequence of the reference drivers for one image (context.cu: solve_image_impl).
+// The stage sequence of the reference drivers for one image (host.cpp: stage_list) in the form k_batch_check reads.
 static int build_stages(const deff2d_params *p, BatchStages *st, double *stageD, int *nst)
 {
-    int n = 0;
-    auto add = [&](double Df, double Ds, double Dg, double tol, long long mi, int pre, double sd) {
-        if (n >= BATCH_MAX_STAGES) return false;
-        st->s[n].D[0] = Df; st->s[n].D[1] = Ds; st->s[n].D[2] = Dg;
-        st->s[n].tol = tol; st->s[n].max_iter = mi; st->s[n].precond = pre; st->s[n].pad = 0;
-        stageD[n] = sd;
-        n++;
-        return true;
-    };
-    if (p->mode == DEFF2D_MODE_2PH_BATCH) {
-        if (!add(p->Df, p->Ds, 0.0, p->tol, p->max_iter, 0, p->Df)) return 1;          // cuh:2004-2009
-    } else if (p->mode == DEFF2D_MODE_3PH) {
-        double DCG_Temp = 10;                                                         // cuh:1492
-        while (DCG_Temp < p->Dg) {                                                    // cuh:1504; tol*10, MAX_ITER 1e6: cuh:1501-1502
-            if (!add(p->Df, p->Ds, DCG_Temp, p->tol * 10, 1000000, 1, DCG_Temp)) return 1;
-            DCG_Temp = DCG_Temp * 10;                                                 // cuh:1547
-        }
-        if (!add(p->Df, p->Ds, p->Dg, p->tol, p->max_iter, 0, p->Dg)) return 1;       // cuh:1557-1591
-    } else {
-        return 1;
+    if (p->mode != DEFF2D_MODE_2PH_BATCH && p->mode != DEFF2D_MODE_3PH) return 1;
+    StageSpec spec[BATCH_MAX_STAGES];
+    const int n = stage_list(p, spec, BATCH_MAX_STAGES);
+    if (n < 1) return 1;
+    for (int k = 0; k < n; k++) {
+        st->s[k].D[0] = spec[k].Df; st->s[k].D[1] = spec[k].Ds; st->s[k].D[2] = spec[k].Dg;
+        st->s[k].tol = spec[k].tol; st->s[k].max_iter = spec[k].max_iter; st->s[k].precond = spec[k].precond; st->s[k].pad = 0;
+        stageD[k] = spec[k].stageD;
+        // the packed loop needs at least one sweep per stage (cuh:1232)
+        if (!(spec[k].tol < 100.0) || spec[k].max_iter < 1) return 1;
     }
-    for (int k = 0; k < n; k++)     // the packed loop needs at least one sweep per stage (cuh:1232)
-        if (!(st->s[k].tol < 100.0) || st->s[k].max_iter < 1) return 1;
     *nst = n;
     return 0;
 }
@@ -345,6 +338,7 @@ void batch_plan(int64_t Nx, int64_t Ny, int count, int limit, int *GX, int *GY)
 {
     int gx = (int)std::max<int64_t>(1, 4096 / (Nx + 1));
     int64_t max_slots = std::max<int64_t>(1, ((int64_t)48 << 20) / (Nx * Ny));
+    if (max_slots > 65535) max_slots = 65535;            // one k_batch_init launch covers every slot (gridDim.y)
     if (limit > 0 && limit < max_slots) max_slots = limit;
     int slots = (int)std::min<int64_t>(count, max_slots);
     if (gx > slots) gx = slots;
@@ -395,13 +389,15 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
                                                          // per-tile weight gather best at depth 6 (measured 424 / 436 / 452 / 422 GLUP/s at T = 4 / 5 / 6 / 8)
     if (const char *e = std::getenv("DEFF2D_BATCH_T")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) T = v; }   // tuning
 
-    // ---- FloodFill on host threads (cuh:557-713): PathFlag always, pinned mask in 3-phase -----------
+    // ---- FloodFill (cuh:557-713): PathFlag always, pinned mask in 3-phase.  On the device after the upload below
+    //      (all images of the chunk in the same launches, floodfill.cu); on host threads with deff2d_set_floodfill(ctx, 1)
     std::vector<int> pathflag((size_t)count, 0);
     std::vector<uint8_t> masks;
-    if (nphase == 3) masks.resize((size_t)count * cells);
-    {
-        const bool strict = p->strict_reference != 0;    // see domain_load_impl (context.cu)
-        const int thr = (nphase == 3) ? 200 : (strict ? 150 : 149);       // cuh:1368, cuh:1695
+    const bool strict = p->strict_reference != 0;        // see domain_load_impl (context.cu)
+    const int ff_thr = (nphase == 3) ? 200 : (strict ? 150 : 149);        // cuh:1368, cuh:1695
+    const bool ff_host = c->floodfill_mode == 1 || Nx < 2;
+    if (ff_host) {
+        if (nphase == 3) masks.resize((size_t)count * cells);
         std::atomic<int> next(0);
         const int nthreads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
         auto work = [&]() {
@@ -416,7 +412,7 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
                 for (int64_t i = 0; i < Ny; i++) {
                     const uint8_t *srow = src + (size_t)(i / p->amp_y) * W;
                     uint8_t *gr = g + (size_t)i * Nx;
-                    for (int64_t j = 0; j < Nx; j++) gr[j] = srow[j / p->amp_x] > thr;
+                    for (int64_t j = 0; j < Nx; j++) gr[j] = srow[j / p->amp_x] > ff_thr;
                 }
                 pathflag[(size_t)k] = floodfill(g, Nx, Ny, strict);
             }
@@ -462,10 +458,12 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     if ((rc = grow(c->x[0], stack_cells)) || (rc = grow(c->x[1], stack_cells)) || (rc = grow(c->code, stack_cells)) ||
         (rc = grow(c->idx16, stack_cells))) return rc;
     if ((rc = grow(c->img, npix * count))) return rc;
-    if (nphase == 3 && (rc = grow(c->grid, (size_t)cells * count))) return rc;
+    // FloodFill states: all images at once in 3-phase (they become the pinned masks); in 2-phase only PathFlag is
+    // needed, so the images go through a bounded scratch group by group
+    const int ff_group = (nphase == 3) ? count : (int)std::max<int64_t>(1, std::min<int64_t>(count, ((int64_t)256 << 20) / cells));
+    if ((nphase == 3 || !ff_host) && (rc = grow(c->grid, (size_t)cells * (nphase == 3 ? count : ff_group)))) return rc;
     if ((rc = grow(c->lut, (size_t)nstages * DEFF2D_LUT_ENTRIES * 4)) || (rc = grow(c->dead, (size_t)nstages * DEFF2D_LUT_ENTRIES)) ||
-        (rc = grow(c->clut, (size_t)nstages * DEFF2D_CLUT_ENTRIES * 4)) ||
-        (rc = grow(c->clut_aos, (size_t)nstages * DEFF2D_CLUT_ENTRIES * 4))) return rc;
+        (rc = grow(c->clut, (size_t)nstages * DEFF2D_CLUT_ENTRIES * 4))) return rc;
     c->lut_stages = nstages;
     if (fields && (rc = grow(c->dense, (size_t)cells))) return rc;
     if ((rc = dev_ensure(c, b->slots, (size_t)nslots)) || (rc = dev_ensure(c, b->outs, (size_t)count)) ||
@@ -480,18 +478,26 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     CUB(cudaMemsetAsync(b->slots.p, 0, (size_t)nslots * sizeof(BatchSlot), s));
     CUB(cudaMemsetAsync(b->outs.p, 0, (size_t)count * sizeof(BatchOut), s));
     CUB(cudaMemcpyAsync(c->img.p, gray, npix * count, cudaMemcpyHostToDevice, s));
-    if (nphase == 3) CUB(cudaMemcpyAsync(c->grid.p, masks.data(), (size_t)cells * count, cudaMemcpyHostToDevice, s));
+    if (nphase == 3 && ff_host) CUB(cudaMemcpyAsync(c->grid.p, masks.data(), (size_t)cells * count, cudaMemcpyHostToDevice, s));
+    if (!ff_host) {
+        const int per_call = std::min(ff_group, 32768);
+        if ((rc = dev_ensure(c, b->ff_flags, (size_t)per_call + 1)) || (rc = host_ensure(c, b->h_ff_flags, b->h_ff_flags_cap, (size_t)per_call + 1))) return rc;
+        for (int k0 = 0; k0 < count; k0 += per_call) {
+            const int nk = std::min(per_call, count - k0);
+            uint8_t *st = (nphase == 3) ? c->grid.p + (size_t)k0 * cells : c->grid.p;
+            if ((rc = floodfill_device_batch(c, c->img.p + (size_t)k0 * npix, W, H, p->amp_x, p->amp_y, ff_thr, st, Nx, Ny, nk,
+                                             b->ff_flags.p, b->h_ff_flags, pathflag.data() + k0, nullptr, strict))) return rc;
+        }
+    }
     {
         std::vector<double> lut((size_t)nstages * DEFF2D_LUT_ENTRIES * 4);
         std::vector<uint8_t> dead((size_t)nstages * DEFF2D_LUT_ENTRIES);
-        std::vector<double> clut((size_t)nstages * DEFF2D_CLUT_ENTRIES * 4), aos((size_t)nstages * DEFF2D_CLUT_ENTRIES * 4);
+        std::vector<double> clut((size_t)nstages * DEFF2D_CLUT_ENTRIES * 4);
         for (int k = 0; k < nstages; k++) {
             build_tables(stages.s[k].D, Nx, Ny, c->CL, c->CR, c->omega, lut.data() + (size_t)k * DEFF2D_LUT_ENTRIES * 4,
                          dead.data() + (size_t)k * DEFF2D_LUT_ENTRIES);
             compact_table(lut.data() + (size_t)k * DEFF2D_LUT_ENTRIES * 4, clut.data() + (size_t)k * DEFF2D_CLUT_ENTRIES * 4, nphase);
-            interleave_table(clut.data() + (size_t)k * DEFF2D_CLUT_ENTRIES * 4, aos.data() + (size_t)k * DEFF2D_CLUT_ENTRIES * 4);
         }
-        CUB(cudaMemcpyAsync(c->clut_aos.p, aos.data(), aos.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         CUB(cudaMemcpyAsync(c->clut.p, clut.data(), clut.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         CUB(cudaMemcpyAsync(c->lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         CUB(cudaMemcpyAsync(c->dead.p, dead.data(), dead.size(), cudaMemcpyHostToDevice, s));

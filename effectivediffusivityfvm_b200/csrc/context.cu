@@ -81,15 +81,11 @@ static int upload_tables(deff2d_ctx *c)
     int rc;
     std::vector<double> clut((size_t)DEFF2D_CLUT_ENTRIES * 4);
     compact_table(lut.data(), clut.data(), c->nphase);
-    std::vector<double> aos(clut.size());
-    interleave_table(clut.data(), aos.data());
     if ((rc = ensure(c, c->lut, lut.size()))) return rc;
     if ((rc = ensure(c, c->clut, clut.size()))) return rc;
-    if ((rc = ensure(c, c->clut_aos, aos.size()))) return rc;
     if ((rc = ensure(c, c->dead, dead.size()))) return rc;
     c->lut_stages = 1;
     CU(cudaMemcpyAsync(c->clut.p, clut.data(), clut.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(c->clut_aos.p, aos.data(), aos.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     // pageable source: the copy is staged before the call returns, the vectors may die
     CU(cudaMemcpyAsync(c->lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->dead.p, dead.data(), dead.size(), cudaMemcpyHostToDevice, c->stream));
@@ -162,12 +158,18 @@ int solve_loop(deff2d_ctx *c, double tol, int64_t max_iter, bool verbose_checks,
         if (rc) return rc;
         iter += n;
         if (last == next_check) {
-            launch_flux(c->stream, view(c), c->Dphase, c->CL, c->CR, c->NxG, c->own_first, c->own_rows, c->d_state);
-            c->launches++;
-            if ((rc = slab_allreduce_q(c))) return rc;
             // residual mode: the Deff-change test is switched off (tol -1 is never reached; NaN still stops)
-            launch_check(c->stream, c->d_state, c->NyG, c->CL, c->CR, c->residual_tol > 0 ? -1.0 : tol, last);
-            c->launches++;
+            const double tol_eff = c->residual_tol > 0 ? -1.0 : tol;
+            if (slab_is_distributed(c)) {
+                launch_flux(c->stream, view(c), c->Dphase, c->CL, c->CR, c->NxG, c->own_first, c->own_rows, c->d_state);
+                c->launches++;
+                if ((rc = slab_allreduce_q(c))) return rc;
+                launch_check(c->stream, c->d_state, c->NyG, c->CL, c->CR, tol_eff, last);
+                c->launches++;
+            } else {
+                launch_flux_check(c->stream, view(c), c->Dphase, c->CL, c->CR, c->NxG, c->NyG, c->own_first, c->own_rows, tol_eff, last, c->d_state);
+                c->launches++;
+            }
             if ((rc = read_state(c))) return rc;
             if (c->residual_tol > 0 && !c->h_state->stop) {
                 CU(cudaMemsetAsync(c->d_scalar, 0, sizeof(double), c->stream));
@@ -192,7 +194,7 @@ int solve_loop(deff2d_ctx *c, double tol, int64_t max_iter, bool verbose_checks,
 static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc, int nphase,
                             const deff2d_params *p, int64_t grow0, int64_t img_row0, int64_t NyLocal,
                             int64_t NyG, int64_t own_first, int64_t own_rows, const uint8_t *grid_host,
-                            bool run_floodfill)
+                            bool run_floodfill, bool global_image = false)
 {
     if (!gray || W < 1 || Hsrc < 1 || !p || (nphase != 2 && nphase != 3) || p->amp_x < 1 || p->amp_y < 1) {
         set_error(c, "domain_load: invalid argument");
@@ -238,11 +240,22 @@ static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc,
     const int ff_thr = (nphase == 3) ? 200 : (strict ? 150 : 149);
     const bool ff_device = run_floodfill && Nx >= 2 &&
                            (c->floodfill_mode == 2 || (c->floodfill_mode == 0 && Nx * Ny >= ((int64_t)1 << 16)));
-    if (ff_device) {
+    if (global_image) {
+        // slab of a decomposed domain, `gray` is the whole global image: the flood needs global connectivity, so every
+        // rank floods the whole domain on its own GPU (replicas) and keeps the mask rows of its slab --
+        // no host flood, no 1 B/cell mask upload, the same steps as an undecomposed load
+        if ((rc = ensure(c, c->grid, (size_t)Nx * NyG))) return rc;
+        int pf = 0;
+        if ((rc = floodfill_device(c, c->img.p, W, Hsrc, p->amp_x, p->amp_y, ff_thr, c->grid.p, Nx, NyG,
+                                   reinterpret_cast<int *>(c->d_scalar), reinterpret_cast<int *>(c->h_scalar), &pf,
+                                   &c->floodfill_passes, strict))) return rc;
+        c->pathflag = pf;
+        if (nphase == 3) grid_dev = c->grid.p + (size_t)grow0 * Nx;
+    } else if (ff_device) {
         // label propagation on the device (floodfill.cu): same reachability, no 1 B/cell mask upload
         if ((rc = ensure(c, c->grid, (size_t)Nx * Ny))) return rc;
         int pf = 0;
-        if ((rc = floodfill_device(c, c->img.p, W, p->amp_x, p->amp_y, ff_thr, c->grid.p, Nx, Ny,
+        if ((rc = floodfill_device(c, c->img.p, W, Hsrc, p->amp_x, p->amp_y, ff_thr, c->grid.p, Nx, Ny,
                                    reinterpret_cast<int *>(c->d_scalar), reinterpret_cast<int *>(c->h_scalar), &pf,
                                    &c->floodfill_passes, strict))) return rc;
         c->pathflag = pf;
@@ -366,49 +379,31 @@ int solve_image_impl(deff2d_ctx *c, const uint8_t *gray, int W, int H, const def
     }
     cudaMemsetAsync(&c->d_state->conv, 0, sizeof(double), c->stream);
 
-    if (p->mode == DEFF2D_MODE_2PH_BATCH) {
-        const double DCF = p->Df;
-        if ((rc = run_stage(c, p, res, p->Ds, DCF, 0.0, DCF, p->tol, p->max_iter, false, p->Df))) return rc;
-        res->deff = res->deff_raw / DCF;                       // cuh:2017
-        res->last_df = DCF;
-        if (p->verbose == 1)                                    // cuh:2020
-            std::cout << "Number" << image_number << "DCF = " << DCF << ", Deff " << res->deff << std::endl;
-    } else if (p->mode == DEFF2D_MODE_2PH_SINGLE) {
-        const double DCF_Max = p->Df;
-        double DCF = 10.0;                                      // cuh:1714
-        int count = 1;
-        res->last_df = p->Df;
-        if (DCF > DCF_Max && p->strict_reference == 0) {        // defined behaviour for quirk Q8: one stage at Df
-            if ((rc = run_stage(c, p, res, p->Ds, DCF_Max, 0.0, DCF_Max, p->tol, p->max_iter, false, p->Df))) return rc;
-            res->deff = res->deff_raw / DCF_Max;
-            res->last_df = DCF_Max;
+    // the stage sequence of the driver (host.cpp: stage_list -- shared with the packed batch and the multi-GPU driver)
+    StageSpec stages[DEFF2D_MAX_STAGES];
+    const int nst = stage_list(p, stages, DEFF2D_MAX_STAGES);
+    if (nst < 0) { set_error(c, "solve_image: more than %d continuation stages", DEFF2D_MAX_STAGES); return DEFF2D_ERR_ARG; }
+    res->last_df = p->Df;
+    for (int k = 0; k < nst; k++) {
+        const StageSpec &st = stages[k];
+        if (p->mode == DEFF2D_MODE_3PH) {
+            if (st.precond) {
+                if (p->verbose == 1) std::printf("Pre-Cond Stage %d: DCG = %1.3e\n", k + 1, st.Dg);
+            } else {
+                c->Dphase[0] = p->Df; c->Dphase[1] = p->Ds; c->Dphase[2] = p->Dg;
+                fracts3(c, p->Ds, p->Df, &res->SVF, &res->LVF);     // cuh:1582
+            }
         }
-        while (DCF <= DCF_Max) {                                // cuh:1761 (no stage when Df < 10, quirk Q8)
-            DCF = std::pow(100, count);                         // cuh:1762
-            if (DCF >= DCF_Max) DCF = DCF_Max;
-            if ((rc = run_stage(c, p, res, p->Ds, DCF, 0.0, DCF, p->tol, p->max_iter, false, p->Df))) return rc;
-            res->deff = res->deff_raw / DCF;                    // cuh:1802
-            res->last_df = DCF;
-            if (p->verbose == 1) std::cout << "DCF = " << DCF << ", Deff " << res->deff << std::endl;   // cuh:1807
-            if (DCF == DCF_Max) break;                          // cuh:1812
-            count++;
+        if ((rc = run_stage(c, p, res, st.Ds, st.Df, st.Dg, st.stageD, st.tol, st.max_iter, st.precond != 0, p->Df))) return rc;
+        if (st.precond) continue;
+        res->deff = res->deff_raw / st.Df;                          // cuh:1802, cuh:2017, cuh:1601
+        res->last_df = st.Df;
+        if (p->verbose == 1) {
+            if (p->mode == DEFF2D_MODE_2PH_BATCH)                   // cuh:2020
+                std::cout << "Number" << image_number << "DCF = " << st.Df << ", Deff " << res->deff << std::endl;
+            else if (!st.defined_q8)                                // cuh:1807, cuh:1607
+                std::cout << "DCF = " << st.Df << ", Deff " << res->deff << std::endl;
         }
-    } else {
-        double DCG_Temp = 10;                                   // cuh:1492
-        int stage = 1;
-        while (DCG_Temp < p->Dg) {                              // cuh:1504; tol*10, MAX_ITER 1e6: cuh:1501-1502
-            if (p->verbose == 1) std::printf("Pre-Cond Stage %d: DCG = %1.3e\n", stage, DCG_Temp);
-            if ((rc = run_stage(c, p, res, p->Ds, p->Df, DCG_Temp, DCG_Temp, p->tol * 10, 1000000, true, p->Df)))
-                return rc;
-            DCG_Temp = DCG_Temp * 10;                           // cuh:1547
-            stage++;
-        }
-        c->Dphase[0] = p->Df; c->Dphase[1] = p->Ds; c->Dphase[2] = p->Dg;
-        fracts3(c, p->Ds, p->Df, &res->SVF, &res->LVF);         // cuh:1582
-        if ((rc = run_stage(c, p, res, p->Ds, p->Df, p->Dg, p->Dg, p->tol, p->max_iter, false, p->Df))) return rc;
-        res->deff = res->deff_raw / p->Df;                      // cuh:1601
-        res->last_df = p->Df;
-        if (p->verbose == 1) std::cout << "DCF = " << p->Df << ", Deff " << res->deff << std::endl;   // cuh:1607
     }
     if (field) {
         rc = deff2d_domain_get_field(c, field);
@@ -486,7 +481,6 @@ DEFF2D_EXPORT void deff2d_destroy(deff2d_ctx *c)
     if (c->grid.p) cudaFree(c->grid.p);
     if (c->lut.p) cudaFree(c->lut.p);
     if (c->clut.p) cudaFree(c->clut.p);
-    if (c->clut_aos.p) cudaFree(c->clut_aos.p);
     if (c->dead.p) cudaFree(c->dead.p);
     if (c->dense.p) cudaFree(c->dense.p);
     if (c->dense8.p) cudaFree(c->dense8.p);
@@ -555,6 +549,10 @@ DEFF2D_EXPORT int deff2d_domain_load_slab(deff2d_ctx *c, const uint8_t *gray, in
     const int64_t above = std::min<int64_t>(halo_rows, row0);
     const int64_t below = std::min<int64_t>(halo_rows, NyGlobal - (row0 + own_rows));
     if (below < 0) { set_error(c, "slab exceeds the global domain"); return DEFF2D_ERR_ARG; }
+    if ((row0 > 0 && above != halo_rows) || (row0 + own_rows < NyGlobal && below != halo_rows)) {
+        set_error(c, "slab: a neighbouring slab is thinner than the %d halo rows", halo_rows);   // the exchange moves whole halo blocks
+        return DEFF2D_ERR_ARG;
+    }
     const int64_t NyLocal = above + own_rows + below;
     const int Hsrc = (int)(NyLocal / p->amp_y);
     c->halo_above = above; c->halo_below = below; c->grow0 = row0 - above;
@@ -562,6 +560,29 @@ DEFF2D_EXPORT int deff2d_domain_load_slab(deff2d_ctx *c, const uint8_t *gray, in
     c->halo_valid = std::max(above, below);                  // x0 is exact everywhere
     return domain_load_impl(c, gray, W, Hsrc, nphase, p, row0 - above, (row0 - above) / p->amp_y, NyLocal,
                             NyGlobal, above, own_rows, pinned, false);
+}
+
+DEFF2D_EXPORT int deff2d_domain_load_slab_global(deff2d_ctx *c, const uint8_t *gray, int W, int H, int nphase,
+                                                 const deff2d_params *p, int64_t row0, int64_t own_rows, int halo_rows)
+{
+    if (!c || !p || !gray || W < 1 || H < 1 || p->amp_x < 1 || p->amp_y < 1) return DEFF2D_ERR_ARG;
+    const int64_t NyGlobal = (int64_t)H * p->amp_y;
+    if (row0 < 0 || own_rows < 1 || row0 + own_rows > NyGlobal || halo_rows < 0) {
+        set_error(c, "slab rows [%lld, %lld) outside the global domain of %lld rows", (long long)row0, (long long)(row0 + own_rows), (long long)NyGlobal);
+        return DEFF2D_ERR_ARG;
+    }
+    const int64_t above = std::min<int64_t>(halo_rows, row0);
+    const int64_t below = std::min<int64_t>(halo_rows, NyGlobal - (row0 + own_rows));
+    if ((row0 > 0 && above != halo_rows) || (row0 + own_rows < NyGlobal && below != halo_rows)) {
+        set_error(c, "slab: a neighbouring slab is thinner than the %d halo rows", halo_rows);   // the exchange moves whole halo blocks
+        return DEFF2D_ERR_ARG;
+    }
+    c->halo_above = above; c->halo_below = below; c->grow0 = row0 - above;
+    c->slab_domain = true;
+    c->halo_valid = std::max(above, below);                  // x0 is exact everywhere
+    // the device holds the whole source image (1 B per pixel); rows are addressed globally (img_row0 = 0)
+    return domain_load_impl(c, gray, W, H, nphase, p, row0 - above, 0, above + own_rows + below, NyGlobal, above, own_rows,
+                            nullptr, false, true);
 }
 
 DEFF2D_EXPORT int deff2d_domain_set_D(deff2d_ctx *c, double Ds, double Df, double Dg)
@@ -735,6 +756,8 @@ DEFF2D_EXPORT int deff2d_set_graphs(deff2d_ctx *c, int enable)
     c->use_graphs = enable != 0;
     return DEFF2D_OK;
 }
+
+DEFF2D_EXPORT int deff2d_get_graphs(const deff2d_ctx *c) { return (c && c->use_graphs) ? 1 : 0; }
 
 DEFF2D_EXPORT int deff2d_set_floodfill(deff2d_ctx *c, int mode)
 {

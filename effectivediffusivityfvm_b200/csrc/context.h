@@ -43,7 +43,6 @@ struct deff2d_ctx {
     DevBuf<uint16_t> idx16;          // per-cell weight-table index derived from `code` (k_build_idx), read by the tiled sweep
     DevBuf<double> lut, dense;
     DevBuf<double> clut;             // compact per-stage weight tables of the tiled sweep (tables.cpp: compact_table), four planes
-    DevBuf<double> clut_aos;         // the same entries as [slot][4] (two 16-byte loads per cell)
     int lut_stages = 1;              // stages resident in lut / clut (packed batches: all stages of the mode)
     std::vector<uint8_t> h_grid;
 
@@ -55,7 +54,7 @@ struct deff2d_ctx {
     int kernel = 0;                  // 0 default, 1 simple, 2 TMA tiled
     int tblock = 1;
     int tile_family = 0;             // sweep_tma.cu thread layout: 3 = 4 x 4 patches, 4 = 2 x 8 patches, else the default
-    int k2_variant = 0;              // sweep_tma.cu: bit 0 [slot][4] weight table, bit 1 split-phase sweep barrier
+    int k2_variant = 0;              // sweep_tma.cu: bit 0 selects the row-major 16-byte N / S exchange (tuning)
     int k2_default_family = DEFF2D_DEFAULT_TILE_FAMILY;
     int k2_default_depth = DEFF2D_DEFAULT_DEPTH;   // sweeps per HBM pass of kernel 0
     int64_t launches = 0;
@@ -107,6 +106,7 @@ void tma_destroy(deff2d_ctx *c);
 
 // slab.cu
 int slab_allreduce_q(deff2d_ctx *c);     // no-op unless the resident domain is a slab of a multi-rank group
+bool slab_is_distributed(const deff2d_ctx *c);   // the resident domain is one slab of a group of >= 2 ranks
 int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n);
 void slab_destroy(deff2d_ctx *c);
 void batch_destroy(deff2d_ctx *c);
@@ -117,8 +117,12 @@ int resident_sweeps(deff2d_ctx *c, int64_t n, int64_t Nx, int64_t Ny, int GX, co
 void resident_destroy(deff2d_ctx *c);
 
 // floodfill.cu: FloodFill (cuh:557-713) by label propagation on the device; blocks
-int floodfill_device(deff2d_ctx *c, const uint8_t *img, int W, int amp_x, int amp_y, int thr, uint8_t *st, int64_t Nx,
+int floodfill_device(deff2d_ctx *c, const uint8_t *img, int W, int Hsrc, int amp_x, int amp_y, int thr, uint8_t *st, int64_t Nx,
                      int64_t Ny, int *d_flags, int *h_flags, int *pathflag, int *passes, bool reference_quirk);
+// the same for `count` images of a packed batch in the same launches (flags: int[1 + count])
+int floodfill_device_batch(deff2d_ctx *c, const uint8_t *img, int W, int Hsrc, int amp_x, int amp_y, int thr, uint8_t *st,
+                           int64_t Nx, int64_t Ny, int count, int *d_flags, int *h_flags, int *pathflags, int *passes,
+                           bool reference_quirk);
 
 // batch.cu: returns 1 when the resident small-image kernel does not cover the request
 int batch_resident_solve(deff2d_ctx *c, const uint8_t *gray, int count, int W, int H,

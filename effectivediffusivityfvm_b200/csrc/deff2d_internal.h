@@ -49,8 +49,21 @@ DEFF2D_HD inline unsigned clut_slot(unsigned p, unsigned w, unsigned e, unsigned
     return 243u + p * 256u + (w | (e << 2) | (s << 4) | (n << 6));
 }
 void compact_table(const double *lut, double *clut, int nphase);
-// planar compact table (4 x DEFF2D_CLUT_ENTRIES) -> [slot][4]
-void interleave_table(const double *clut, double *aos);
+
+// One continuation stage of the reference drivers: the coefficients it solves with, its stop rule, and whether it is
+// a JacobiGPUPreCond stage (its Deff and time are not reported, cuh:1144-1159 vs cuh:1309-1311).
+struct StageSpec {
+    double Ds, Df, Dg;
+    double stageD;          // the value the stage is named by (DCF of a 2-phase stage, DCG of a 3-phase one)
+    double tol;
+    int64_t max_iter;
+    int precond;
+    int defined_q8;         // the extra stage of strict_reference = 0 for quirk Q8 (2-phase single with Df < 10)
+};
+// The stage sequence of one image for p->mode: SingleSim (cuh:1714, 1759-1817), the BatchSim body (cuh:2004-2017),
+// SingleSim3Phase / BatchSim3Phase (cuh:1492-1597).  Returns the number of stages (0: no solve at all, quirk Q8),
+// -1 if there are more than `cap`.  The one place this sequence is written down.
+int stage_list(const deff2d_params *p, StageSpec *out, int cap);
 
 // FloodFill (cuh:557-713) on a byte grid; returns PathFlag.
 // reference_quirk: keep the right-column seeding of cuh:601 (quirk Q11); false = flood from the left column only

@@ -30,11 +30,14 @@ namespace deff2d {
 
 __device__ __forceinline__ bool ff_reached(unsigned v) { return v == 0u || v == 3u; }
 
+// blockIdx.y: image of a packed batch (source images W x Hsrc apart, states Nx * Ny apart)
 __global__ void __launch_bounds__(256)
-k_ff_init(const uint8_t *__restrict__ img, int W, int amp_x, int amp_y, int thr, uint8_t *__restrict__ st,
+k_ff_init(const uint8_t *__restrict__ img, int W, int Hsrc, int amp_x, int amp_y, int thr, uint8_t *__restrict__ st,
           long long Nx, long long Ny, int reference_quirk)
 {
     const long long n = Nx * Ny;
+    img += (size_t)blockIdx.y * W * Hsrc;
+    st += (size_t)blockIdx.y * n;
     // cuh:601 tests Domain[0]: the quirk is on while cell (0,0) is solid
     const bool quirk = reference_quirk && img[0] > thr;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
@@ -47,9 +50,11 @@ k_ff_init(const uint8_t *__restrict__ img, int W, int amp_x, int amp_y, int thr,
     }
 }
 
+// blockIdx.z: image of a packed batch
 __global__ void __launch_bounds__(256)
 k_ff_tile(uint8_t *st, long long Nx, long long Ny, int *changed)
 {
+    st += (size_t)blockIdx.z * Nx * Ny;
     __shared__ uint8_t s[(FF_TH + 2) * FF_PITCH];
     __shared__ int any_work, blk_changed, iter_changed;
     const long long x0 = (long long)blockIdx.x * FF_TW, y0 = (long long)blockIdx.y * FF_TH;
@@ -137,10 +142,13 @@ k_ff_tile(uint8_t *st, long long Nx, long long Ny, int *changed)
     }
 }
 
+// blockIdx.y: image of a packed batch (one PathFlag per image)
 __global__ void __launch_bounds__(256)
 k_ff_finish(uint8_t *st, long long Nx, long long Ny, int *pathflag)
 {
     const long long n = Nx * Ny;
+    st += (size_t)blockIdx.y * n;
+    pathflag += blockIdx.y;
     int pf = 0;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
         const unsigned v = st[k];
@@ -152,17 +160,21 @@ k_ff_finish(uint8_t *st, long long Nx, long long Ny, int *pathflag)
     if (__any_sync(0xffffffffu, pf) && (threadIdx.x & 31) == 0) atomicOr(pathflag, 1);
 }
 
-// FloodFill of the amplified solid mask of `img` (device, W x Hsrc) into `st` (device, Nx * Ny
-// bytes: 0 reached, 1 solid, 2 unreached open).  flags: device int[2] scratch.  Blocks.
-int floodfill_device(deff2d_ctx *c, const uint8_t *img, int W, int amp_x, int amp_y, int thr, uint8_t *st, int64_t Nx,
-                     int64_t Ny, int *d_flags, int *h_flags, int *pathflag, int *passes, bool reference_quirk)
+// FloodFill of the amplified solid masks of `count` images (device, W x Hsrc each, back to back) into `st` (device,
+// Nx * Ny bytes per image: 0 reached, 1 solid, 2 unreached open).  d_flags: device int[1 + count] scratch (changed
+// flag, then one PathFlag per image); h_flags: pinned host int[1 + count].  pathflags[k] = PathFlag of image k.  Blocks.
+int floodfill_device_batch(deff2d_ctx *c, const uint8_t *img, int W, int Hsrc, int amp_x, int amp_y, int thr, uint8_t *st,
+                           int64_t Nx, int64_t Ny, int count, int *d_flags, int *h_flags, int *pathflags, int *passes,
+                           bool reference_quirk)
 {
     cudaStream_t s = c->stream;
     const long long n = Nx * Ny;
-    int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 16);
-    k_ff_init<<<blocks, 256, 0, s>>>(img, W, amp_x, amp_y, thr, st, Nx, Ny, reference_quirk ? 1 : 0);
+    if (count < 1) return DEFF2D_OK;
+    if (count > 65535) { set_error(c, "device FloodFill: at most 65535 images per call"); return DEFF2D_ERR_ARG; }
+    int blocks = (int)std::min<long long>((n + 255) / 256, count > 1 ? 64 : 148 * 16);
+    k_ff_init<<<dim3((unsigned)blocks, (unsigned)count), 256, 0, s>>>(img, W, Hsrc, amp_x, amp_y, thr, st, Nx, Ny, reference_quirk ? 1 : 0);
     c->launches++;
-    dim3 grid((unsigned)((Nx + FF_TW - 1) / FF_TW), (unsigned)((Ny + FF_TH - 1) / FF_TH));
+    dim3 grid((unsigned)((Nx + FF_TW - 1) / FF_TW), (unsigned)((Ny + FF_TH - 1) / FF_TH), (unsigned)count);
     int total = 0;
     const int burst = 4;                                      // passes per host round trip
     for (;;) {
@@ -176,15 +188,22 @@ int floodfill_device(deff2d_ctx *c, const uint8_t *img, int W, int amp_x, int am
         if (!h_flags[0]) break;
         if (total > 1000000) { set_error(c, "device FloodFill did not converge"); return DEFF2D_ERR_STATE; }
     }
-    cudaMemsetAsync(d_flags + 1, 0, sizeof(int), s);
-    k_ff_finish<<<blocks, 256, 0, s>>>(st, Nx, Ny, d_flags + 1);
+    cudaMemsetAsync(d_flags + 1, 0, sizeof(int) * (size_t)count, s);
+    k_ff_finish<<<dim3((unsigned)blocks, (unsigned)count), 256, 0, s>>>(st, Nx, Ny, d_flags + 1);
     c->launches++;
-    cudaMemcpyAsync(h_flags, d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(h_flags, d_flags, (1 + (size_t)count) * sizeof(int), cudaMemcpyDeviceToHost, s);
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { set_error(c, "device FloodFill failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
-    *pathflag = h_flags[1] ? 1 : 0;
+    for (int k = 0; k < count; k++) pathflags[k] = h_flags[1 + k] ? 1 : 0;
     if (passes) *passes = total;
     return DEFF2D_OK;
+}
+
+// One image: see floodfill_device_batch.  flags: device / pinned host int[2] scratch.
+int floodfill_device(deff2d_ctx *c, const uint8_t *img, int W, int Hsrc, int amp_x, int amp_y, int thr, uint8_t *st, int64_t Nx,
+                     int64_t Ny, int *d_flags, int *h_flags, int *pathflag, int *passes, bool reference_quirk)
+{
+    return floodfill_device_batch(c, img, W, Hsrc, amp_x, amp_y, thr, st, Nx, Ny, 1, d_flags, h_flags, pathflag, passes, reference_quirk);
 }
 
 }  // namespace deff2d

@@ -3,6 +3,7 @@
 #include "deff2d_internal.h"
 
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -57,13 +58,77 @@ int floodfill(uint8_t *grid, int64_t Nx, int64_t Ny, bool reference_quirk)
 }
 
 // cuh:402 / cuh:437: the reference accumulates fractions as `+= 1.0/total` per cell, so
-// e.g. 0.3 prints as 0.299999999999983.  Reproduce the rounding, not the closed form.
+// e.g. 0.3 prints as 0.299999999999983.  Reproduce the rounding, not the closed form -- but not by
+// looping over 268 M cells: while the running sum stays inside one binade every addition adds the
+// same multiple of that binade's ulp (the increment rounded to the ulp grid), so whole binades are
+// jumped in one step and only the additions that cross a power of two (and the first few, where
+// ties occur) are performed for real.  Bit-identical to the loop (tests/test_host_logic.py).
 double accumulate_fraction(int64_t count, int64_t total)
 {
     const double inc = 1.0 / (double)total;
     double s = 0;
-    for (int64_t k = 0; k < count; k++) s += inc;
+    int64_t left = count;
+    for (int k = 0; k < 64 && left > 0; k++, left--) s += inc;      // small sums: ties and exact additions, done literally
+    if (left <= 0) return s;
+    int ei = 0;
+    const double mi = std::frexp(inc, &ei);                           // inc = mi * 2^ei, 0.5 <= mi < 1
+    const uint64_t M = (uint64_t)std::ldexp(mi, 53);                  // 53-bit integer mantissa: inc = M * 2^(ei - 53)
+    const int einc = ei - 53;
+    while (left > 0) {
+        int es = 0;
+        const double ms = std::frexp(s, &es);
+        const int eu = es - 53;                                       // ulp(s) = 2^eu while s stays in [2^(es-1), 2^es)
+        const int sh = eu - einc;
+        if (sh <= 0 || sh >= 63) { s += inc; left--; continue; }      // exact additions (or inc below half an ulp): literal
+        const uint64_t q = M >> sh, r = M & ((1ull << sh) - 1), half = 1ull << (sh - 1);
+        if (r == half) { s += inc; left--; continue; }                // a tie in this binade: round-half-even, literal
+        const uint64_t d = q + (r > half ? 1 : 0);                    // every addition moves the sum by d ulps
+        if (d == 0) return s;                                         // the increment no longer registers
+        const uint64_t m = (uint64_t)std::ldexp(ms, 53);              // s = m * 2^eu, 2^52 <= m < 2^53
+        const uint64_t room = ((1ull << 53) - 1 - m) / d;             // additions that stay below 2^es
+        const uint64_t n = std::min<uint64_t>(room, (uint64_t)left);
+        if (n > 0) { s = std::ldexp((double)(m + n * d), eu); left -= (int64_t)n; }
+        if (left > 0) { s += inc; left--; }                           // the addition that crosses into the next binade
+    }
     return s;
+}
+
+int stage_list(const deff2d_params *p, StageSpec *out, int cap)
+{
+    int n = 0;
+    auto add = [&](double Ds, double Df, double Dg, double sd, double tol, int64_t mi, int pre, int q8) {
+        if (n >= cap) return false;
+        out[n].Ds = Ds; out[n].Df = Df; out[n].Dg = Dg; out[n].stageD = sd; out[n].tol = tol; out[n].max_iter = mi;
+        out[n].precond = pre; out[n].defined_q8 = q8;
+        n++;
+        return true;
+    };
+    if (p->mode == DEFF2D_MODE_2PH_BATCH) {
+        if (!add(p->Ds, p->Df, 0.0, p->Df, p->tol, p->max_iter, 0, 0)) return -1;              // cuh:2004-2017
+    } else if (p->mode == DEFF2D_MODE_2PH_SINGLE) {
+        const double DCF_Max = p->Df;
+        double DCF = 10.0;                                                                       // cuh:1714
+        int count = 1;
+        if (DCF > DCF_Max && p->strict_reference == 0)                                           // defined behaviour for quirk Q8
+            if (!add(p->Ds, DCF_Max, 0.0, DCF_Max, p->tol, p->max_iter, 0, 1)) return -1;
+        while (DCF <= DCF_Max) {                                                                 // cuh:1761 (no stage when Df < 10, quirk Q8)
+            DCF = std::pow(100, count);                                                          // cuh:1762
+            if (DCF >= DCF_Max) DCF = DCF_Max;
+            if (!add(p->Ds, DCF, 0.0, DCF, p->tol, p->max_iter, 0, 0)) return -1;
+            if (DCF == DCF_Max) break;                                                           // cuh:1812
+            count++;
+        }
+    } else if (p->mode == DEFF2D_MODE_3PH) {
+        double DCG_Temp = 10;                                                                    // cuh:1492
+        while (DCG_Temp < p->Dg) {                                                               // cuh:1504; tol*10, MAX_ITER 1e6: cuh:1501-1502
+            if (!add(p->Ds, p->Df, DCG_Temp, DCG_Temp, p->tol * 10, 1000000, 1, 0)) return -1;
+            DCG_Temp = DCG_Temp * 10;                                                            // cuh:1547
+        }
+        if (!add(p->Ds, p->Df, p->Dg, p->Dg, p->tol, p->max_iter, 0, 0)) return -1;              // cuh:1557-1591
+    } else {
+        return -1;
+    }
+    return n;
 }
 
 }  // namespace deff2d
@@ -78,6 +143,12 @@ DEFF2D_EXPORT int deff2d_version(void) { return DEFF2D_VERSION; }
 
 DEFF2D_EXPORT void deff2d_free(void *p) { std::free(p); }
 
+DEFF2D_EXPORT double deff2d_accumulate_fraction(int64_t count, int64_t total)
+{
+    if (count < 0 || total < 1) return 0.0;
+    return deff2d::accumulate_fraction(count, total);
+}
+
 DEFF2D_EXPORT void deff2d_default_params(deff2d_params *p)
 {
     // Deff2DGPU/input.txt:2-18
@@ -90,7 +161,7 @@ DEFF2D_EXPORT void deff2d_default_params(deff2d_params *p)
     p->mode = DEFF2D_MODE_3PH;
     p->check_every = 10000;
     p->omega = 2.0 / 3.0;
-    p->tblock = 0;
+    p->solver = 0;
     p->verbose = 0;
     p->residual_tol = 0;
     p->strict_reference = 1;

@@ -260,9 +260,29 @@ void launch_sweep_simple(cudaStream_t s, const DomainView &d, const int *stop)
 // partials are combined in a fixed order, so the result is deterministic.
 // ------------------------------------------------------------------------------------------
 struct FluxParams { double D[3]; double CL, CR, half_dx; };
+// fused stop rule (single-GPU domains): cuh:1263-1276 and the loop condition of cuh:1232 right behind the flux sums
+struct CheckParams { int enable; double two_ny, tol; long long iter_index; };
+
+__device__ __forceinline__ void apply_check(SolveState *st, double two_ny, double CL, double CR, double tol, long long iter_index)
+{
+    if (st->stop) return;
+    const double qAvg = (st->q[0] + st->q[1]) / two_ny;          // cuh:1263
+    const double deffNew = qAvg / (CR - CL);                     // cuh:1264
+    const double change = (st->deff_old - deffNew) / (st->deff_old);   // cuh:1265
+    st->deff_new = deffNew;
+    st->change = change;
+    st->conv = change;                                           // cuh:1275
+    st->deff_old = deffNew;                                      // cuh:1273
+    if (st->nchecks < 256) st->trace[st->nchecks] = deffNew;
+    st->nchecks++;
+    if (!(tol < fabs(change))) {                                 // cuh:1232 (NaN ends the loop)
+        st->stop = 1;
+        st->stop_iter = iter_index + 1;                          // iterCount after the increment of cuh:1289
+    }
+}
 
 __global__ void __launch_bounds__(1024)
-k_flux(DomainView d, FluxParams fp, long long row_first, long long nrows, SolveState *st)
+k_flux(DomainView d, FluxParams fp, CheckParams ck, long long row_first, long long nrows, SolveState *st)
 {
     __shared__ double s1[32], s2[32];
     double q1 = 0, q2 = 0;
@@ -292,37 +312,42 @@ k_flux(DomainView d, FluxParams fp, long long row_first, long long nrows, SolveS
         q2 = lane < nw ? s2[lane] : 0.0;
         q1 = warp_sum(q1);
         q2 = warp_sum(q2);
-        if (lane == 0) { st->q[0] = q1; st->q[1] = q2; }
+        if (lane == 0) {
+            st->q[0] = q1; st->q[1] = q2;
+            if (ck.enable) apply_check(st, ck.two_ny, fp.CL, fp.CR, ck.tol, ck.iter_index);
+        }
     }
 }
 
-void launch_flux(cudaStream_t s, const DomainView &d, const double Dphase[3], double CL, double CR,
-                 int64_t NxG, int64_t row_first, int64_t nrows, SolveState *st)
+static FluxParams flux_params(const double Dphase[3], double CL, double CR, int64_t NxG)
 {
     FluxParams fp;
     fp.D[0] = Dphase[0]; fp.D[1] = Dphase[1]; fp.D[2] = Dphase[2];
     fp.CL = CL; fp.CR = CR;
     fp.half_dx = (1.0 / (double)NxG) / 2.0;      // dx / 2.0, cuh:1256
-    k_flux<<<1, 1024, 0, s>>>(d, fp, row_first, nrows, st);
+    return fp;
 }
 
-// cuh:1263-1276 and the loop condition of cuh:1232
+void launch_flux(cudaStream_t s, const DomainView &d, const double Dphase[3], double CL, double CR,
+                 int64_t NxG, int64_t row_first, int64_t nrows, SolveState *st)
+{
+    CheckParams ck = {0, 0.0, 0.0, 0};
+    k_flux<<<1, 1024, 0, s>>>(d, flux_params(Dphase, CL, CR, NxG), ck, row_first, nrows, st);
+}
+
+// K4 fused: boundary flux, Deff, signed change and the stop flag in one launch (single-GPU domains; a decomposed
+// domain needs the all-reduce of {Q1, Q2} between the two halves and uses launch_flux + launch_check)
+void launch_flux_check(cudaStream_t s, const DomainView &d, const double Dphase[3], double CL, double CR, int64_t NxG,
+                       int64_t NyG, int64_t row_first, int64_t nrows, double tol, long long iter_index, SolveState *st)
+{
+    CheckParams ck = {1, 2.0 * (double)NyG, tol, iter_index};
+    k_flux<<<1, 1024, 0, s>>>(d, flux_params(Dphase, CL, CR, NxG), ck, row_first, nrows, st);
+}
+
+// the stop rule alone, on all-reduced {Q1, Q2} (multi-GPU slabs)
 __global__ void k_check(SolveState *st, double two_ny, double CL, double CR, double tol, long long iter_index)
 {
-    if (st->stop) return;
-    const double qAvg = (st->q[0] + st->q[1]) / two_ny;          // cuh:1263
-    const double deffNew = qAvg / (CR - CL);                     // cuh:1264
-    const double change = (st->deff_old - deffNew) / (st->deff_old);   // cuh:1265
-    st->deff_new = deffNew;
-    st->change = change;
-    st->conv = change;                                           // cuh:1275
-    st->deff_old = deffNew;                                      // cuh:1273
-    if (st->nchecks < 256) st->trace[st->nchecks] = deffNew;
-    st->nchecks++;
-    if (!(tol < fabs(change))) {                                 // cuh:1232 (NaN ends the loop)
-        st->stop = 1;
-        st->stop_iter = iter_index + 1;                          // iterCount after the increment of cuh:1289
-    }
+    apply_check(st, two_ny, CL, CR, tol, iter_index);
 }
 
 void launch_check(cudaStream_t s, SolveState *st, int64_t NyG, double CL, double CR, double tol,

@@ -72,6 +72,9 @@ void launch_sweep_simple(cudaStream_t s, const DomainView &d, const int *stop);
 // K4: boundary-flux sums over local rows [row_first, row_first+nrows) (cuh:1252-1260)
 void launch_flux(cudaStream_t s, const DomainView &d, const double Dphase[3], double CL, double CR,
                  int64_t NxG, int64_t row_first, int64_t nrows, SolveState *st);
+// K4 fused: flux sums + Deff + stop rule in one launch (single-GPU domains)
+void launch_flux_check(cudaStream_t s, const DomainView &d, const double Dphase[3], double CL, double CR, int64_t NxG,
+                       int64_t NyG, int64_t row_first, int64_t nrows, double tol, long long iter_index, SolveState *st);
 // stop rule of cuh:1263-1276 + cuh:1232 on the (all-reduced) Q1, Q2
 void launch_check(cudaStream_t s, SolveState *st, int64_t NyG, double CL, double CR, double tol,
                   long long iter_index);

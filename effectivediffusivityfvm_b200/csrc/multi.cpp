@@ -18,36 +18,7 @@
 #include <thread>
 #include <vector>
 
-namespace {
-
-struct Stage { double Ds, Df, Dg, D, tol; int64_t max_iter; bool precond; };
-
-// The stage list of solve_image_impl (context.cu), which follows cuh:1759-1817 and cuh:1492-1597.
-std::vector<Stage> stage_list(const deff2d_params *p)
-{
-    std::vector<Stage> st;
-    if (p->mode == DEFF2D_MODE_2PH_BATCH) {
-        st.push_back({p->Ds, p->Df, 0.0, p->Df, p->tol, p->max_iter, false});           // cuh:2004-2009
-    } else if (p->mode == DEFF2D_MODE_2PH_SINGLE) {
-        double DCF = 10.0;                                                              // cuh:1714
-        int count = 1;
-        if (DCF > p->Df && p->strict_reference == 0) st.push_back({p->Ds, p->Df, 0.0, p->Df, p->tol, p->max_iter, false});
-        while (DCF <= p->Df) {                                                          // cuh:1761 (quirk Q8)
-            DCF = std::pow(100, count);                                                 // cuh:1762
-            if (DCF >= p->Df) DCF = p->Df;
-            st.push_back({p->Ds, DCF, 0.0, DCF, p->tol, p->max_iter, false});
-            if (DCF == p->Df) break;                                                    // cuh:1812
-            count++;
-        }
-    } else {
-        for (double g = 10; g < p->Dg; g *= 10)                                         // cuh:1492-1547
-            st.push_back({p->Ds, p->Df, g, g, p->tol * 10, 1000000, true});
-        st.push_back({p->Ds, p->Df, p->Dg, p->Dg, p->tol, p->max_iter, false});         // cuh:1557-1591
-    }
-    return st;
-}
-
-}  // namespace
+using deff2d::StageSpec;
 
 DEFF2D_EXPORT int deff2d_solve_image_slabs(deff2d_ctx *const *ctxs, int nctx, const uint8_t *gray, int W, int H,
                                            const deff2d_params *p, deff2d_result *res, double *field)
@@ -66,16 +37,8 @@ DEFF2D_EXPORT int deff2d_solve_image_slabs(deff2d_ctx *const *ctxs, int nctx, co
     while (n > 1 && (H / n) < halo_src) n--;
     if (n == 1) return deff2d_solve_image(ctxs[0], gray, W, H, p, res, field);
 
-    // ---- host pre-processing: FloodFill on the whole amplified domain (cuh:557-713), fractions -------
-    const bool strict = p->strict_reference != 0;
-    const int thr = (nphase == 3) ? 200 : (strict ? 150 : 149);
-    std::vector<uint8_t> grid((size_t)Nx * Ny);
-    for (int64_t i = 0; i < Ny; i++) {
-        const uint8_t *srow = gray + (size_t)(i / p->amp_y) * W;
-        uint8_t *g = grid.data() + (size_t)i * Nx;
-        for (int64_t j = 0; j < Nx; j++) g[j] = srow[j / p->amp_x] > thr;
-    }
-    res->pathflag = deff2d::floodfill(grid.data(), Nx, Ny, strict);
+    // ---- fractions on the host (source pixels only); FloodFill runs on every rank's device over the whole domain
+    //      inside deff2d_domain_load_slab_global (replicated: the flood needs global connectivity) ----------
     res->n_cells = Nx * Ny;
     {
         int64_t below150 = 0, cnt[3] = {0, 0, 0};
@@ -97,12 +60,15 @@ DEFF2D_EXPORT int deff2d_solve_image_slabs(deff2d_ctx *const *ctxs, int nctx, co
             res->LVF = deff2d::accumulate_fraction(nl * amp2, Nx * Ny);
         }
     }
-    const std::vector<Stage> stages = stage_list(p);
+    StageSpec spec[DEFF2D_MAX_STAGES];
+    const int nst = deff2d::stage_list(p, spec, DEFF2D_MAX_STAGES);
+    if (nst < 0) return DEFF2D_ERR_ARG;
+    const std::vector<StageSpec> stages(spec, spec + nst);
     uint8_t id[DEFF2D_NCCL_ID_BYTES];
     int rc = deff2d_nccl_unique_id(id);
     if (rc) return rc;
 
-    struct RankOut { int rc = 0; std::vector<int64_t> iters; std::vector<double> deff, ms; double conv = 0; };
+    struct RankOut { int rc = 0; int pathflag = 0; std::vector<int64_t> iters; std::vector<double> deff, ms; double conv = 0; };
     std::vector<RankOut> out((size_t)n);
     // A rank whose slab failed to load must not leave the others waiting in a halo exchange: all ranks
     // meet once after loading and give up together if any of them failed.
@@ -115,30 +81,38 @@ DEFF2D_EXPORT int deff2d_solve_image_slabs(deff2d_ctx *const *ctxs, int nctx, co
         if (++arrived == n) cv.notify_all();
         else cv.wait(lk, [&] { return arrived == n; });
     };
+    // A failure on one rank in the middle of a stage (set_D, a launch, NCCL) would leave the others blocked in a halo
+    // exchange or the flux all-reduce: the failing rank aborts every communicator of the group, which makes the peers'
+    // pending NCCL work return, and all ranks leave with an error.
+    auto give_up = [&]() {
+        if (!failed.exchange(1))
+            for (int k = 0; k < n; k++) deff2d_slab_abort(ctxs[k]);
+    };
+    std::vector<int> graphs_before((size_t)n, 1);
     auto work = [&](int r) {
         RankOut &o = out[(size_t)r];
         deff2d_ctx *c = ctxs[r];
         // NCCL reports an internal error when send/recv of ranks that are threads of one process are
         // captured into CUDA graphs (measured, NCCL 2.28): enqueue the passes directly in this mode
+        graphs_before[(size_t)r] = deff2d_get_graphs(c);
         deff2d_set_graphs(c, 0);
         if ((o.rc = deff2d_nccl_init(c, id, r, n))) { failed.store(1); meet(); return; }
         const int s0 = (int)((int64_t)H * r / n), s1 = (int)((int64_t)H * (r + 1) / n);
         const int sa = (r > 0) ? halo_src : 0, sb = (r < n - 1) ? halo_src : 0;
-        const int64_t a0 = (int64_t)(s0 - sa) * p->amp_y, a1 = (int64_t)(s1 + sb) * p->amp_y;       // local amplified rows [a0, a1)
         deff2d_params q = *p;
         q.verbose = 0;
-        o.rc = deff2d_domain_load_slab(c, gray + (size_t)(s0 - sa) * W, W, s1 - s0, nphase, &q, (int64_t)s0 * p->amp_y, Ny, halo,
-                                       nphase == 3 ? grid.data() + (size_t)a0 * Nx : nullptr);
-        (void)a1;
+        o.rc = deff2d_domain_load_slab_global(c, gray, W, H, nphase, &q, (int64_t)s0 * p->amp_y, (int64_t)(s1 - s0) * p->amp_y, halo);
+        if (!o.rc) o.rc = deff2d_domain_info(c, nullptr, nullptr, &o.pathflag, nullptr, nullptr, nullptr);
         if (o.rc) failed.store(1);
         meet();
         if (failed.load()) { if (!o.rc) o.rc = DEFF2D_ERR_STATE; return; }
-        for (const Stage &st : stages) {
-            if ((o.rc = deff2d_domain_set_D(c, st.Ds, st.Df, st.Dg))) return;
+        for (const StageSpec &st : stages) {
+            if ((o.rc = deff2d_domain_set_D(c, st.Ds, st.Df, st.Dg))) { give_up(); return; }
             int64_t it = 0;
             double d = 0, cv = 0;
             const auto t0 = std::chrono::steady_clock::now();
-            if ((o.rc = deff2d_domain_solve(c, st.tol, st.max_iter, &it, &d, &cv, nullptr, 0, nullptr))) return;
+            if ((o.rc = deff2d_domain_solve(c, st.tol, st.max_iter, &it, &d, &cv, nullptr, 0, nullptr))) { give_up(); return; }
+            if (failed.load()) { o.rc = DEFF2D_ERR_STATE; return; }
             o.ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
             o.iters.push_back(it);
             o.deff.push_back(d);
@@ -157,15 +131,16 @@ DEFF2D_EXPORT int deff2d_solve_image_slabs(deff2d_ctx *const *ctxs, int nctx, co
     for (int r = 1; r < n; r++) pool.emplace_back(work, r);
     work(0);
     for (auto &t : pool) t.join();
-    for (int r = 0; r < n; r++) deff2d_set_graphs(ctxs[r], 1);
+    for (int r = 0; r < n; r++) deff2d_set_graphs(ctxs[r], graphs_before[(size_t)r]);
     for (int r = 0; r < n; r++) if (out[(size_t)r].rc) return out[(size_t)r].rc;
+    res->pathflag = out[0].pathflag;
 
     const RankOut &o0 = out[0];
     res->nstages = (int)stages.size();
     for (size_t k = 0; k < stages.size() && k < DEFF2D_MAX_STAGES; k++) {
         res->iters[k] = o0.iters[k];
         res->stage_deff_raw[k] = o0.deff[k];
-        res->stage_D[k] = stages[k].D;
+        res->stage_D[k] = stages[k].stageD;
         res->total_iters += o0.iters[k];
         double ms = 0;
         for (int r = 0; r < n; r++) ms = std::max(ms, out[(size_t)r].ms[k]);

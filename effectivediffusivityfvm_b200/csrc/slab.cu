@@ -36,6 +36,7 @@ struct NcclApi {
     decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
     decltype(&ncclCommInitRank) CommInitRank = nullptr;
     decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclCommAbort) CommAbort = nullptr;
     decltype(&ncclSend) Send = nullptr;
     decltype(&ncclRecv) Recv = nullptr;
     decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -58,6 +59,7 @@ static void nccl_bind(NcclApi &api)
     api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
     api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
     api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.CommAbort = (decltype(api.CommAbort))sym("ncclCommAbort");
     api.Send = (decltype(api.Send))sym("ncclSend");
     api.Recv = (decltype(api.Recv))sym("ncclRecv");
     api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
@@ -90,7 +92,6 @@ struct SlabState {
     SlabGraph graph[2];           // one per parity of c->cur at the start of the run
     bool use_graphs = true;
     bool split = false;           // boundary tiles in an own launch, exchange overlapped with the interior launch
-    bool debug_nocomm = false;    // timing experiments only: skip the halo exchange (results are then wrong)
     uint64_t lists_version = 0;
     int rank = 0, nranks = 1;
     cudaEvent_t evA = nullptr, evC = nullptr;
@@ -204,7 +205,7 @@ static int slab_exchange(deff2d_ctx *c, SlabState *s, NcclApi *api, double *buf,
 // (the two-launch split costs more than the exchange it hides), kept for comparison.
 static int slab_pass(deff2d_ctx *c, SlabState *s, NcclApi *api, int T)
 {
-    const bool comm = (c->halo_above > 0 || c->halo_below > 0) && !s->debug_nocomm;
+    const bool comm = (c->halo_above > 0 || c->halo_below > 0);
     int rc;
     if (s->split) {
         if ((rc = tma_pass(c, T, s->tiles.p + s->off_b[T], s->cnt_b[T], c->stream))) return rc;
@@ -313,6 +314,12 @@ int slab_allreduce_q(deff2d_ctx *c)
     return DEFF2D_OK;
 }
 
+bool slab_is_distributed(const deff2d_ctx *c)
+{
+    const SlabState *s = static_cast<const SlabState *>(c->slab);
+    return s && s->comm && s->nranks >= 2 && c->slab_domain;
+}
+
 void slab_destroy(deff2d_ctx *c)
 {
     SlabState *s = static_cast<SlabState *>(c->slab);
@@ -353,7 +360,6 @@ DEFF2D_EXPORT int deff2d_nccl_init(deff2d_ctx *c, const uint8_t id[DEFF2D_NCCL_I
     c->slab = s;
     s->rank = rank; s->nranks = nranks;
     if (const char *e = std::getenv("DEFF2D_SLAB_SPLIT")) s->split = std::atoi(e) != 0;          // tuning
-    if (const char *e = std::getenv("DEFF2D_SLAB_DEBUG_NOCOMM")) s->debug_nocomm = std::atoi(e) != 0;
     if (const char *e = std::getenv("DEFF2D_SLAB_GRAPHS")) s->use_graphs = std::atoi(e) != 0;   // tuning
     if (const char *e = std::getenv("DEFF2D_SLAB_RESERVE_SMS")) { const int v = std::atoi(e); if (v >= 0 && v <= 64) s->reserve_sms = v; }   // tuning
     CUS(cudaSetDevice(c->device));
@@ -362,6 +368,20 @@ DEFF2D_EXPORT int deff2d_nccl_init(deff2d_ctx *c, const uint8_t id[DEFF2D_NCCL_I
     ncclUniqueId u;
     std::memcpy(&u, id, sizeof(u));
     NCCLCHECK(api->CommInitRank(&s->comm, nranks, u, rank));
+    return DEFF2D_OK;
+}
+
+// Abort this context's communicator (another rank of the group failed): pending and future NCCL work on it returns
+// an error instead of waiting for a peer that will never arrive.  The communicator is gone afterwards.
+DEFF2D_EXPORT int deff2d_slab_abort(deff2d_ctx *c)
+{
+    if (!c) return DEFF2D_ERR_ARG;
+    SlabState *s = static_cast<SlabState *>(c->slab);
+    NcclApi *api = nccl_api();
+    if (!s || !s->comm || !api->CommAbort) return DEFF2D_OK;
+    ncclComm_t comm = s->comm;
+    s->comm = nullptr;
+    api->CommAbort(comm);
     return DEFF2D_OK;
 }
 

@@ -425,7 +425,7 @@ struct GraphEntry {
     uint64_t version = 0;        // tensor-map generation the graph was captured with
     int T = 0, fam = 0, src = 0, count = 0, grid_limit = 0;
     const uint32_t *list = nullptr;
-    const double *lut = nullptr, *lut2 = nullptr;
+    const double *lut = nullptr;
     double omega = 0;
 };
 
@@ -619,7 +619,7 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
         GraphEntry *g = nullptr;
         for (auto &e : ts->graphs)
             if (e.exec && e.version == ts->version && e.T == T && e.fam == (k2_family(c) * 8 + (c->k2_variant & 3)) && e.src == c->cur && e.list == list &&
-                e.count == count && e.grid_limit == c->grid_limit && e.lut == c->clut.p && e.lut2 == c->clut_aos.p && e.omega == c->omega) { g = &e; break; }
+                e.count == count && e.grid_limit == c->grid_limit && e.lut == c->clut.p && e.omega == c->omega) { g = &e; break; }
         if (!g) {
             // drop stale graphs, then capture GRAPH_PASSES passes
             for (auto &e : ts->graphs)
@@ -642,7 +642,7 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) { slot->exec = nullptr; set_error(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
             slot->version = ts->version; slot->T = T; slot->fam = k2_family(c) * 8 + (c->k2_variant & 3); slot->src = c->cur; slot->list = list;
-            slot->count = count; slot->grid_limit = c->grid_limit; slot->lut = c->clut.p; slot->lut2 = c->clut_aos.p; slot->omega = c->omega;
+            slot->count = count; slot->grid_limit = c->grid_limit; slot->lut = c->clut.p; slot->omega = c->omega;
             g = slot;
         }
         cudaError_t e = cudaGraphLaunch(g->exec, c->stream);

@@ -110,12 +110,6 @@ void compact_table(const double *lut, double *clut, int nphase)
         }
 }
 
-void interleave_table(const double *clut, double *aos)
-{
-    for (size_t slot = 0; slot < DEFF2D_CLUT_ENTRIES; slot++)
-        for (int f = 0; f < 4; f++) aos[slot * 4 + f] = clut[(size_t)f * DEFF2D_CLUT_ENTRIES + slot];
-}
-
 }  // namespace deff2d
 
 DEFF2D_EXPORT int deff2d_build_tables(double Ds, double Df, double Dg, int64_t Nx, int64_t Ny, double CL,

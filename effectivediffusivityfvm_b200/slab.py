@@ -76,8 +76,9 @@ class SlabDomain:
              vertical copies of `img` (every rank then owns one whole copy).
     halo:    amplified halo rows held of each neighbour.  A pass of depth T consumes T of them, so
              the exchange runs every halo / T passes (32 rows, T = 8: once per 4 passes = 32 sweeps).
-    pinned:  3-phase only -- the global FloodFill mask (cuh:557-713) at amplified resolution, or
-             None to compute it here with the library's host FloodFill.
+    pinned:  None (default): FloodFill runs on the device over the whole domain (deff2d_domain_load_slab_global).
+             Otherwise the global FloodFill mask (cuh:557-713) at amplified resolution, computed by the caller;
+             only the slab's rows of the image and of the mask are uploaded then (deff2d_domain_load_slab).
     """
 
     def __init__(self, ctx, img, params, rank, world, nphase=3, halo=32, pinned=None, weak=False, nccl_id=None):
@@ -89,32 +90,33 @@ class SlabDomain:
         self.layout = L = SlabLayout(H, rank, world, params.amp_y, halo)
         self.Nx = W * params.amp_x
         self.global_cells = self.Nx * L.ny_global
-        lo, hi = L.local_src
-        gray = _take_rows(img, lo, hi, period_src)
-        pin = None
-        self.pathflag = None
-        if nphase == 3:
-            if pinned is None:
-                # FloodFill is y-periodic (cuh:641-665): the mask of `world` stacked copies is the
-                # stacked mask of one copy, so the weak-scaling domain never needs a global flood
-                base = np.repeat(np.repeat(img > 200, params.amp_y, axis=0), params.amp_x, axis=1).astype(np.uint8)
-                pinned, self.pathflag = api.floodfill(base)
-                period = base.shape[0] if weak else None
-            else:
-                period = None
-            a, b = L.local_rows
-            pin = _take_rows(np.asarray(pinned, dtype=np.uint8), a, b, period)
         if nccl_id is None:
             nccl_id = self._broadcast_id()
         ctx.nccl_init(nccl_id, rank, world)
-        self._load_args = (gray, nphase, params, L.row0, L.ny_global, L.halo, L.src_rows, pin)
-        self.h2d_bytes = int(gray.size + (pin.size if pin is not None else 0))
-        ctx.domain_load_slab(*self._load_args)
+        self.pathflag = None
+        if pinned is None:
+            # default: every rank uploads the WHOLE source image (1 B per pixel); FloodFill (cuh:557-713) runs on its
+            # device over the whole domain -- the flood needs global connectivity, so it is replicated, not sharded --
+            # and the slab keeps its rows of the mask.  No host flood, no 1 B/cell mask upload: the same steps as an
+            # undecomposed deff2d_domain_load, which is what `reload()` times end to end.
+            gimg = np.ascontiguousarray(np.tile(img, (world, 1))) if weak else img
+            self._loader, self._load_args = ctx.domain_load_slab_global, (gimg, nphase, params, L.row0, L.own_rows, L.halo)
+            self.h2d_bytes = int(gimg.size)
+        else:
+            lo, hi = L.local_src
+            gray = _take_rows(img, lo, hi, period_src)
+            a, b = L.local_rows
+            pin = _take_rows(np.asarray(pinned, dtype=np.uint8), a, b, None) if nphase == 3 else None
+            self._loader, self._load_args = ctx.domain_load_slab, (gray, nphase, params, L.row0, L.ny_global, L.halo, L.src_rows, pin)
+            self.h2d_bytes = int(gray.size + (pin.size if pin is not None else 0))
+        self._loader(*self._load_args)
+        if pinned is None:
+            self.pathflag = ctx.info()["pathflag"]
 
     def reload(self):
-        """Upload the slab again from the host buffers (image rows + pinned mask) and reset the
-        iterate to x0: what a fresh solve of the same domain costs end to end."""
-        self.ctx.domain_load_slab(*self._load_args)
+        """Upload again from the host buffers and reset the iterate to x0: what a fresh solve of the same domain
+        costs end to end (image upload, FloodFill, assembly)."""
+        self._loader(*self._load_args)
 
     def _broadcast_id(self):
         import torch.distributed as dist

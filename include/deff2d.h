@@ -52,7 +52,10 @@ typedef struct {
     int mode;                 /* deff2d_mode                                        */
     int check_every;          /* 0 -> 10000, the reference's hard-coded cadence  cuh:1174 */
     double omega;             /* 0 -> 2/3, the reference's damping               cuh:72   */
-    int tblock;               /* sweeps fused per HBM pass; 0 -> library default         */
+    int solver;               /* 0 (default): the reference's damped Jacobi, its iterate and stop rule.  1: NON-PARITY
+                               * Chebyshev-accelerated Jacobi (csrc/chebyshev.cu): per-sweep relaxation factors from the
+                               * Chebyshev polynomial on the tiled kernel, stop on the true relative residual
+                               * (residual_tol, default 1e-8) -- the converged answer, not the reference iterate */
     int verbose;              /* 1: print the reference's per-check / per-stage stdout lines */
     double residual_tol;      /* > 0: NON-PARITY stop rule -- at every check stop when the reference's (dead) Residual
                                * (mean |flux imbalance| per cell, cuh:451-494) is <= residual_tol instead of testing
@@ -138,6 +141,12 @@ int deff2d_domain_load(deff2d_ctx *ctx, const uint8_t *gray, int W, int H, int n
 int deff2d_domain_load_slab(deff2d_ctx *ctx, const uint8_t *gray, int W, int Hslab, int nphase,
                             const deff2d_params *p, int64_t row0, int64_t NyGlobal, int halo_rows,
                             const uint8_t *pinned);
+/* The same slab from the WHOLE source image (W x H): the image is uploaded once (1 B per pixel), FloodFill runs on
+ * the device over the whole domain (every rank floods its own copy: the flood needs global connectivity), and the
+ * slab keeps the rows [row0, row0 + own_rows) plus `halo_rows` rows of each neighbour -- no host flood, no mask
+ * upload, the same steps as deff2d_domain_load.  row0, own_rows, halo_rows in amplified rows. */
+int deff2d_domain_load_slab_global(deff2d_ctx *ctx, const uint8_t *gray, int W, int H, int nphase,
+                                   const deff2d_params *p, int64_t row0, int64_t own_rows, int halo_rows);
 /* New continuation stage: only the 3 diffusivities change (cuh:1762, 1524); the phase
  * codes and the iterate stay resident (warm start, cuh:1793). */
 int deff2d_domain_set_D(deff2d_ctx *ctx, double Ds, double Df, double Dg);
@@ -184,6 +193,7 @@ int deff2d_set_batch_slots(deff2d_ctx *ctx, int max_slots);
 /* CUDA-graph replay of long runs of passes: 1 (default) on, 0 off.  Tuning hook; the single-process
  * multi-GPU driver switches it off (NCCL cannot capture when its ranks are threads of one process). */
 int deff2d_set_graphs(deff2d_ctx *ctx, int enable);
+int deff2d_get_graphs(const deff2d_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t deff2d_kernel_launches(const deff2d_ctx *ctx);
 /* The CUDA stream (cudaStream_t as an opaque pointer) all work of the context is enqueued on. */
@@ -198,14 +208,20 @@ int deff2d_domain_buffers(deff2d_ctx *ctx, void **x_cur, void **x_next, int64_t 
 #define DEFF2D_NCCL_ID_BYTES 128
 int deff2d_nccl_unique_id(uint8_t id[DEFF2D_NCCL_ID_BYTES]);       /* call on rank 0, broadcast by the host layer */
 int deff2d_nccl_init(deff2d_ctx *ctx, const uint8_t id[DEFF2D_NCCL_ID_BYTES], int rank, int nranks);
-/* Sweeps on a slab with halo exchange every `tblock` sweeps (ncclSend/ncclRecv of the
- * boundary rows to the two neighbours) -- enqueue only. */
+/* Sweeps on a slab; the halo rows travel to the two neighbours (ncclSend/ncclRecv) whenever the next pass
+ * needs more exact halo rows than are left -- enqueue only. */
 int deff2d_slab_sweeps(deff2d_ctx *ctx, int64_t n);
 /* Global Deff: local {Q1,Q2} -> ncclAllReduce(sum) -> same value on every rank; blocks. */
 int deff2d_slab_flux(deff2d_ctx *ctx, double *deff_raw);
+/* Another rank of the group failed: abort this context's communicator so that its pending NCCL work returns
+ * instead of waiting for a peer that will never arrive.  deff2d_nccl_init is needed again afterwards. */
+int deff2d_slab_abort(deff2d_ctx *ctx);
 
 /* ---- host-side pieces of the path (no GPU needed; CPU-testable) ---------------------- */
 
+/* `count` additions of 1.0/total in double precision, as calcPorosity / calcFracts3D accumulate their fractions
+ * (cuh:402, cuh:437) -- the same bits as the loop, without looping over every cell. */
+double deff2d_accumulate_fraction(int64_t count, int64_t total);
 /* Coefficient tables for one stage, exactly as the library uploads them: lut is
  * 2048*4 doubles -- for the 11-bit index  p | pW<<2 | pE<<4 | pS<<6 | pN<<8 | pinned<<10
  * the four sweep weights (w/A0)*c_f in order W,E,S,N following cuh:815-902 and cuh:89;

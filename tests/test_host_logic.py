@@ -381,3 +381,27 @@ def test_csv_batch_rows_streamed_equal_bulk_write(tmp_path):
                     assert L.deff2d_append_csv_batch_row(C.byref(inp), k, C.byref(res[k])) == 0
             files.append(path.read_bytes())
         assert files[0] == files[1] and files[0].count(b"\n") == 4
+
+
+def test_fraction_accumulation_equals_the_literal_loop():
+    """calcPorosity / calcFracts3D add 1.0/total once per cell (cuh:402, cuh:437); the library jumps whole binades of
+    the running sum instead of looping, and must land on the same bits -- including totals that are powers of two
+    (exact additions), ties, and counts that end in the middle of a binade."""
+    L = _lib.lib()
+    rng = np.random.default_rng(0)
+    cases = [(0, 7), (1, 3), (63, 100), (64, 100), (65, 100), (3000, 10000), (10000, 10000), (4096, 4096), (1 << 20, 1 << 20),
+             (12345, 1 << 16), (700001, 1000003), (2 * 10**6, 3 * 10**6), (16384, 128 * 128), (5678901, 2007 * 1002 * 16 // 4)]
+    for _ in range(30):
+        total = int(rng.integers(2, 4_000_000))
+        cases.append((int(rng.integers(0, total + 1)), total))
+    for count, total in cases:
+        inc, s = 1.0 / total, 0.0
+        for _ in range(count):
+            s += inc
+        got = L.deff2d_accumulate_fraction(count, total)
+        assert got == s, (count, total, got, s)
+    # far beyond what a loop is pleasant for: monotone, close to the closed form, and additive consistency
+    big = L.deff2d_accumulate_fraction(200_000_000, 268_435_456)
+    assert big == 200_000_000 / 268_435_456            # power-of-two total: every addition is exact
+    v = L.deff2d_accumulate_fraction(160_000_000, 268_435_457)
+    assert abs(v - 160_000_000 / 268_435_457) < 1e-7
