@@ -702,7 +702,7 @@ int batch_resident_solve(deff2d_ctx *c, const uint8_t *gray, int count, int W, i
 {
     if (count < 2 || W < 1 || H < 1 || p->amp_x < 1 || p->amp_y < 1) return 1;
     if (p->verbose == 1) return 1;                  // keep the reference's per-image stdout order
-    if (p->residual_tol > 0) return 1;              // non-parity residual stop rule: per-image path
+    if (p->residual_tol > 0 || p->solver != 0) return 1;   // non-parity stop rule / solver: per-image path
     BatchStages stages;
     double stageD[BATCH_MAX_STAGES];
     int nstages = 0;

@@ -145,6 +145,27 @@ int solve_loop(deff2d_ctx *c, double tol, int64_t max_iter, bool verbose_checks,
 {
     launch_reset_state(c->stream, c->d_state);
     c->launches++;
+    if (c->solver == 1) {
+        // NON-PARITY mode: Chebyshev-accelerated Jacobi to a relative residual (chebyshev.cu), then Deff of the result
+        int64_t sweeps = 0;
+        int rc = chebyshev_solve(c, c->residual_tol, max_iter, &sweeps);
+        if (rc) return rc;
+        const double relres = c->h_state->resid;
+        launch_flux(c->stream, view(c), c->Dphase, c->CL, c->CR, c->NxG, c->own_first, c->own_rows, c->d_state);
+        c->launches++;
+        if ((rc = read_state(c))) return rc;
+        const double qAvg = (c->h_state->q[0] + c->h_state->q[1]) / (2.0 * (double)c->NyG);   // cuh:1263
+        c->h_state->deff_new = qAvg / (c->CR - c->CL);                                        // cuh:1264
+        c->h_state->resid = relres;
+        c->h_state->conv = relres;                  // what this mode converged on: the relative residual reached
+        c->h_state->change = relres;
+        c->h_state->nchecks = 1;
+        c->h_state->trace[0] = c->h_state->deff_new;
+        if (verbose_checks)
+            std::printf("Chebyshev: %lld sweeps, relative residual %1.3e, Deff = %1.3e\n", (long long)sweeps, relres, c->h_state->deff_new / print_div);
+        *iters_out = sweeps;
+        return DEFF2D_OK;
+    }
     const int64_t ce = c->check_every;
     int64_t iter = 0;
     bool stopped = false;
@@ -215,6 +236,10 @@ static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc,
     c->omega = (p->omega > 0) ? p->omega : 2.0 / 3.0;
     c->check_every = (p->check_every > 0) ? p->check_every : 10000;
     c->residual_tol = (p->residual_tol > 0 && !c->slab_domain) ? p->residual_tol : 0;
+    if (p->solver != 0 && p->solver != 1) { set_error(c, "unknown solver %d", p->solver); return DEFF2D_ERR_ARG; }
+    if (p->solver == 1 && c->slab_domain) { set_error(c, "the Chebyshev solver (solver = 1) runs on single-GPU domains"); return DEFF2D_ERR_ARG; }
+    c->solver = p->solver;
+    if (c->solver == 1) c->omega = 1.0;          // chebyshev.cu: the tables hold the plain Jacobi weights, the factors come per sweep
     c->Dphase[0] = p->Df; c->Dphase[1] = p->Ds; c->Dphase[2] = p->Dg;
     c->cur = 0;
     const size_t cells = (size_t)c->rows * (size_t)c->pitch;

@@ -32,6 +32,7 @@ struct deff2d_ctx {
     double CL = 0, CR = 1, omega = 2.0 / 3.0;
     int check_every = 10000;
     double residual_tol = 0;         // > 0: stop on the residual instead of the Deff change (non-parity mode)
+    int solver = 0;                  // 1: Chebyshev-accelerated Jacobi (chebyshev.cu, non-parity mode)
     int cur = 0;                     // x[cur] holds the newest iterate
     int pathflag = 0;
     double porosity = 0;
@@ -102,6 +103,7 @@ int tma_pass(deff2d_ctx *c, int T, const uint32_t *list, int count, cudaStream_t
 // npasses passes of depth T on c->stream, flipping c->cur after each (CUDA graphs for long runs)
 int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int count);
 void tma_tile_geometry(const deff2d_ctx *c, int T, int *ow, int *oh);
+int tma_cheb_pass(deff2d_ctx *c, const double tau[8]);   // chebyshev.cu: 8 Richardson steps with per-sweep factors (omega = 1 table)
 void tma_destroy(deff2d_ctx *c);
 
 // slab.cu
@@ -115,6 +117,9 @@ void batch_destroy(deff2d_ctx *c);
 bool resident_eligible(deff2d_ctx *c, int64_t Nx, int64_t Ny);
 int resident_sweeps(deff2d_ctx *c, int64_t n, int64_t Nx, int64_t Ny, int GX, const int *active, int nactive);
 void resident_destroy(deff2d_ctx *c);
+
+// chebyshev.cu: the opt-in accelerated solver (non-parity): sweeps until the relative residual is <= rtol or max_sweeps
+int chebyshev_solve(deff2d_ctx *c, double rtol, int64_t max_sweeps, int64_t *sweeps_out);
 
 // floodfill.cu: FloodFill (cuh:557-713) by label propagation on the device; blocks
 int floodfill_device(deff2d_ctx *c, const uint8_t *img, int W, int Hsrc, int amp_x, int amp_y, int thr, uint8_t *st, int64_t Nx,

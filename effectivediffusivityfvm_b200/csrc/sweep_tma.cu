@@ -83,6 +83,9 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map)
 
 // ------------------------------------------------------------------------------------------ kernel
 
+// CHEB variant (chebyshev.cu): per-sweep relaxation factors of one pass; the weight table then holds omega = 1
+struct ChebTaus { double t[8]; };
+
 struct TmaMaps {
     CUtensorMap x_load[2];     // padded iterate buffers, box TW x TH
     CUtensorMap x_store[2];    // interior of the iterate buffers, box OW x OH
@@ -131,11 +134,14 @@ struct Cfg {
 template <class C, bool LIST, int VAR>
 __global__ void __launch_bounds__(C::NT, 1)
 k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, double om,
-            int tiles_x, int ntiles, const uint32_t *__restrict__ tile_list)
+            int tiles_x, int ntiles, const uint32_t *__restrict__ tile_list, const ChebTaus taus)
 {
     constexpr int T = C::T, TE = C::TE, PX = C::PX, PY = C::PY, TW = C::TW, TH = C::TH, OW = C::OW, OH = C::OH;
     constexpr int PW = C::PLANE_W, IW = C::IW;
     constexpr bool ROWEX = (VAR & 1) != 0 && PX == 2;   // N / S row exchange row-major with 16-byte accesses instead of planar 8-byte ones
+    // NON-PARITY Chebyshev mode: sweep s of the pass is the Richardson step x' = x + tau_s (sum_f u_f x_f - x) with the
+    // omega = 1 table u; ghost columns keep their value (factor 0)
+    constexpr bool CHEB = (VAR & 2) != 0;
     static_assert(C::NWX == 1, "a warp spans the tile width (W / E halo by shuffles)");
 
     // No integer round trip on the base pointer: the compiler must keep seeing the shared
@@ -259,7 +265,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
                 unsigned any = 0;
 #pragma unroll
                 for (int py = 0; py < PY; py++) any |= idx[py][px];
-                omc[px] = (any & 0x8000u) ? 1.0 : om;
+                omc[px] = CHEB ? ((any & 0x8000u) ? 0.0 : 1.0) : ((any & 0x8000u) ? 1.0 : om);
             }
 #pragma unroll
             for (int py = 0; py < PY; py++)
@@ -308,17 +314,26 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         };
         // x' = (1-w) x + wW xW + wE xE + wS xS + wN xN   (cuh:76-89, A and b folded into w): one patch row
         auto row_update = [&](int py, double hw, double he, const double (&upv)[PX], const double (&dnv)[PX],
-                              const double (&cur)[PX], double (&out)[PX]) {
+                              const double (&cur)[PX], double (&out)[PX], const double (&fac)[PX]) {
             double left = hw;
 #pragma unroll
             for (int px = 0; px < PX; px++) {
                 const double c = cur[px];
                 const double right = (px == PX - 1) ? he : cur[px + 1];
-                double r = omc[px] * c;
-                r = fma(w[py][px][0], left, r);
-                r = fma(w[py][px][1], right, r);
-                r = fma(w[py][px][2], dnv[px], r);
-                r = fma(w[py][px][3], upv[px], r);
+                double r;
+                if constexpr (CHEB) {
+                    double t = w[py][px][0] * left;
+                    t = fma(w[py][px][1], right, t);
+                    t = fma(w[py][px][2], dnv[px], t);
+                    t = fma(w[py][px][3], upv[px], t);
+                    r = fma(fac[px], t - c, c);
+                } else {
+                    r = fac[px] * c;
+                    r = fma(w[py][px][0], left, r);
+                    r = fma(w[py][px][1], right, r);
+                    r = fma(w[py][px][2], dnv[px], r);
+                    r = fma(w[py][px][3], upv[px], r);
+                }
                 out[px] = r;
                 left = c;
             }
@@ -359,16 +374,16 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
                 }
             }
             // in-place update; `up[px]` carries the old value of the row above
-            double up[PX];
+            double up[PX], fac[PX];
 #pragma unroll
-            for (int px = 0; px < PX; px++) up[px] = hN[px];
+            for (int px = 0; px < PX; px++) { up[px] = hN[px]; fac[px] = CHEB ? omc[px] * taus.t[s - 1] : omc[px]; }
 #pragma unroll
             for (int py = 0; py < PY; py++) {
                 double cur[PX];
 #pragma unroll
                 for (int px = 0; px < PX; px++) cur[px] = x[py][px];
-                if (py == PY - 1) row_update(py, hW[py], hE[py], up, hS, cur, x[py]);
-                else row_update(py, hW[py], hE[py], up, x[py + 1], cur, x[py]);
+                if (py == PY - 1) row_update(py, hW[py], hE[py], up, hS, cur, x[py], fac);
+                else row_update(py, hW[py], hE[py], up, x[py + 1], cur, x[py], fac);
 #pragma unroll
                 for (int px = 0; px < PX; px++) up[px] = cur[px];
             }
@@ -480,7 +495,8 @@ static bool attr_done(TmaState *ts, const void *fn)
 }
 
 template <int T, int F, int VAR>
-static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, int count, cudaStream_t stream)
+static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, int count, cudaStream_t stream,
+                    const ChebTaus &taus = ChebTaus())
 {
     using C = typename Family<T, F>::type;
     auto kern = list ? k_sweep_tma<C, true, VAR> : k_sweep_tma<C, false, VAR>;
@@ -495,7 +511,7 @@ static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, 
     if (c->grid_limit > 0 && grid > c->grid_limit) grid = c->grid_limit;
     if (grid > ntiles) grid = ntiles;
     const double *table = c->clut.p;
-    kern<<<grid, C::NT, smem, stream>>>(ts->maps, src, table, 1.0 - c->omega, ts->tiles_x, ntiles, list);
+    kern<<<grid, C::NT, smem, stream>>>(ts->maps, src, table, 1.0 - c->omega, ts->tiles_x, ntiles, list, taus);
     return DEFF2D_OK;
 }
 
@@ -584,6 +600,22 @@ static int pass_from(deff2d_ctx *c, int T, int src, const uint32_t *list, int co
     }
 #undef DEFF2D_CASE
 #undef DEFF2D_VAR
+    return DEFF2D_OK;
+}
+
+// NON-PARITY Chebyshev mode (chebyshev.cu): one pass of 8 Richardson steps with the factors tau[0..7] from x[c->cur] into
+// x[c->cur ^ 1] over the whole tile grid; flips c->cur.  The context's table must hold omega = 1.
+int tma_cheb_pass(deff2d_ctx *c, const double tau[8])
+{
+    TmaState *ts = tma_state(c);
+    if (!ts->encode) { set_error(c, "cuTensorMapEncodeTiled is not available from this driver"); return DEFF2D_ERR_CUDA; }
+    ChebTaus t;
+    for (int k = 0; k < 8; k++) t.t[k] = tau[k];
+    int rc;
+    if ((rc = prepare_T<8, 4>(c, ts))) return rc;
+    if ((rc = launch_T<8, 4, 2>(c, ts, c->cur, nullptr, 0, c->stream, t))) return rc;
+    c->cur ^= 1;
+    c->launches++;
     return DEFF2D_OK;
 }
 

@@ -676,7 +676,8 @@ def test_packed_batch_of_config3_images_vs_oracle(ctx):
 
 def test_stop_rule_at_the_tolerance_boundary(ctx):
     """cuh:1232 continues while `tol < fabs(change)`: a tolerance equal to |change| of a check stops there, the next
-    representable smaller tolerance does not.  Both against the oracle's loop."""
+    representable smaller tolerance does not.  Against the oracle's loop with |change| within 1e-9 (relative) of tol on
+    either side -- the two implementations' Deff agree to ~1e-13, so they must take the same decision there."""
     img = blobs(31, (64, 96))
     opts = dict(Ds=1e-2, Df=1.0, mode=E.MODE_2PH_BATCH, check_every=500, max_iter=100000)
     ctx.domain_load(img, 2, E.default_params(**opts))
@@ -684,15 +685,15 @@ def test_stop_rule_at_the_tolerance_boundary(ctx):
     tr = probe["trace"]
     k = 6                                                # the check after sweep 3001
     change = abs((tr[k - 1] - tr[k]) / tr[k - 1])
-    for tol, want in ((change, k * 500 + 1), (np.nextafter(change, 0.0), None)):
+    stop_at = k * 500 + 1
+    assert ctx.solve_image(img, E.default_params(tol=change, **opts))["iters"] == [stop_at]                  # tol == |change|: stop
+    assert ctx.solve_image(img, E.default_params(tol=float(np.nextafter(change, 0.0)), **opts))["iters"][0] > stop_at
+    for tol, stops in ((change * (1 + 1e-9), True), (change * (1 - 1e-9), False)):
         got = ctx.solve_image(img, E.default_params(tol=tol, **opts))
         ref = O.solve_image(img, O.make_opts(Ds=1e-2, Df=1.0, nphase=2, check_every=500, max_iter=100000, tol=tol), O.MODE_2PH_BATCH)
         assert got["iters"] == ref["iters"]
+        assert (got["iters"] == [stop_at]) == stops
         assert rel(got["deff"], ref["deff"]) < DEFF_RTOL_TIGHT
-        if want is not None:
-            assert got["iters"] == [want]
-        else:
-            assert got["iters"][0] > k * 500 + 1
 
 
 # ----------------------------------------------------------------------------- K5 (cluster-resident) == K3 (streaming)
@@ -734,6 +735,35 @@ def test_resident_packed_batch_matches_tiled_packed_batch(ctx):
     ctx.set_batch_slots(0)
     for a, b in zip(out[1], out[2]):
         assert a["iters"] == b["iters"] and a["deff"] == b["deff"] and a["conv"] == b["conv"] and a["pathflag"] == b["pathflag"]
+
+
+# ----------------------------------------------------------------------------- opt-in accelerated solver (non-parity mode)
+
+@pytest.mark.parametrize("nphase,Ds,Dg", [(2, 1e-2, 0.0), (3, 0.0, 30.0)])
+def test_chebyshev_solver_reaches_the_limit_of_the_reference_iteration(ctx, nphase, Ds, Dg):
+    """solver = 1 (csrc/chebyshev.cu) solves the same linear system as the reference's damped Jacobi, so it must land
+    on the limit of that iteration -- here reached by brute force, 400 000 reference sweeps on a small domain -- in a
+    small fraction of the sweeps.  Non-parity mode: the reference's stop rule and its intermediate iterates do not apply."""
+    img = blobs(9 + nphase, (48, 64), levels=(0, 150, 255), fracs=(0.3, 0.4), smooth=2)
+    base = dict(Ds=Ds, Df=1.0, Dg=Dg, CL=0.2, CR=1.3)
+    ctx.set_kernel(0)
+    ctx.domain_load(img, nphase, E.default_params(**base))
+    ctx.sweeps(400000)
+    limit = ctx.flux()[0]
+    field = ctx.get_field()
+    ctx.domain_load(img, nphase, E.default_params(solver=1, residual_tol=1e-11, **base))
+    got = ctx.solve(0.0, 100000)
+    assert got["iters"] < 20000
+    assert got["conv"] <= 1e-11                                   # the relative residual reached
+    assert rel(got["deff_raw"], limit) < 1e-9
+    f = ctx.get_field()
+    live = np.isfinite(field) & np.isfinite(f)
+    assert np.max(np.abs(f[live] - field[live])) < 1e-8
+    # through the driver: same answer, stages and all
+    mode = E.MODE_3PH if nphase == 3 else E.MODE_2PH_BATCH
+    r = ctx.solve_image(img, E.default_params(solver=1, residual_tol=1e-11, mode=mode, max_iter=100000, **base))
+    assert rel(r["deff_raw"], limit) < 1e-9
+    ctx.domain_load(blobs(1, (16, 16)), 2, E.default_params())     # leave a plain-solver domain resident
 
 # ----------------------------------------------------------------------------- K2 (TMA tiled) == K3 (streaming)
 
