@@ -762,7 +762,7 @@ def test_chebyshev_solver_reaches_the_limit_of_the_reference_iteration(ctx, npha
     # through the driver: same answer, stages and all
     mode = E.MODE_3PH if nphase == 3 else E.MODE_2PH_BATCH
     r = ctx.solve_image(img, E.default_params(solver=1, residual_tol=1e-11, mode=mode, max_iter=100000, **base))
-    assert rel(r["deff_raw"], limit) < 1e-9
+    assert rel(r["deff_raw"], limit) < 1e-8                       # (the brute-force limit itself is only that converged)
     ctx.domain_load(blobs(1, (16, 16)), 2, E.default_params())     # leave a plain-solver domain resident
 
 # ----------------------------------------------------------------------------- K2 (TMA tiled) == K3 (streaming)
