@@ -570,8 +570,8 @@ def run_ours(args):
             r = ctx.solve(1e-30, Se)                        # 2 checks; Deff read back (D2H)
         dt = time.perf_counter() - t0
         e2e = {"value": cells * Se * e_steps / dt / 1e9, "unit": "GLUP/s",
-               # image + FloodFill mask (1 B/cell) + weight LUT and dead table
-               "h2d_bytes_per_step": int(img.size + Nx * Ny + 2048 * 32 + 2048),
+               # image (the FloodFill mask is computed on the device) + weight LUT, dead table and compact table
+               "h2d_bytes_per_step": int(img.size + 2048 * 32 + 2048 + 1024 * 32),
                # phase counts (48 B) + the convergence state read at each of the 2 checks
                "d2h_bytes_per_step": int(48 + 2 * 2120), "steps": e_steps, "sweeps_per_step": Se,
                "deff_raw": r["deff_raw"]}

@@ -54,6 +54,9 @@ class Input(C.Structure):
                 ("output_name", C.c_char * 1000), ("cmap_name", C.c_char * 1000), ("devices", C.c_int), ("field_npy", C.c_int)]
 
 
+BATCH_FETCH_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_ubyte), C.c_int)
+BATCH_DONE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(Result), C.POINTER(C.c_double))
+
 _lib = None
 
 
@@ -75,6 +78,8 @@ def lib():
         "deff2d_default_params": (None, [C.POINTER(Params)]),
         "deff2d_solve_image": (i32, [vp, c_ubyte_p, i32, i32, C.POINTER(Params), C.POINTER(Result), c_double_p]),
         "deff2d_solve_batch": (i32, [vp, c_ubyte_p, i32, i32, i32, C.POINTER(Params), C.POINTER(Result), c_double_p]),
+        "deff2d_solve_batch_stream": (i32, [vp, i32, i32, i32, C.POINTER(Params), BATCH_FETCH_FN, BATCH_DONE_FN, vp, i32, C.POINTER(i32)]),
+        "deff2d_batch_supported": (i32, [C.POINTER(Params), i32, i32]),
         "deff2d_solve_image_slabs": (i32, [C.POINTER(vp), i32, c_ubyte_p, i32, i32, C.POINTER(Params), C.POINTER(Result), c_double_p]),
         "deff2d_domain_load": (i32, [vp, c_ubyte_p, i32, i32, i32, C.POINTER(Params)]),
         "deff2d_domain_load_slab": (i32, [vp, c_ubyte_p, i32, i32, i32, C.POINTER(Params), i64, i64, i32, c_ubyte_p]),

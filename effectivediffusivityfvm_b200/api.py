@@ -186,6 +186,52 @@ class Deff2D:
                 out[k]["field"] = fields[k]
         return out
 
+    def solve_batch_stream(self, count, shape, params, fetch, done=None, want_fields=False):
+        """The packed batch solve as a stream (deff2d_solve_batch_stream).
+
+        fetch(k, wait) -> (H, W) uint8 array of image k, None if it is not ready yet (only when wait is False) or
+        StopIteration-like `False` when there is no image k; done(k, result_dict, field_or_None) is called as each
+        image finishes (any order).  Returns the number of images solved."""
+        H, W = shape
+        ncell = H * params.amp_y * W * params.amp_x
+        err = []
+
+        def _fetch(_user, k, dst, wait):
+            try:
+                img = fetch(k, bool(wait))
+                if img is None:
+                    return 1
+                if img is False:
+                    return 2
+                a = np.ascontiguousarray(img, dtype=np.uint8)
+                if a.shape != (H, W):
+                    return 2
+                C.memmove(dst, a.ctypes.data, a.size)
+                return 0
+            except Exception as e:      # exceptions must not cross the C frames
+                err.append(e)
+                return -2
+
+        def _done(_user, k, res, field):
+            try:
+                if done is not None:
+                    f = np.ctypeslib.as_array(field, shape=(H * params.amp_y, W * params.amp_x)).copy() if (want_fields and field) else None
+                    done(k, res.contents.as_dict(), f)
+                return 0
+            except Exception as e:
+                err.append(e)
+                return 1
+
+        solved = C.c_int(0)
+        cb_f, cb_d = _lib.BATCH_FETCH_FN(_fetch), _lib.BATCH_DONE_FN(_done)
+        rc = self._L.deff2d_solve_batch_stream(self._h, int(count), W, H, C.byref(params), cb_f, cb_d, None, 1 if want_fields else 0,
+                                               C.byref(solved))
+        if err:
+            raise err[0]
+        self._ck(rc)
+        del ncell
+        return solved.value
+
     # the reference's four drivers by name (Deff2D.cu:17-50)
     def SingleSim(self, gray, params, want_field=False):
         params.mode = MODE_2PH_SINGLE

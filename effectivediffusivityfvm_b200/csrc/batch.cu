@@ -60,7 +60,7 @@ struct BatchOut {
     int nstages, pad;
 };
 
-struct BatchJob { int slot, image; };
+struct BatchJob { int slot, image, src, pad; };   // src: position of the image in the staging buffers of this refill
 
 struct BatchGeom {
     int W, H, amp_x, amp_y, Nx, Ny, GX, nphase;
@@ -94,8 +94,8 @@ k_batch_init(BatchGeom g, const BatchJob *__restrict__ jobs, const uint8_t *__re
     const BatchJob job = jobs[blockIdx.y];
     const int gx = job.slot % g.GX, gy = job.slot / g.GX;
     const long long col0 = (long long)gx * (g.Nx + 1), row0 = (long long)gy * (g.Ny + 1);
-    const uint8_t *img = img_base + (size_t)job.image * g.W * g.H;
-    const uint8_t *grid = grid_base ? grid_base + (size_t)job.image * g.Nx * g.Ny : nullptr;
+    const uint8_t *img = img_base + (size_t)job.src * g.W * g.H;
+    const uint8_t *grid = grid_base ? grid_base + (size_t)job.src * g.Nx * g.Ny : nullptr;
     const long long wp = g.Nx + 2, total = (long long)(g.Ny + 2) * wp;
     unsigned long long cnt[3] = {0, 0, 0}, below = 0;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
@@ -124,7 +124,7 @@ k_batch_init(BatchGeom g, const BatchJob *__restrict__ jobs, const uint8_t *__re
     const long long npix = (long long)g.W * g.H;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < npix; k += (long long)gridDim.x * blockDim.x)
         below += (img[k] < 150) ? 1u : 0u;
-    BatchOut *o = outs + job.image;
+    BatchOut *o = outs + job.slot;              // zeroed by k_batch_clear
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const unsigned long long s = warp_sum_ull(cnt[k]);
@@ -138,6 +138,16 @@ k_batch_init(BatchGeom g, const BatchJob *__restrict__ jobs, const uint8_t *__re
         s.iter = 0; s.stage = 0; s.status = 1; s.image = job.image; s.nchecks = 0;
         slots[job.slot] = s;
     }
+}
+
+// the result record of every slot that is about to receive a new image
+__global__ void k_batch_clear(const BatchJob *__restrict__ jobs, int njobs, BatchOut *outs)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= njobs) return;
+    BatchOut z;
+    memset(&z, 0, sizeof(z));
+    outs[jobs[k].slot] = z;
 }
 
 // After `nsweeps` more sweeps of every active slot: the reference's check (boundary flux,
@@ -203,7 +213,7 @@ k_batch_check(BatchGeom g, BatchStages stages, BatchSlot *slots, BatchOut *outs,
         }
         S.iter = it;
         if (stop || it >= st.max_iter) {
-            BatchOut *o = outs + S.image;
+            BatchOut *o = outs + slot;
             o->iters[S.stage] = it;
             o->stage_deff_raw[S.stage] = S.deff_new;
             if (!st.precond) { o->deff_raw = S.deff_new; o->conv = S.conv; }   // cuh:1309-1311 vs cuh:1144-1159
@@ -242,6 +252,10 @@ struct BatchState {
     DevBuf<int> ff_flags;
     int *h_ff_flags = nullptr;
     size_t h_ff_flags_cap = 0;
+    uint8_t *h_in = nullptr;              // pinned staging of the images of one refill
+    size_t h_in_cap = 0;
+    BatchOut *h_out = nullptr;            // pinned: the record of one finished slot
+    size_t h_out_cap = 0;
     BatchSlot *h_slots = nullptr;
     BatchJob *h_jobs = nullptr;
     int *h_active = nullptr;
@@ -295,6 +309,8 @@ void batch_destroy(deff2d_ctx *c)
     if (b->tiles.p) cudaFree(b->tiles.p);
     if (b->ff_flags.p) cudaFree(b->ff_flags.p);
     if (b->h_ff_flags) cudaFreeHost(b->h_ff_flags);
+    if (b->h_in) cudaFreeHost(b->h_in);
+    if (b->h_out) cudaFreeHost(b->h_out);
     if (b->h_slots) cudaFreeHost(b->h_slots);
     if (b->h_jobs) cudaFreeHost(b->h_jobs);
     if (b->h_active) cudaFreeHost(b->h_active);
@@ -366,9 +382,15 @@ void batch_tile_list(int64_t Nx, int64_t Ny, int GX, const int *active, int nact
             if (mark[(size_t)ty * tiles_x + tx]) out.push_back(((uint32_t)ty << 16) | (uint32_t)tx);
 }
 
-static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int H, const deff2d_params *p,
-                       deff2d_result *results, double *fields, const BatchStages &stages, const double *stageD,
-                       int nstages)
+// The packed batch solve as a stream: images are pulled through `fetch` when a slot is free and every finished image
+// is handed to `done` at once -- the caller can decode ahead on its own threads while the GPU sweeps, and write each
+// result row when it exists (the reference keeps all rows until the end, cuh:2051).
+//   fetch(user, k, dst, wait): W*H pixels of image k into dst.  0 ok; 1 not ready yet (only when wait == 0: the
+//       solve goes on with the slots it has); 2 no image k and none after it (the batch ends at k); < 0 error.
+//   done(user, k, result, field): image k is finished; field: NULL or its concentration map.  Non-zero aborts.
+static int batch_stream(deff2d_ctx *c, int count, int W, int H, const deff2d_params *p, deff2d_batch_fetch_fn fetch,
+                        deff2d_batch_done_fn done, void *user, bool want_fields, const BatchStages &stages,
+                        const double *stageD, int nstages, int *solved)
 {
     CUB(cudaSetDevice(c->device));                       // before anything is created: the caller's thread may sit on another device
     BatchState *b = static_cast<BatchState *>(c->batch);
@@ -389,42 +411,13 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
                                                          // per-tile weight gather best at depth 6 (measured 424 / 436 / 452 / 422 GLUP/s at T = 4 / 5 / 6 / 8)
     if (const char *e = std::getenv("DEFF2D_BATCH_T")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) T = v; }   // tuning
 
-    // ---- FloodFill (cuh:557-713): PathFlag always, pinned mask in 3-phase.  On the device after the upload below
-    //      (all images of the chunk in the same launches, floodfill.cu); on host threads with deff2d_set_floodfill(ctx, 1)
-    std::vector<int> pathflag((size_t)count, 0);
-    std::vector<uint8_t> masks;
+    // FloodFill (cuh:557-713): PathFlag always, pinned mask in 3-phase.  On the device, all images of a refill in the
+    // same launches (floodfill.cu); on the host with deff2d_set_floodfill(ctx, 1)
     const bool strict = p->strict_reference != 0;        // see domain_load_impl (context.cu)
     const int ff_thr = (nphase == 3) ? 200 : (strict ? 150 : 149);        // cuh:1368, cuh:1695
     const bool ff_host = c->floodfill_mode == 1 || Nx < 2;
-    if (ff_host) {
-        if (nphase == 3) masks.resize((size_t)count * cells);
-        std::atomic<int> next(0);
-        const int nthreads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
-        auto work = [&]() {
-            std::vector<uint8_t> local;
-            for (;;) {
-                const int k = next.fetch_add(1);
-                if (k >= count) break;
-                uint8_t *g = nullptr;
-                if (nphase == 3) g = masks.data() + (size_t)k * cells;
-                else { local.resize((size_t)cells); g = local.data(); }
-                const uint8_t *src = gray + npix * k;
-                for (int64_t i = 0; i < Ny; i++) {
-                    const uint8_t *srow = src + (size_t)(i / p->amp_y) * W;
-                    uint8_t *gr = g + (size_t)i * Nx;
-                    for (int64_t j = 0; j < Nx; j++) gr[j] = srow[j / p->amp_x] > ff_thr;
-                }
-                pathflag[(size_t)k] = floodfill(g, Nx, Ny, strict);
-            }
-        };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nthreads && t < count; t++) pool.emplace_back(work);
-        work();
-        for (auto &t : pool) t.join();
-    }
 
     // ---- resident stack -----------------------------------------------------------------------
-    CUB(cudaSetDevice(c->device));
     c->loaded = false;
     c->slab_domain = false;
     c->halo_above = c->halo_below = 0;
@@ -439,6 +432,7 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     c->CL = p->CL; c->CR = p->CR;
     c->omega = (p->omega > 0) ? p->omega : 2.0 / 3.0;
     c->check_every = (p->check_every > 0) ? p->check_every : 10000;
+    c->solver = 0;
     c->cur = 0;
     const size_t stack_cells = (size_t)c->rows * (size_t)c->pitch;
     int rc;
@@ -457,38 +451,25 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
     };
     if ((rc = grow(c->x[0], stack_cells)) || (rc = grow(c->x[1], stack_cells)) || (rc = grow(c->code, stack_cells)) ||
         (rc = grow(c->idx16, stack_cells))) return rc;
-    if ((rc = grow(c->img, npix * count))) return rc;
-    // FloodFill states: all images at once in 3-phase (they become the pinned masks); in 2-phase only PathFlag is
-    // needed, so the images go through a bounded scratch group by group
-    const int ff_group = (nphase == 3) ? count : (int)std::max<int64_t>(1, std::min<int64_t>(count, ((int64_t)256 << 20) / cells));
-    if ((nphase == 3 || !ff_host) && (rc = grow(c->grid, (size_t)cells * (nphase == 3 ? count : ff_group)))) return rc;
+    // staging of one refill (at most every slot at once): source images and their FloodFill states / pinned masks
+    if ((rc = grow(c->img, npix * (size_t)nslots)) || (rc = grow(c->grid, (size_t)cells * (size_t)nslots))) return rc;
     if ((rc = grow(c->lut, (size_t)nstages * DEFF2D_LUT_ENTRIES * 4)) || (rc = grow(c->dead, (size_t)nstages * DEFF2D_LUT_ENTRIES)) ||
         (rc = grow(c->clut, (size_t)nstages * DEFF2D_CLUT_ENTRIES * 4))) return rc;
     c->lut_stages = nstages;
-    if (fields && (rc = grow(c->dense, (size_t)cells))) return rc;
-    if ((rc = dev_ensure(c, b->slots, (size_t)nslots)) || (rc = dev_ensure(c, b->outs, (size_t)count)) ||
-        (rc = dev_ensure(c, b->jobs, (size_t)nslots)) || (rc = dev_ensure(c, b->active, (size_t)nslots))) return rc;
+    if (want_fields && (rc = grow(c->dense, (size_t)cells))) return rc;
+    if ((rc = dev_ensure(c, b->slots, (size_t)nslots)) || (rc = dev_ensure(c, b->outs, (size_t)nslots)) ||
+        (rc = dev_ensure(c, b->jobs, (size_t)nslots)) || (rc = dev_ensure(c, b->active, (size_t)nslots)) ||
+        (rc = dev_ensure(c, b->ff_flags, (size_t)std::min(nslots, 32768) + 1))) return rc;
     if ((rc = host_ensure(c, b->h_slots, b->h_slots_cap, (size_t)nslots)) || (rc = host_ensure(c, b->h_jobs, b->h_jobs_cap, (size_t)nslots)) ||
-        (rc = host_ensure(c, b->h_active, b->h_active_cap, (size_t)nslots))) return rc;
+        (rc = host_ensure(c, b->h_active, b->h_active_cap, (size_t)nslots)) ||
+        (rc = host_ensure(c, b->h_ff_flags, b->h_ff_flags_cap, (size_t)std::min(nslots, 32768) + 1)) ||
+        (rc = host_ensure(c, b->h_in, b->h_in_cap, npix * (size_t)nslots)) || (rc = host_ensure(c, b->h_out, b->h_out_cap, 1))) return rc;
 
     cudaStream_t s = c->stream;
     CUB(cudaMemsetAsync(c->x[0].p, 0, stack_cells * sizeof(double), s));
     CUB(cudaMemsetAsync(c->x[1].p, 0, stack_cells * sizeof(double), s));
     CUB(cudaMemsetAsync(c->code.p, DEFF2D_PHASE_GHOST, stack_cells, s));
     CUB(cudaMemsetAsync(b->slots.p, 0, (size_t)nslots * sizeof(BatchSlot), s));
-    CUB(cudaMemsetAsync(b->outs.p, 0, (size_t)count * sizeof(BatchOut), s));
-    CUB(cudaMemcpyAsync(c->img.p, gray, npix * count, cudaMemcpyHostToDevice, s));
-    if (nphase == 3 && ff_host) CUB(cudaMemcpyAsync(c->grid.p, masks.data(), (size_t)cells * count, cudaMemcpyHostToDevice, s));
-    if (!ff_host) {
-        const int per_call = std::min(ff_group, 32768);
-        if ((rc = dev_ensure(c, b->ff_flags, (size_t)per_call + 1)) || (rc = host_ensure(c, b->h_ff_flags, b->h_ff_flags_cap, (size_t)per_call + 1))) return rc;
-        for (int k0 = 0; k0 < count; k0 += per_call) {
-            const int nk = std::min(per_call, count - k0);
-            uint8_t *st = (nphase == 3) ? c->grid.p + (size_t)k0 * cells : c->grid.p;
-            if ((rc = floodfill_device_batch(c, c->img.p + (size_t)k0 * npix, W, H, p->amp_x, p->amp_y, ff_thr, st, Nx, Ny, nk,
-                                             b->ff_flags.p, b->h_ff_flags, pathflag.data() + k0, nullptr, strict))) return rc;
-        }
-    }
     {
         std::vector<double> lut((size_t)nstages * DEFF2D_LUT_ENTRIES * 4);
         std::vector<uint8_t> dead((size_t)nstages * DEFF2D_LUT_ENTRIES);
@@ -530,49 +511,93 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
 
     std::vector<int> slot_image((size_t)nslots, -1);     // host mirror: image in each slot (-1 empty)
     std::vector<long long> slot_iter((size_t)nslots, 0);
-    std::vector<int> slot_stage((size_t)nslots, 0);
-    std::vector<double> solve_ms((size_t)count, 0.0), total_ms((size_t)count, 0.0);
-    std::vector<uint8_t> mark;
+    std::vector<int> slot_stage((size_t)nslots, 0), slot_pathflag((size_t)nslots, 0);
+    std::vector<double> slot_solve_ms((size_t)nslots, 0.0), slot_total_ms((size_t)nslots, 0.0);
+    std::vector<uint8_t> mark, host_mask;
     std::vector<uint32_t> tl;
+    std::vector<double> field_host;
+    if (want_fields) field_host.resize((size_t)cells);
     int next_image = 0, nactive = 0, done_images = 0;
     bool active_changed = true;
     c->tblock = T;
     // measured on 256 x 256 images: 595-643 GLUP/s cluster-resident against 695 with the tiled kernel, so packed batches
     // only go cluster-resident on request (deff2d_set_resident(ctx, 2))
     const bool use_resident = c->resident_mode == 2 && resident_eligible(c, Nx, Ny);
-    auto restore = [&]() {
-        c->tile_family = old_family; c->tblock = old_tblock;
-        c->tile_list = nullptr; c->tile_count = 0;
-    };
 
     while (done_images < count) {
-        // ---- refill empty slots from the queue ------------------------------------------------
-        int njobs = 0;
-        for (int sl = 0; sl < nslots && next_image < count; sl++)
-            if (slot_image[(size_t)sl] < 0) {
-                b->h_jobs[njobs].slot = sl;
-                b->h_jobs[njobs].image = next_image;
-                slot_image[(size_t)sl] = next_image;
-                slot_iter[(size_t)sl] = 0;
-                slot_stage[(size_t)sl] = 0;
-                next_image++;
-                njobs++;
-                active_changed = true;
-            }
+        // ---- refill empty slots from the stream ------------------------------------------------
+        int njobs = 0, in_flight = 0;
+        for (int sl = 0; sl < nslots; sl++) if (slot_image[(size_t)sl] >= 0) in_flight++;
+        for (int sl = 0; sl < nslots && next_image < count; sl++) {
+            if (slot_image[(size_t)sl] >= 0) continue;
+            const int fr = fetch(user, next_image, b->h_in + npix * (size_t)njobs, (in_flight + njobs == 0) ? 1 : 0);
+            if (fr == 1) break;                              // not decoded yet: go on sweeping what is resident
+            if (fr == 2) { count = next_image; break; }      // the stream ends here
+            if (fr != 0) { set_error(c, "packed batch: image %d could not be fetched (%d)", next_image, fr); return fr < 0 ? fr : DEFF2D_ERR_IO; }
+            b->h_jobs[njobs].slot = sl;
+            b->h_jobs[njobs].image = next_image;
+            b->h_jobs[njobs].src = njobs;
+            b->h_jobs[njobs].pad = 0;
+            slot_image[(size_t)sl] = next_image;
+            slot_iter[(size_t)sl] = 0;
+            slot_stage[(size_t)sl] = 0;
+            slot_solve_ms[(size_t)sl] = slot_total_ms[(size_t)sl] = 0;
+            next_image++;
+            njobs++;
+            active_changed = true;
+        }
         if (njobs) {
+            CUB(cudaMemcpyAsync(c->img.p, b->h_in, npix * (size_t)njobs, cudaMemcpyHostToDevice, s));
+            if (ff_host) {
+                host_mask.resize((size_t)cells * (size_t)njobs);
+                std::atomic<int> next(0);
+                const int nthreads = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+                auto work = [&]() {
+                    for (;;) {
+                        const int k = next.fetch_add(1);
+                        if (k >= njobs) break;
+                        uint8_t *gm = host_mask.data() + (size_t)k * cells;
+                        const uint8_t *src = b->h_in + npix * (size_t)k;
+                        for (int64_t i = 0; i < Ny; i++) {
+                            const uint8_t *srow = src + (size_t)(i / p->amp_y) * W;
+                            uint8_t *gr = gm + (size_t)i * Nx;
+                            for (int64_t j = 0; j < Nx; j++) gr[j] = srow[j / p->amp_x] > ff_thr;
+                        }
+                        slot_pathflag[(size_t)b->h_jobs[k].slot] = floodfill(gm, Nx, Ny, strict);
+                    }
+                };
+                std::vector<std::thread> pool;
+                for (int t = 1; t < nthreads && t < njobs; t++) pool.emplace_back(work);
+                work();
+                for (auto &t : pool) t.join();
+                if (nphase == 3) CUB(cudaMemcpyAsync(c->grid.p, host_mask.data(), (size_t)cells * (size_t)njobs, cudaMemcpyHostToDevice, s));
+            } else {
+                std::vector<int> pf((size_t)njobs, 0);
+                for (int k0 = 0; k0 < njobs; k0 += 32768) {
+                    const int nk = std::min(32768, njobs - k0);
+                    if ((rc = floodfill_device_batch(c, c->img.p + (size_t)k0 * npix, W, H, p->amp_x, p->amp_y, ff_thr,
+                                                     c->grid.p + (size_t)k0 * cells, Nx, Ny, nk, b->ff_flags.p, b->h_ff_flags,
+                                                     pf.data() + k0, nullptr, strict))) return rc;
+                }
+                for (int k = 0; k < njobs; k++) slot_pathflag[(size_t)b->h_jobs[k].slot] = pf[(size_t)k];
+            }
             CUB(cudaMemcpyAsync(b->jobs.p, b->h_jobs, (size_t)njobs * sizeof(BatchJob), cudaMemcpyHostToDevice, s));
+            k_batch_clear<<<(njobs + 255) / 256, 256, 0, s>>>(b->jobs.p, njobs, b->outs.p);
             int bx = (int)std::min<int64_t>(((Ny + 2) * (Nx + 2) + 255) / 256, 64);
             k_batch_init<<<dim3((unsigned)bx, (unsigned)njobs), 256, 0, s>>>(g, b->jobs.p, c->img.p, nphase == 3 ? c->grid.p : nullptr,
                                                                             c->x[c->cur].p, c->x[c->cur ^ 1].p, c->code.p,
                                                                             b->slots.p, b->outs.p);
-            // the table indices of the new images (and of their neighbours' shared ghost ring)
+            // the table indices of the new images (and of their neighbours' shared ghost ring); the whole stack is
+            // rebuilt -- 3 B per cell, once per refill, against >= 10 000 sweeps between refills
             launch_build_idx(s, c->code.p, c->idx16.p, c->Nx, c->Ny, c->pitch, c->ghost_period, nphase);
-            c->launches += 2;
+            c->launches += 3;
+            CUB(cudaStreamSynchronize(s));                   // the staging buffer is free for the next refill
         }
         if (active_changed) {
             nactive = 0;
             for (int sl = 0; sl < nslots; sl++)
                 if (slot_image[(size_t)sl] >= 0) b->h_active[nactive++] = sl;
+            if (nactive == 0) break;                         // the stream ended (fetch returned 2) and nothing is resident
             CUB(cudaMemcpyAsync(b->active.p, b->h_active, (size_t)nactive * sizeof(int), cudaMemcpyHostToDevice, s));
             size_t off = 0;
             for (int t = 1; t <= T; t++) {
@@ -588,7 +613,6 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
         // ---- sweeps up to the next event of any active image (check or MaxIter) ---------------
         long long n = -1;
         const long long ce = c->check_every;
-        int npre = 0;
         for (int a = 0; a < nactive; a++) {
             const int sl = b->h_active[a];
             const long long it = slot_iter[(size_t)sl];
@@ -597,17 +621,16 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
             const long long to_max = st.max_iter - it;
             const long long m = std::min(to_check, to_max);
             if (n < 0 || m < n) n = m;
-            if (st.precond) npre++;
         }
-        if (n < 1) { restore(); set_error(c, "packed batch: internal scheduling error"); return DEFF2D_ERR_STATE; }
+        if (n < 1) { set_error(c, "packed batch: internal scheduling error"); return DEFF2D_ERR_STATE; }
         CUB(cudaEventRecord(b->e0, s));
         if (use_resident) {
             // images of up to 256 x 256 cells: one cluster per image keeps it on chip for all n sweeps (resident.cu)
-            if ((rc = resident_sweeps(c, n, Nx, Ny, GX, b->active.p, nactive))) { restore(); return rc; }
+            if ((rc = resident_sweeps(c, n, Nx, Ny, GX, b->active.p, nactive))) return rc;
         } else {
-            if (n >= T && (rc = tma_passes(c, T, n / T, b->tiles.p + tile_off[T], tile_cnt[T]))) { restore(); return rc; }
+            if (n >= T && (rc = tma_passes(c, T, n / T, b->tiles.p + tile_off[T], tile_cnt[T]))) return rc;
             if (const int t = (int)(n % T)) {
-                if ((rc = tma_pass(c, t, b->tiles.p + tile_off[t], tile_cnt[t], s))) { restore(); return rc; }
+                if ((rc = tma_pass(c, t, b->tiles.p + tile_off[t], tile_cnt[t], s))) return rc;
                 c->cur ^= 1;
             }
         }
@@ -618,7 +641,7 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
         CUB(cudaStreamSynchronize(s));
         {
             cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) { restore(); set_error(c, "packed batch launch failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
+            if (e != cudaSuccess) { set_error(c, "packed batch launch failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
         }
         float ms = 0;
         CUB(cudaEventElapsedTime(&ms, b->e0, b->e1));
@@ -626,73 +649,98 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
         // reference's `Time` only the non-PreCond stages count towards solve_ms (cuh:1311)
         for (int a = 0; a < nactive; a++) {
             const int sl = b->h_active[a];
-            const int im = slot_image[(size_t)sl];
-            total_ms[(size_t)im] += ms / nactive;
-            if (!stages.s[slot_stage[(size_t)sl]].precond) solve_ms[(size_t)im] += ms / nactive;
+            slot_total_ms[(size_t)sl] += ms / nactive;
+            if (!stages.s[slot_stage[(size_t)sl]].precond) slot_solve_ms[(size_t)sl] += ms / nactive;
         }
-        // ---- adopt the device's decisions -------------------------------------------------------
+        // ---- adopt the device's decisions; finished images leave at once -------------------------
         for (int a = 0; a < nactive; a++) {
             const int sl = b->h_active[a];
             const BatchSlot &S = b->h_slots[sl];
             slot_iter[(size_t)sl] = S.iter;
             slot_stage[(size_t)sl] = S.stage;
-            if (S.status == 2) {
-                const int im = slot_image[(size_t)sl];
-                if (fields) {
-                    DomainView v = view(c);
-                    const int gx = sl % GX, gy = sl / GX;
-                    const int64_t off = ((int64_t)gy * (Ny + 1)) * c->pitch + (int64_t)gx * (Nx + 1);
-                    v.x_in += off; v.code += off;
-                    v.Nx = Nx; v.Ny = Ny;
-                    launch_extract_field(s, v, c->dense.p);
-                    c->launches++;
-                    CUB(cudaMemcpyAsync(fields + (size_t)im * cells, c->dense.p, (size_t)cells * sizeof(double), cudaMemcpyDeviceToHost, s));
-                    CUB(cudaStreamSynchronize(s));
+            if (S.status != 2) continue;
+            const int im = slot_image[(size_t)sl];
+            CUB(cudaMemcpyAsync(b->h_out, b->outs.p + sl, sizeof(BatchOut), cudaMemcpyDeviceToHost, s));
+            if (want_fields) {
+                DomainView v = view(c);
+                const int gx = sl % GX, gy = sl / GX;
+                const int64_t off = ((int64_t)gy * (Ny + 1)) * c->pitch + (int64_t)gx * (Nx + 1);
+                v.x_in += off; v.code += off;
+                v.Nx = Nx; v.Ny = Ny;
+                launch_extract_field(s, v, c->dense.p);
+                c->launches++;
+                CUB(cudaMemcpyAsync(field_host.data(), c->dense.p, (size_t)cells * sizeof(double), cudaMemcpyDeviceToHost, s));
+            }
+            CUB(cudaStreamSynchronize(s));
+            const BatchOut &o = *b->h_out;
+            deff2d_result r;
+            std::memset(&r, 0, sizeof(r));
+            r.n_cells = cells;
+            r.pathflag = slot_pathflag[(size_t)sl];
+            if (nphase == 2) r.porosity = accumulate_fraction((int64_t)o.below150, (int64_t)npix);       // cuh:397-405
+            else {                                                                                       // calcFracts3D, cuh:411-448 (quirk Q21)
+                int64_t ns = 0, nl = 0;
+                const double Dfin[3] = {p->Df, p->Ds, p->Dg};
+                for (int ph = 0; ph < 3; ph++) {
+                    if (Dfin[ph] == p->Ds) ns += (int64_t)o.phase[ph];
+                    else if (Dfin[ph] == p->Df) nl += (int64_t)o.phase[ph];
                 }
-                slot_image[(size_t)sl] = -1;
-                done_images++;
-                active_changed = true;
+                r.SVF = accumulate_fraction(ns, cells);
+                r.LVF = accumulate_fraction(nl, cells);
             }
+            r.nstages = o.nstages;
+            for (int st = 0; st < o.nstages && st < DEFF2D_MAX_STAGES; st++) {
+                r.iters[st] = o.iters[st];
+                r.stage_deff_raw[st] = o.stage_deff_raw[st];
+                r.stage_D[st] = stageD[st];
+                r.total_iters += o.iters[st];
+            }
+            r.deff_raw = o.deff_raw;
+            r.conv = o.conv;
+            r.deff = o.deff_raw / p->Df;                        // cuh:2017, cuh:2370
+            r.last_df = p->Df;
+            r.solve_ms = slot_solve_ms[(size_t)sl];
+            r.total_ms = slot_total_ms[(size_t)sl];
+            if (done && done(user, im, &r, want_fields ? field_host.data() : nullptr)) {
+                set_error(c, "packed batch: aborted by the result callback at image %d", im);
+                return DEFF2D_ERR_STATE;
+            }
+            slot_image[(size_t)sl] = -1;
+            done_images++;
+            active_changed = true;
         }
     }
-    restore();
-
-    // ---- results -----------------------------------------------------------------------------------
-    std::vector<BatchOut> outs((size_t)count);
-    CUB(cudaMemcpyAsync(outs.data(), b->outs.p, (size_t)count * sizeof(BatchOut), cudaMemcpyDeviceToHost, s));
-    CUB(cudaStreamSynchronize(s));
-    for (int k = 0; k < count; k++) {
-        deff2d_result *r = results + k;
-        const BatchOut &o = outs[(size_t)k];
-        std::memset(r, 0, sizeof(*r));
-        r->n_cells = cells;
-        r->pathflag = pathflag[(size_t)k];
-        if (nphase == 2) r->porosity = accumulate_fraction((int64_t)o.below150, (int64_t)npix);     // cuh:397-405
-        else {                                                                                      // calcFracts3D, cuh:411-448 (quirk Q21)
-            int64_t ns = 0, nl = 0;
-            const double Dfin[3] = {p->Df, p->Ds, p->Dg};
-            for (int ph = 0; ph < 3; ph++) {
-                if (Dfin[ph] == p->Ds) ns += (int64_t)o.phase[ph];
-                else if (Dfin[ph] == p->Df) nl += (int64_t)o.phase[ph];
-            }
-            r->SVF = accumulate_fraction(ns, cells);
-            r->LVF = accumulate_fraction(nl, cells);
-        }
-        r->nstages = o.nstages;
-        for (int st = 0; st < o.nstages && st < DEFF2D_MAX_STAGES; st++) {
-            r->iters[st] = o.iters[st];
-            r->stage_deff_raw[st] = o.stage_deff_raw[st];
-            r->stage_D[st] = stageD[st];
-            r->total_iters += o.iters[st];
-        }
-        r->deff_raw = o.deff_raw;
-        r->conv = o.conv;
-        r->deff = o.deff_raw / p->Df;                        // cuh:2017, cuh:2370
-        r->last_df = p->Df;
-        r->solve_ms = solve_ms[(size_t)k];
-        r->total_ms = total_ms[(size_t)k];
-    }
+    if (solved) *solved = done_images;
     return DEFF2D_OK;
+}
+
+struct ArrayStream { const uint8_t *gray; size_t npix, ncell; deff2d_result *results; double *fields; };
+
+static int array_fetch(void *user, int k, uint8_t *dst, int)
+{
+    const ArrayStream *a = static_cast<const ArrayStream *>(user);
+    std::memcpy(dst, a->gray + a->npix * (size_t)k, a->npix);
+    return 0;
+}
+
+static int array_done(void *user, int k, const deff2d_result *r, const double *field)
+{
+    const ArrayStream *a = static_cast<const ArrayStream *>(user);
+    a->results[k] = *r;
+    if (a->fields && field) std::memcpy(a->fields + a->ncell * (size_t)k, field, a->ncell * sizeof(double));
+    return 0;
+}
+
+static bool batch_covers(const deff2d_params *p, int count, int W, int H, BatchStages *stages, double *stageD, int *nstages)
+{
+    if (count < 2 || W < 1 || H < 1 || p->amp_x < 1 || p->amp_y < 1) return false;
+    if (p->verbose == 1) return false;              // keep the reference's per-image stdout order
+    if (p->residual_tol > 0 || p->solver != 0) return false;   // non-parity stop rule / solver: per-image path
+    std::memset(stages, 0, sizeof(*stages));
+    if (build_stages(p, stages, stageD, nstages)) return false;
+    const int64_t Nx = (int64_t)W * p->amp_x, Ny = (int64_t)H * p->amp_y;
+    if (Nx * Ny > ((int64_t)16 << 20)) return false;    // large images fill the machine on their own
+    return true;
 }
 
 // Returns 1 when the packed path does not cover the request (the caller then solves image by
@@ -700,29 +748,41 @@ static int batch_chunk(deff2d_ctx *c, const uint8_t *gray, int count, int W, int
 int batch_resident_solve(deff2d_ctx *c, const uint8_t *gray, int count, int W, int H, const deff2d_params *p,
                          deff2d_result *results, double *fields)
 {
-    if (count < 2 || W < 1 || H < 1 || p->amp_x < 1 || p->amp_y < 1) return 1;
-    if (p->verbose == 1) return 1;                  // keep the reference's per-image stdout order
-    if (p->residual_tol > 0 || p->solver != 0) return 1;   // non-parity stop rule / solver: per-image path
     BatchStages stages;
     double stageD[BATCH_MAX_STAGES];
     int nstages = 0;
-    std::memset(&stages, 0, sizeof(stages));
-    if (build_stages(p, &stages, stageD, &nstages)) return 1;
-    const int64_t Nx = (int64_t)W * p->amp_x, Ny = (int64_t)H * p->amp_y;
-    if (Nx * Ny > ((int64_t)16 << 20)) return 1;    // large images fill the machine on their own
-    // host staging (images, 3-phase masks) is bounded to ~1 GiB per chunk
-    const int64_t per_image = std::max<int64_t>((int64_t)W * H, (p->mode == DEFF2D_MODE_3PH) ? Nx * Ny : 0);
-    int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(count, ((int64_t)1 << 30) / per_image));
-    for (int k0 = 0; k0 < count; k0 += chunk) {
-        const int n = std::min(chunk, count - k0);
-        int rc = batch_chunk(c, gray + (size_t)k0 * W * H, n, W, H, p, results + k0,
-                             fields ? fields + (size_t)k0 * Nx * Ny : nullptr, stages, stageD, nstages);
-        if (rc) return rc;
-    }
-    return DEFF2D_OK;
+    if (!batch_covers(p, count, W, H, &stages, stageD, &nstages)) return 1;
+    ArrayStream a{gray, (size_t)W * H, (size_t)W * H * (size_t)p->amp_x * (size_t)p->amp_y, results, fields};
+    return batch_stream(c, count, W, H, p, array_fetch, array_done, &a, fields != nullptr, stages, stageD, nstages, nullptr);
 }
 
 }  // namespace deff2d
+
+DEFF2D_EXPORT int deff2d_batch_supported(const deff2d_params *p, int W, int H)
+{
+    if (!p) return 0;
+    deff2d::BatchStages stages;
+    double stageD[BATCH_MAX_STAGES];
+    int nstages = 0;
+    return deff2d::batch_covers(p, 2, W, H, &stages, stageD, &nstages) ? 1 : 0;
+}
+
+DEFF2D_EXPORT int deff2d_solve_batch_stream(deff2d_ctx *c, int count, int W, int H, const deff2d_params *p,
+                                            deff2d_batch_fetch_fn fetch, deff2d_batch_done_fn done, void *user,
+                                            int want_fields, int *solved)
+{
+    if (!c || !p || !fetch || count < 0) return DEFF2D_ERR_ARG;
+    if (solved) *solved = 0;
+    if (count == 0) return DEFF2D_OK;
+    deff2d::BatchStages stages;
+    double stageD[BATCH_MAX_STAGES];
+    int nstages = 0;
+    if (!deff2d::batch_covers(p, std::max(count, 2), W, H, &stages, stageD, &nstages)) {
+        deff2d::set_error(c, "solve_batch_stream: these parameters are not covered by the packed batch mode");
+        return DEFF2D_ERR_ARG;
+    }
+    return deff2d::batch_stream(c, count, W, H, p, fetch, done, user, want_fields != 0, stages, stageD, nstages, solved);
+}
 
 DEFF2D_EXPORT int deff2d_batch_plan(int64_t Nx, int64_t Ny, int count, int limit, int *GX, int *GY)
 {

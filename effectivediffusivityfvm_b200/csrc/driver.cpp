@@ -9,6 +9,9 @@
 #include <iostream>
 #include <atomic>
 #include <string>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -115,102 +118,174 @@ DEFF2D_EXPORT int deff2d_run_input_file(deff2d_ctx *ctx, const char *path)
         }
         return rc;
     }
-    // BatchSim (cuh:1843-2054) / BatchSim3Phase (cuh:2056-2419): images "%05d.jpg" from 0;
-    // results are written once at the end (cuh:2051); only the 3-phase batch writes
-    // per-image CMAP_%05d.csv files (cuh:2395-2398, quirk Q17).
-    std::vector<deff2d_result> results((size_t)std::max(in.num_images, 0));
+    // BatchSim (cuh:1843-2054) / BatchSim3Phase (cuh:2056-2419): images "%05d.jpg" from 0.  The reference decodes,
+    // solves and keeps every row until the end (cuh:2051: a crash loses the whole batch, doc 3.6).  Here host threads
+    // decode ahead while the GPU sweeps, equally sized images are solved PACKED (many per launch, batch.cu) through
+    // the streaming call, every result row is appended as soon as it and all rows before it exist (same file, same
+    // order), and the 3-phase CMAP_%05d.csv of an image (cuh:2395-2398; quirk Q17: 2-phase batches write none) is
+    // written when that image finishes.  `Devices: N` (ignored by the reference parser, cuh:261-311) splits the
+    // images over N GPUs with no communication.
+    const int N = std::max(in.num_images, 0);
     const bool cmap = (in.nphase == 3 && in.print_cmap == 1);
-    // Decode every image first (decoding overlaps nothing here, but it decides the path): a batch of
-    // equally sized images without per-image verbose output is solved PACKED -- all images resident
-    // at once, many per launch (batch.cu) -- and, with the optional `Devices: N` key (ignored by the
-    // reference parser, cuh:261-311), split over N GPUs with no communication.
-    std::vector<uint8_t> packed;
-    int W0 = 0, H0 = 0;
-    bool uniform = in.num_images > 0;
-    std::vector<std::vector<uint8_t>> singles((size_t)std::max(in.num_images, 0));
-    std::vector<int> Ws((size_t)std::max(in.num_images, 0), 0), Hs(Ws), chs(Ws), rcs_load(Ws);
-    {
-        // decode on the host threads (file order is kept: slot k belongs to "%05d.jpg" % k)
-        std::atomic<int> next(0);
-        auto load = [&]() {
-            for (;;) {
-                const int k = next.fetch_add(1);
-                if (k >= in.num_images) break;
-                char name[100];
-                std::snprintf(name, sizeof(name), "%05d.jpg", k);   // cuh:1876
-                uint8_t *gray = nullptr;
-                rcs_load[(size_t)k] = deff2d_load_image(name, &gray, &Ws[(size_t)k], &Hs[(size_t)k], &chs[(size_t)k]);
-                if (!rcs_load[(size_t)k] && chs[(size_t)k] == 1) singles[(size_t)k].assign(gray, gray + (size_t)Ws[(size_t)k] * Hs[(size_t)k]);
-                deff2d_free(gray);
+    struct Decoded {
+        std::vector<uint8_t> px;
+        int W = 0, H = 0, ch = 0, rc = 0;
+        int state = 0;                       // 0 pending, 1 decoded
+    };
+    std::vector<Decoded> dec((size_t)N);
+    std::mutex mtx;
+    std::condition_variable cv;
+    std::atomic<int> next_decode(0);
+    auto decode_worker = [&]() {
+        for (;;) {
+            const int k = next_decode.fetch_add(1);                 // in file order: slot k belongs to "%05d.jpg" % k
+            if (k >= N) break;
+            char name[100];
+            std::snprintf(name, sizeof(name), "%05d.jpg", k);       // cuh:1876
+            uint8_t *gray = nullptr;
+            Decoded d;
+            d.rc = deff2d_load_image(name, &gray, &d.W, &d.H, &d.ch);
+            if (!d.rc && d.ch == 1) d.px.assign(gray, gray + (size_t)d.W * d.H);
+            deff2d_free(gray);
+            d.state = 1;
+            {
+                std::lock_guard<std::mutex> lk(mtx);
+                dec[(size_t)k] = std::move(d);
             }
-        };
+            cv.notify_all();
+        }
+    };
+    std::vector<std::thread> decoders;
+    {
         const int nt = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nt && t < in.num_images; t++) pool.emplace_back(load);
-        load();
-        for (auto &t : pool) t.join();
+        for (int t = 0; t < nt && t < N; t++) decoders.emplace_back(decode_worker);
     }
-    for (int k = 0; k < in.num_images; k++) {
-        if (rcs_load[(size_t)k]) { std::printf("Error: could not read image %05d.jpg\n", k); return rcs_load[(size_t)k]; }
-        if (chs[(size_t)k] != 1) {
-            std::printf("Error: please enter a grascale image with 1 channel.\n Current number of channels = %d\n", chs[(size_t)k]);
+    struct JoinAll { std::vector<std::thread> &v; ~JoinAll() { for (auto &t : v) if (t.joinable()) t.join(); } } join_guard{decoders};
+    auto wait_decoded = [&](int k) {
+        std::unique_lock<std::mutex> lk(mtx);
+        cv.wait(lk, [&] { return dec[(size_t)k].state != 0; });
+    };
+    auto check_image = [&](int k) -> int {                          // the reference's own input checks, per image
+        const Decoded &d = dec[(size_t)k];
+        if (d.rc) { std::printf("Error: could not read image %05d.jpg\n", k); return d.rc; }   // reference: NULL deref (Q24)
+        if (d.ch != 1) {                                            // cuh:1886-1889
+            std::printf("Error: please enter a grascale image with 1 channel.\n Current number of channels = %d\n", d.ch);
             return DEFF2D_ERR_ARG;
         }
-        if (k == 0) { W0 = Ws[0]; H0 = Hs[0]; }
-        if (Ws[(size_t)k] != W0 || Hs[(size_t)k] != H0) uniform = false;
-    }
-    if (uniform && in.p.verbose != 1 && in.num_images >= 2) {
-        const size_t npix = (size_t)W0 * H0, ncell = npix * (size_t)in.p.amp_x * (size_t)in.p.amp_y;
-        packed.resize(npix * (size_t)in.num_images);
-        for (int k = 0; k < in.num_images; k++) std::memcpy(packed.data() + npix * k, singles[(size_t)k].data(), npix);
-        singles.clear();
-        std::vector<double> fields;
-        if (cmap) fields.resize(ncell * (size_t)in.num_images);
-        // one context per device; device 0 is the caller's
+        return DEFF2D_OK;
+    };
+
+    // rows leave in image order as soon as the prefix is complete
+    std::vector<deff2d_result> results((size_t)N);
+    std::vector<char> have((size_t)N, 0);
+    int next_row = 0, io_rc = 0;
+    std::mutex out_mtx;
+    if ((rc = deff2d_append_csv_batch_row(&in, -1, nullptr))) return rc;       // header (cuh:209, cuh:224)
+    auto finish_image = [&](int k, const deff2d_result *r, const double *field, int W, int H) -> int {
+        std::lock_guard<std::mutex> lk(out_mtx);
+        results[(size_t)k] = *r;
+        have[(size_t)k] = 1;
+        if (cmap && field) {
+            char cm[100];
+            std::snprintf(cm, sizeof(cm), "CMAP_%05d.csv", k);      // cuh:2396
+            const int e = deff2d_write_cmap(cm, field, (int64_t)W * in.p.amp_x, (int64_t)H * in.p.amp_y);
+            if (e && !io_rc) io_rc = e;
+        }
+        while (next_row < N && have[(size_t)next_row]) {
+            const int e = deff2d_append_csv_batch_row(&in, next_row, &results[(size_t)next_row]);
+            if (e && !io_rc) io_rc = e;
+            next_row++;
+        }
+        return io_rc;
+    };
+
+    int first_unsolved = 0;
+    if (N >= 2 && in.p.verbose != 1) {
+        wait_decoded(0);
+        if ((rc = check_image(0))) return rc;
+        const int W0 = dec[0].W, H0 = dec[0].H;
+        // one context per device; device 0 is the caller's.  Each device streams a contiguous block of images.
         std::vector<deff2d_ctx *> ctxs{ctx};
-        for (int d = 1; d < in.devices && d < in.num_images; d++) {
+        for (int d = 1; d < in.devices && d < N; d++) {
             deff2d_ctx *cx = nullptr;
             if (deff2d_create(&cx, d) != DEFF2D_OK) break;          // fewer GPUs than asked for: use what is there
             ctxs.push_back(cx);
         }
         const int nd = (int)ctxs.size();
-        std::vector<int> rcs((size_t)nd, 0);
-        std::vector<std::thread> pool;
-        auto work = [&](int d) {
-            const int k0 = (int)((int64_t)in.num_images * d / nd), k1 = (int)((int64_t)in.num_images * (d + 1) / nd);
-            deff2d_params p = in.p;
-            rcs[(size_t)d] = deff2d_solve_batch(ctxs[(size_t)d], packed.data() + npix * k0, k1 - k0, W0, H0, &p, results.data() + k0,
-                                                cmap ? fields.data() + ncell * k0 : nullptr);
+        struct Block {
+            int k0 = 0, k1 = 0, W0 = 0, H0 = 0, end = -1, rc = 0;
+            std::vector<Decoded> *dec = nullptr;
+            std::mutex *mtx = nullptr;
+            std::condition_variable *cv = nullptr;
+            std::function<int(int, const deff2d_result *, const double *)> finish;
+            std::function<int(int)> check;
         };
-        for (int d = 1; d < nd; d++) pool.emplace_back(work, d);
-        work(0);
-        for (auto &t : pool) t.join();
-        for (int d = 1; d < nd; d++) deff2d_destroy(ctxs[(size_t)d]);
-        for (int d = 0; d < nd; d++) if (rcs[(size_t)d]) return rcs[(size_t)d];
-        if (cmap)
-            for (int k = 0; k < in.num_images; k++) {
-                char cm[100];
-                std::snprintf(cm, sizeof(cm), "CMAP_%05d.csv", k);  // cuh:2396
-                if ((rc = deff2d_write_cmap(cm, fields.data() + ncell * k, (int64_t)W0 * in.p.amp_x, (int64_t)H0 * in.p.amp_y))) return rc;
+        std::vector<Block> blocks((size_t)nd);
+        auto fetch = [](void *user, int k, uint8_t *dst, int wait) -> int {
+            Block *b = static_cast<Block *>(user);
+            const int g = b->k0 + k;
+            if (g >= b->k1) return 2;
+            Decoded *d = &(*b->dec)[(size_t)g];
+            {
+                std::unique_lock<std::mutex> lk(*b->mtx);
+                if (d->state == 0) {
+                    if (!wait) return 1;                            // not decoded yet: the GPU goes on with what it has
+                    b->cv->wait(lk, [&] { return d->state != 0; });
+                }
             }
-        return deff2d_write_csv_batch(&in, results.data(), in.num_images);
+            if (d->rc || d->ch != 1) { b->rc = b->check(g); b->end = g; return b->rc ? b->rc : DEFF2D_ERR_IO; }
+            if (d->W != b->W0 || d->H != b->H0) { b->end = g; return 2; }   // another size: the packed run ends here
+            std::memcpy(dst, d->px.data(), d->px.size());
+            std::vector<uint8_t>().swap(d->px);                     // the pixels now live in the library's staging buffer
+            return 0;
+        };
+        auto done = [](void *user, int k, const deff2d_result *r, const double *field) -> int {
+            Block *b = static_cast<Block *>(user);
+            return b->finish(b->k0 + k, r, field);
+        };
+        std::vector<int> rcs((size_t)nd, 0), solved((size_t)nd, 0);
+        auto work = [&](int d) {
+            Block &b = blocks[(size_t)d];
+            b.k0 = (int)((int64_t)N * d / nd); b.k1 = (int)((int64_t)N * (d + 1) / nd);
+            b.W0 = W0; b.H0 = H0; b.dec = &dec; b.mtx = &mtx; b.cv = &cv;
+            b.finish = [&](int k, const deff2d_result *r, const double *f) { return finish_image(k, r, f, W0, H0); };
+            b.check = check_image;
+            deff2d_params p = in.p;
+            rcs[(size_t)d] = deff2d_solve_batch_stream(ctxs[(size_t)d], b.k1 - b.k0, W0, H0, &p, fetch, done, &b, cmap ? 1 : 0, &solved[(size_t)d]);
+        };
+        // parameters the packed mode does not cover (e.g. the non-parity solver) fall through to the per-image loop
+        const bool packed_ok = deff2d_batch_supported(&in.p, W0, H0) == 1;
+        if (packed_ok) {
+            std::vector<std::thread> pool;
+            for (int d = 1; d < nd; d++) pool.emplace_back(work, d);
+            work(0);
+            for (auto &t : pool) t.join();
+            for (int d = 1; d < nd; d++) deff2d_destroy(ctxs[(size_t)d]);
+            for (int d = 0; d < nd; d++) if (rcs[(size_t)d]) return rcs[(size_t)d];
+            if (io_rc) return io_rc;
+            // images a block could not take (another size) and everything behind them: one at a time below
+            first_unsolved = N;
+            for (int d = 0; d < nd; d++)
+                if (blocks[(size_t)d].k0 + solved[(size_t)d] < blocks[(size_t)d].k1) { first_unsolved = std::min(first_unsolved, blocks[(size_t)d].k0 + solved[(size_t)d]); }
+        } else {
+            for (int d = 1; d < nd; d++) deff2d_destroy(ctxs[(size_t)d]);
+        }
     }
     // one image at a time: keeps the reference's per-image stdout order (Verbose: 1) and handles
-    // images of different sizes; every row is appended as soon as its image is solved
-    if ((rc = deff2d_append_csv_batch_row(&in, -1, nullptr))) return rc;
-    for (int k = 0; k < in.num_images; k++) {
-        const int W = Ws[(size_t)k], H = Hs[(size_t)k];
+    // images of different sizes; every row is appended as soon as its image (and all before it) is solved
+    for (int k = first_unsolved; k < N; k++) {
+        if (have[(size_t)k]) continue;
+        wait_decoded(k);
+        if ((rc = check_image(k))) return rc;
+        const int W = dec[(size_t)k].W, H = dec[(size_t)k].H;
         std::vector<double> field;
         if (cmap) field.resize((size_t)W * in.p.amp_x * (size_t)H * in.p.amp_y);
         deff2d_params p = in.p;
-        rc = deff2d_solve_batch(ctx, singles[(size_t)k].data(), 1, W, H, &p, &results[(size_t)k], cmap ? field.data() : nullptr);
+        deff2d_result r;
+        rc = deff2d_solve_batch(ctx, dec[(size_t)k].px.data(), 1, W, H, &p, &r, cmap ? field.data() : nullptr);
         if (rc) return rc;
-        if ((rc = deff2d_append_csv_batch_row(&in, k, &results[(size_t)k]))) return rc;
-        if (cmap) {
-            char cm[100];
-            std::snprintf(cm, sizeof(cm), "CMAP_%05d.csv", k);      // cuh:2396
-            if ((rc = deff2d_write_cmap(cm, field.data(), (int64_t)W * in.p.amp_x, (int64_t)H * in.p.amp_y))) return rc;
-        }
+        if ((rc = finish_image(k, &r, cmap ? field.data() : nullptr, W, H))) return rc;
+        std::vector<uint8_t>().swap(dec[(size_t)k].px);
     }
-    return DEFF2D_OK;
+    return io_rc;
 }

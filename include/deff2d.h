@@ -117,6 +117,25 @@ int deff2d_solve_image(deff2d_ctx *ctx, const uint8_t *gray, int W, int H,
 /* `count` images of identical size packed back to back (count*H*W bytes): the body of
  * BatchSim / BatchSim3Phase (cuh:1867-2049, 2056-2419) for every image.  results: count
  * entries.  fields: NULL or count*(H*amp_y)*(W*amp_x) doubles. */
+/* The packed batch solve as a stream.  Images are pulled through `fetch` whenever a slot of the resident stack is
+ * free, and every finished image is handed to `done` at once: the caller can decode ahead on its own threads while
+ * the GPU sweeps and write each result row when it exists (the reference keeps every row until the end of the batch,
+ * cuh:2051, doc 3.6).  Images finish in any order.
+ *   fetch(user, k, dst, wait): the W*H pixels of image k into dst.  Return 0 = ok; 1 = not ready yet (allowed only
+ *       when wait == 0: the solve goes on with the images it has and asks again); 2 = there is no image k (the batch
+ *       ends at k); < 0 = error.  Images are requested in order k = 0, 1, 2, ...
+ *   done(user, k, result, field): image k is finished; field is NULL or its concentration map (valid during the
+ *       call).  A non-zero return aborts the batch.
+ * count: upper bound on the number of images; *solved (optional): how many were solved.  Parameters outside the
+ * packed mode (verbose = 1, solver / residual_tol, 2-phase single mode) return an argument error. */
+typedef int (*deff2d_batch_fetch_fn)(void *user, int k, uint8_t *dst, int wait);
+typedef int (*deff2d_batch_done_fn)(void *user, int k, const deff2d_result *result, const double *field);
+int deff2d_solve_batch_stream(deff2d_ctx *ctx, int count, int W, int H, const deff2d_params *p,
+                              deff2d_batch_fetch_fn fetch, deff2d_batch_done_fn done, void *user, int want_fields,
+                              int *solved);
+/* 1 if images of W x H pixels with these parameters go through the packed batch mode, 0 if they are solved one at a
+ * time (verbose = 1, solver / residual_tol, 2-phase single mode, images above 16 M cells). */
+int deff2d_batch_supported(const deff2d_params *p, int W, int H);
 int deff2d_solve_batch(deff2d_ctx *ctx, const uint8_t *gray, int count, int W, int H,
                        const deff2d_params *p, deff2d_result *results, double *fields);
 

@@ -696,6 +696,40 @@ def test_stop_rule_at_the_tolerance_boundary(ctx):
         assert rel(got["deff"], ref["deff"]) < DEFF_RTOL_TIGHT
 
 
+def test_packed_batch_stream_late_images_and_early_results(ctx):
+    """deff2d_solve_batch_stream: images that are not ready when a slot frees up are asked for again later (the solve
+    goes on with what is resident), the stream may end before `count`, results arrive as images finish -- and equal
+    the array call's bit for bit."""
+    from effectivediffusivityfvm_b200.datasets import c3_image
+    imgs = np.stack([c3_image(300 + k, 96) for k in range(9)])
+    p = E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH, max_iter=40001, check_every=2000)
+    ctx.set_batch_slots(4)
+    want = ctx.solve_batch(imgs, p, want_fields=True)
+    calls = {"n": 0, "refused": 0}
+    got, order = {}, []
+
+    def fetch(k, wait):
+        calls["n"] += 1
+        if k >= 9:
+            return False                                  # the stream ends before the announced count of 20
+        if not wait and k >= 2 and calls["n"] % 3 != 0:
+            calls["refused"] += 1
+            return None                                   # "still decoding"
+        return imgs[k]
+
+    def done(k, res, field):
+        got[k] = (res, field)
+        order.append(k)
+
+    solved = ctx.solve_batch_stream(20, (96, 96), p, fetch, done, want_fields=True)
+    ctx.set_batch_slots(0)
+    assert solved == 9 and sorted(got) == list(range(9)) and calls["refused"] > 0
+    for k in range(9):
+        a, b = want[k], got[k][0]
+        assert a["iters"] == b["iters"] and a["deff"] == b["deff"] and a["pathflag"] == b["pathflag"] and a["porosity"] == b["porosity"]
+        assert np.array_equal(want[k]["field"], got[k][1])
+
+
 # ----------------------------------------------------------------------------- K5 (cluster-resident) == K3 (streaming)
 
 @pytest.mark.parametrize("shape", [(64, 64), (24, 16), (100, 130), (65, 64), (64, 65), (200, 70), (129, 255), (256, 256)])
