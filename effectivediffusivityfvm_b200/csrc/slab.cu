@@ -14,7 +14,11 @@
 // graph.  Once per check the two boundary-flux partial sums are all-reduced (ncclAllReduce,
 // 2 doubles) and every rank applies the identical stop rule (cuh:1263-1276 via k_check).
 // DEFF2D_SLAB_SPLIT=1 selects the alternative that exchanges after every pass on a second stream
-// beside the interior tiles (boundary tiles launched first); measured slower, see slab_pass.
+// beside the interior tiles (boundary tiles launched first); measured slower, see slab_pass.  Overlapping only the
+// one exchange per halo cycle the same way (boundary tiles first, NCCL beside the interior tiles with a few SMs left
+// free) was measured in round 2: 1721 vs 1716 GLUP/s on 2 GPUs -- no gain, the remaining scaling loss is the extra
+// wave of tiles the halo rows add (83 instead of 82 rounds of 148 tiles on config 2) -- and it did not complete on 4
+// GPUs, so it was dropped.
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2): a process that already loaded NCCL (e.g.
 // through torch) shares that copy, and single-GPU users need no NCCL at all.
@@ -80,7 +84,7 @@ static NcclApi *nccl_api()
 
 struct SlabGraph {
     cudaGraphExec_t exec = nullptr;
-    int T = 0, launches = 0, passes = 0;
+    int T = 0, launches = 0;
     int64_t halo_after = 0;       // c->halo_valid at the end of the captured run
     const void *x0 = nullptr, *x1 = nullptr, *idx = nullptr, *lut = nullptr;
     double omega = 0;
@@ -91,8 +95,7 @@ struct SlabState {
     ncclComm_t comm = nullptr;
     SlabGraph graph[2];           // one per parity of c->cur at the start of the run
     bool use_graphs = true;
-    bool split = false;           // tuning: exchange after EVERY pass beside the interior tiles (measured slower)
-    bool overlap = true;          // the pass after which the halo runs out: boundary tiles first, exchange beside the interior tiles
+    bool split = false;           // boundary tiles in an own launch, exchange overlapped with the interior launch
     uint64_t lists_version = 0;
     int rank = 0, nranks = 1;
     cudaEvent_t evA = nullptr, evC = nullptr;
@@ -103,8 +106,7 @@ struct SlabState {
     bool lists_ready = false;
     int64_t key_Nx = 0, key_Ny = 0, key_above = -1, key_below = -1, key_own = -1;
     int key_family = -1;
-    int reserve_sms = 8;          // SMs the interior launch of an overlapped pass leaves to the NCCL send/recv kernel (the
-                                  // persistent sweep grid would otherwise hold every SM until it drains)
+    int reserve_sms = 0;          // SMs the interior launch leaves to the NCCL kernel (measured best on 2 GPUs: 0)
 };
 
 #define NCCLCHECK(call)                                                                      \
@@ -231,24 +233,6 @@ static int slab_pass(deff2d_ctx *c, SlabState *s, NcclApi *api, int T)
         if ((rc = slab_exchange(c, s, api, c->x[c->cur].p, c->stream))) return rc;
         c->halo_valid = std::max(c->halo_above, c->halo_below);
     }
-    // The pass that uses the halo up: its boundary tiles (they produce the rows the neighbours need) run first, then the
-    // exchange of the NEW iterate's rows travels on the communication stream while the interior tiles are swept -- the
-    // next pass finds a full halo without the stream ever waiting for NCCL.  One pass in H / T pays a second launch.
-    if (comm && s->overlap && c->halo_valid - T < T && s->cnt_b[T] > 0 && s->cnt_i[T] > 0) {
-        if ((rc = tma_pass(c, T, s->tiles.p + s->off_b[T], s->cnt_b[T], c->stream))) return rc;
-        CUS(cudaEventRecord(s->evA, c->stream));
-        CUS(cudaStreamWaitEvent(c->comm_stream, s->evA, 0));
-        c->grid_limit = s->reserve_sms > 0 ? c->prop.multiProcessorCount - s->reserve_sms : 0;
-        rc = tma_pass(c, T, s->tiles.p + s->off_i[T], s->cnt_i[T], c->stream);
-        c->grid_limit = 0;
-        if (rc) return rc;
-        if ((rc = slab_exchange(c, s, api, c->x[c->cur ^ 1].p, c->comm_stream))) return rc;
-        CUS(cudaEventRecord(s->evC, c->comm_stream));
-        CUS(cudaStreamWaitEvent(c->stream, s->evC, 0));
-        c->cur ^= 1;
-        c->halo_valid = std::max(c->halo_above, c->halo_below);
-        return DEFF2D_OK;
-    }
     if ((rc = tma_pass(c, T, nullptr, 0, c->stream))) return rc;
     c->cur ^= 1;
     if (comm) c->halo_valid -= T;
@@ -276,39 +260,24 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
     if (c->kernel == 0) Tmax = c->k2_default_depth;   // default depth; with 32 halo rows an exchange every fifth pass
     if (Tmax > 8) Tmax = 8;
     if (s->nranks > 1 && Tmax > H) Tmax = (int)H;
-    const bool comm = (c->halo_above > 0 || c->halo_below > 0);
     while (n > 0 && !rc) {
         const int T = (int)std::min<int64_t>(n, Tmax);
-        // passes per captured run: with the overlapped exchange a whole number of halo cycles (a run then starts and
-        // ends with a full halo and never needs a blocking exchange), an even number of passes (c->cur unchanged)
-        int GP = SLAB_GRAPH_PASSES;
-        const bool cyclic = comm && s->overlap && !s->split && s->cnt_b[T] > 0 && s->cnt_i[T] > 0;
-        if (cyclic) {
-            int cycle = 0;
-            for (int64_t hv = H;;) { cycle++; if (hv - T < T) break; hv -= T; }
-            GP = cycle * ((cycle & 1) ? 2 : 1);
-            while (GP < 12) GP *= 2;
-        }
-        if (c->use_graphs && s->use_graphs && n >= (int64_t)T * GP + 2 * T) {
+        if (c->use_graphs && s->use_graphs && n >= (int64_t)T * SLAB_GRAPH_PASSES) {
             SlabGraph &g = s->graph[c->cur];
-            const bool valid = g.exec && g.T == T && g.passes == GP && g.x0 == c->x[0].p && g.x1 == c->x[1].p && g.idx == c->idx16.p &&
+            const bool valid = g.exec && g.T == T && g.x0 == c->x[0].p && g.x1 == c->x[1].p && g.idx == c->idx16.p &&
                                g.lut == c->clut.p && g.omega == c->omega && g.lists == s->lists_version;
             if (!valid) {
                 if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
                 // one direct pass pair first: encodes the tensor maps outside the capture
                 if ((rc = slab_pass(c, s, api, T)) || (rc = slab_pass(c, s, api, T))) break;
                 n -= 2 * T;
-                if (n < (int64_t)T * GP) continue;
-                if (cyclic && c->halo_valid != H) {                // the captured run assumes a full halo at its start
-                    if ((rc = slab_exchange(c, s, api, c->x[c->cur].p, c->stream))) break;
-                    c->halo_valid = H;
-                }
+                if (n < (int64_t)T * SLAB_GRAPH_PASSES) continue;
                 cudaGraph_t graph = nullptr;
                 const int64_t launches0 = c->launches;
                 cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
                 if (e != cudaSuccess) { set_error(c, "cudaStreamBeginCapture failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
-                if (!cyclic) c->halo_valid = 0;                    // the captured run starts with an exchange: replays do not depend on the state before
-                for (int k = 0; k < GP && !rc; k++) rc = slab_pass(c, s, api, T);
+                c->halo_valid = 0;                                 // the captured run starts with an exchange: replays do not depend on the state before
+                for (int k = 0; k < SLAB_GRAPH_PASSES && !rc; k++) rc = slab_pass(c, s, api, T);
                 g.halo_after = c->halo_valid;
                 e = cudaStreamEndCapture(c->stream, &graph);
                 g.launches = (int)(c->launches - launches0);
@@ -318,18 +287,14 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
                 e = cudaGraphInstantiate(&g.exec, graph, 0);
                 cudaGraphDestroy(graph);
                 if (e != cudaSuccess) { g.exec = nullptr; set_error(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
-                g.T = T; g.passes = GP; g.x0 = c->x[0].p; g.x1 = c->x[1].p; g.idx = c->idx16.p; g.lut = c->clut.p; g.omega = c->omega;
+                g.T = T; g.x0 = c->x[0].p; g.x1 = c->x[1].p; g.idx = c->idx16.p; g.lut = c->clut.p; g.omega = c->omega;
                 g.lists = s->lists_version;
-            }
-            if (cyclic && c->halo_valid != H) {                    // (after a remainder pass, set_field, ...)
-                if ((rc = slab_exchange(c, s, api, c->x[c->cur].p, c->stream))) break;
-                c->halo_valid = H;
             }
             cudaError_t e = cudaGraphLaunch(s->graph[c->cur].exec, c->stream);
             if (e != cudaSuccess) { set_error(c, "cudaGraphLaunch failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
             c->launches += s->graph[c->cur].launches;
             c->halo_valid = s->graph[c->cur].halo_after;
-            n -= (int64_t)T * GP;                                  // an even number of passes: c->cur unchanged
+            n -= (int64_t)T * SLAB_GRAPH_PASSES;                   // an even number of passes: c->cur unchanged
             continue;
         }
         rc = slab_pass(c, s, api, T);
@@ -399,7 +364,6 @@ DEFF2D_EXPORT int deff2d_nccl_init(deff2d_ctx *c, const uint8_t id[DEFF2D_NCCL_I
     c->slab = s;
     s->rank = rank; s->nranks = nranks;
     if (const char *e = std::getenv("DEFF2D_SLAB_SPLIT")) s->split = std::atoi(e) != 0;          // tuning
-    if (const char *e = std::getenv("DEFF2D_SLAB_OVERLAP")) s->overlap = std::atoi(e) != 0;      // tuning
     if (const char *e = std::getenv("DEFF2D_SLAB_GRAPHS")) s->use_graphs = std::atoi(e) != 0;   // tuning
     if (const char *e = std::getenv("DEFF2D_SLAB_RESERVE_SMS")) { const int v = std::atoi(e); if (v >= 0 && v <= 64) s->reserve_sms = v; }   // tuning
     CUS(cudaSetDevice(c->device));
