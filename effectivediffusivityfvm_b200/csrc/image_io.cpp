@@ -2,13 +2,17 @@
 // the reference's `stbi_load(name, &W, &H, &nCh, 1)` call does (cuh:342, cuh:377): format is
 // sniffed from the content, not the extension; the channel count reported is the file's.
 // Own decoders, written from the format specifications: binary/ASCII PGM/PPM, PNG (all
-// colour types and bit depths, non-interlaced and Adam7) and baseline/progressive JPEG
-// (jpeg_decode.cpp).  Colour is reduced to luma with the integer weights 77/150/29 >> 8.
+// colour types and bit depths, non-interlaced and Adam7), baseline/progressive JPEG
+// (jpeg_decode.cpp) and TGA.  Colour is reduced to luma with the integer weights 77/150/29 >> 8.
+// The reference decoder's other formats (BMP, GIF, PSD, PIC, HDR) never yield a one-channel image, so its
+// drivers refuse them; they are recognised and reported with their channel count, not decoded.
 #include "deff2d_internal.h"
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -244,6 +248,8 @@ static int png_decode(const uint8_t *d, size_t n, std::vector<uint8_t> &out, int
         pos += 12 + len;
     }
     if (w < 1 || h < 1 || idat.empty()) { err = "bad PNG"; return DEFF2D_ERR_IO; }
+    if (!(depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) { err = "bad PNG bit depth"; return DEFF2D_ERR_IO; }
+    if ((int64_t)w * (int64_t)h > ((int64_t)1 << 31)) { err = "PNG too large"; return DEFF2D_ERR_IO; }   // the decoder's own limit is 2^24 per side
     int comp;
     switch (ctype) { case 0: comp = 1; break; case 2: comp = 3; break; case 3: comp = 1; break; case 4: comp = 2; break; case 6: comp = 4; break; default: err = "bad PNG colour type"; return DEFF2D_ERR_IO; }
     std::vector<uint8_t> raw;
@@ -290,13 +296,159 @@ static int png_decode(const uint8_t *d, size_t n, std::vector<uint8_t> &out, int
     return DEFF2D_OK;
 }
 
+// ---------------------------------------------------------------------------------- TGA
+// Truevision TGA: the one further format of the reference's decoder that can hold a ONE-channel image (image types 3
+// and 11, 8 bits) and so passes the drivers' channel test (cuh:1665-1668).  Colour-mapped and true-colour files decode
+// to luma and report their channel count like every other colour file.  Written from the TGA 2.0 specification.
+static int tga_decode(const uint8_t *d, size_t n, std::vector<uint8_t> &out, int *W, int *H, int *ch, std::string &err)
+{
+    if (n < 18) { err = "truncated TGA"; return DEFF2D_ERR_IO; }
+    const int idlen = d[0], cmtype = d[1], itype = d[2];
+    const int cm_first = d[3] | (d[4] << 8), cm_len = d[5] | (d[6] << 8), cm_bits = d[7];
+    const int w = d[12] | (d[13] << 8), h = d[14] | (d[15] << 8), bpp = d[16], desc = d[17];
+    const bool rle = itype >= 8;
+    const int base = itype & 7;                       // 1 colour-mapped, 2 true colour, 3 gray
+    if (w < 1 || h < 1 || (base != 1 && base != 2 && base != 3)) { err = "bad TGA header"; return DEFF2D_ERR_IO; }
+    auto px_channels = [](int bits, bool gray) { return gray ? (bits == 16 ? 2 : 1) : (bits == 15 || bits == 16 ? 3 : bits / 8); };
+    const int comp = (base == 1) ? px_channels(cm_bits, false) : px_channels(bpp, base == 3);
+    if (comp < 1 || comp > 4) { err = "unsupported TGA pixel size"; return DEFF2D_ERR_IO; }
+    size_t pos = 18 + (size_t)idlen;
+    std::vector<uint8_t> pal;
+    const int cm_bytes = (cm_bits + 7) / 8;
+    if (cmtype == 1) {
+        const size_t sz = (size_t)cm_len * cm_bytes;
+        if (pos + sz > n) { err = "truncated TGA palette"; return DEFF2D_ERR_IO; }
+        pal.assign(d + pos, d + pos + sz);
+        pos += sz;
+    }
+    const int pbytes = (bpp + 7) / 8;
+    if (pbytes < 1 || pbytes > 4) { err = "unsupported TGA pixel size"; return DEFF2D_ERR_IO; }
+    // one pixel of `bytes` little-endian bytes -> gray the way the reference's decoder reduces colour (77/150/29 >> 8)
+    auto to_gray = [&](const uint8_t *p, int bits) -> uint8_t {
+        if (bits == 8) return p[0];
+        if (bits == 15 || bits == 16) {
+            const int v = p[0] | (p[1] << 8);
+            const int r = (v >> 10) & 31, g = (v >> 5) & 31, b = v & 31;
+            return luma((r * 255) / 31, (g * 255) / 31, (b * 255) / 31);
+        }
+        return luma(p[2], p[1], p[0]);                // BGR(A) in the file
+    };
+    out.assign((size_t)w * h, 0);
+    const bool top_down = (desc & 0x20) != 0;
+    size_t count = (size_t)w * h, k = 0;
+    uint8_t cur[4] = {0, 0, 0, 0};
+    int run = 0;
+    bool run_is_rle = false;
+    auto read_px = [&](uint8_t *dst) -> bool {
+        if (pos + (size_t)pbytes > n) return false;
+        for (int q = 0; q < pbytes; q++) dst[q] = d[pos + q];
+        pos += (size_t)pbytes;
+        return true;
+    };
+    while (k < count) {
+        if (rle) {
+            if (run == 0) {
+                if (pos >= n) { err = "truncated TGA"; return DEFF2D_ERR_IO; }
+                const int hd = d[pos++];
+                run = (hd & 127) + 1;
+                run_is_rle = (hd & 128) != 0;
+                if (run_is_rle && !read_px(cur)) { err = "truncated TGA"; return DEFF2D_ERR_IO; }
+            }
+            if (!run_is_rle && !read_px(cur)) { err = "truncated TGA"; return DEFF2D_ERR_IO; }
+            run--;
+        } else if (!read_px(cur)) { err = "truncated TGA"; return DEFF2D_ERR_IO; }
+        uint8_t gval;
+        if (base == 1) {
+            const int idx = (pbytes == 1 ? cur[0] : (cur[0] | (cur[1] << 8))) - cm_first;
+            if (idx < 0 || (size_t)(idx + 1) * cm_bytes > pal.size()) gval = 0;
+            else gval = to_gray(pal.data() + (size_t)idx * cm_bytes, cm_bits);
+        } else if (base == 3) gval = (bpp == 16) ? cur[0] : cur[0];
+        else gval = to_gray(cur, bpp);
+        const size_t row = k / (size_t)w, col = k - row * (size_t)w;
+        const size_t orow = top_down ? row : (size_t)h - 1 - row;
+        out[orow * (size_t)w + col] = gval;
+        k++;
+    }
+    *W = w; *H = h; *ch = comp;
+    return DEFF2D_OK;
+}
+
+static bool tga_plausible(const uint8_t *d, size_t n)
+{
+    if (n < 18) return false;
+    const int cmtype = d[1], itype = d[2], bpp = d[16];
+    if (cmtype > 1) return false;
+    if (!(itype == 1 || itype == 2 || itype == 3 || itype == 9 || itype == 10 || itype == 11)) return false;
+    if (cmtype == 1) { const int cb = d[7]; if (!(cb == 8 || cb == 15 || cb == 16 || cb == 24 || cb == 32)) return false; }
+    else if (itype == 1 || itype == 9) return false;
+    if ((d[12] | (d[13] << 8)) < 1 || (d[14] | (d[15] << 8)) < 1) return false;
+    return bpp == 8 || bpp == 15 || bpp == 16 || bpp == 24 || bpp == 32;
+}
+
+// ---------------------------------------------------------------------------------- colour-only formats
+// BMP, GIF, PSD, Softimage PIC and Radiance HDR files always come out of the reference's decoder with 3 or 4 channels,
+// so its drivers refuse them with "please enter a grascale image with 1 channel" and the channel count (cuh:1665-1668).
+// For the drop-in program to say the same, their headers are recognised here and size + channel count are reported;
+// no pixels are decoded (the result is never used).
+static bool sniff_colour_only(const uint8_t *d, size_t n, int *W, int *H, int *ch)
+{
+    auto le16 = [&](size_t o) { return (int)(d[o] | (d[o + 1] << 8)); };
+    auto le32 = [&](size_t o) { return (int)((uint32_t)d[o] | ((uint32_t)d[o + 1] << 8) | ((uint32_t)d[o + 2] << 16) | ((uint32_t)d[o + 3] << 24)); };
+    auto be16 = [&](size_t o) { return (int)((d[o] << 8) | d[o + 1]); };
+    auto be32s = [&](size_t o) { return (int)(((uint32_t)d[o] << 24) | ((uint32_t)d[o + 1] << 16) | ((uint32_t)d[o + 2] << 8) | (uint32_t)d[o + 3]); };
+    if (n >= 30 && d[0] == 'B' && d[1] == 'M') {                                  // BMP
+        const int hsz = le32(14);
+        int w, h, bpp, compress = 0;
+        uint32_t amask = 0;
+        if (hsz == 12) { w = le16(18); h = le16(20); bpp = le16(24); }
+        else if (hsz == 40 || hsz == 56 || hsz == 108 || hsz == 124) {
+            w = le32(18); h = le32(22); bpp = le16(28); compress = le32(30);
+            if (hsz == 40 && bpp == 32 && compress == 0) amask = 0xff000000u;
+            else if (hsz == 40 && compress == 3 && n >= 70) amask = 0;              // three masks follow the header, no alpha
+            else if (hsz >= 56 && n >= 70 && (bpp == 16 || bpp == 32)) amask = (uint32_t)le32(66);
+        } else return false;
+        *W = w; *H = h < 0 ? -h : h;
+        *ch = amask ? 4 : 3;
+        return *W > 0 && *H > 0;
+    }
+    if (n >= 10 && !std::memcmp(d, "GIF8", 4) && (d[4] == '7' || d[4] == '9') && d[5] == 'a') {   // GIF
+        *W = le16(6); *H = le16(8); *ch = 4;
+        return *W > 0 && *H > 0;
+    }
+    if (n >= 26 && !std::memcmp(d, "8BPS", 4)) {                                  // PSD
+        *H = be32s(14); *W = be32s(18); *ch = 4;
+        return *W > 0 && *H > 0 && be16(4) == 1;
+    }
+    if (n >= 100 && d[0] == 0x53 && d[1] == 0x80 && d[2] == 0xF6 && d[3] == 0x34 && !std::memcmp(d + 88, "PICT", 4)) {   // Softimage PIC
+        *W = be16(92); *H = be16(94);
+        // channel packets follow at 104: alpha present if any packet's channel mask has bit 0x10
+        int c = 3;
+        for (size_t o = 104; o + 4 <= n; o += 4) { if (d[o + 3] & 0x10) c = 4; if (!d[o]) break; }
+        *ch = c;
+        return *W > 0 && *H > 0;
+    }
+    if (n >= 11 && (!std::memcmp(d, "#?RADIANCE", 10) || !std::memcmp(d, "#?RGBE", 6))) {   // Radiance HDR
+        const char *txt = reinterpret_cast<const char *>(d);
+        const std::string hd(txt, txt + std::min<size_t>(n, 4096));
+        const size_t py = hd.find("-Y ");
+        if (py == std::string::npos) return false;
+        int h = 0, w = 0;
+        if (std::sscanf(hd.c_str() + py, "-Y %d +X %d", &h, &w) != 2) return false;
+        *W = w; *H = h; *ch = 3;
+        return w > 0 && h > 0;
+    }
+    return false;
+}
+
 int decode_image_memory(const uint8_t *d, size_t n, std::vector<uint8_t> &out, int *W, int *H, int *ch, std::string &err)
 {
     static const uint8_t pngsig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     if (n >= 8 && !std::memcmp(d, pngsig, 8)) return png_decode(d, n, out, W, H, ch, err);
     if (n >= 3 && d[0] == 0xFF && d[1] == 0xD8) return jpeg_decode_gray(d, n, out, W, H, ch, err);
     if (n >= 7 && d[0] == 'P' && (d[1] == '2' || d[1] == '3' || d[1] == '5' || d[1] == '6')) return pnm_decode(d, n, out, W, H, ch, err);
-    err = "unknown image format (supported: PNG, JPEG, PGM/PPM)";
+    if (sniff_colour_only(d, n, W, H, ch)) { out.clear(); return DEFF2D_OK; }     // reported, not decoded: the drivers refuse them
+    if (tga_plausible(d, n)) return tga_decode(d, n, out, W, H, ch, err);        // no signature: last, as in the reference's decoder
+    err = "unknown image format (supported: PNG, JPEG, PGM/PPM, TGA; BMP/GIF/PSD/PIC/HDR are recognised as colour files)";
     return DEFF2D_ERR_IO;
 }
 
@@ -316,7 +468,12 @@ DEFF2D_EXPORT int deff2d_load_image(const char *path, uint8_t **gray, int *W, in
     std::vector<uint8_t> out;
     std::string err;
     int ch = 0;
-    const int rc = deff2d::decode_image_memory(data.data(), data.size(), out, W, H, &ch, err);
+    int rc;
+    try {
+        rc = deff2d::decode_image_memory(data.data(), data.size(), out, W, H, &ch, err);
+    } catch (const std::exception &) {          // bad_alloc / length_error from a hostile header: an I/O error, not an abort
+        return DEFF2D_ERR_IO;
+    }
     if (rc) return rc;
     if (channels) *channels = ch;
     *gray = (uint8_t *)std::malloc(out.size() ? out.size() : 1);

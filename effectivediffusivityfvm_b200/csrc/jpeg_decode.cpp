@@ -33,8 +33,8 @@ const uint8_t kZigzag[64 + 15] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25
 struct Huff {
     // canonical Huffman code (T.81 Annex C / F.2.2.3): per length the smallest code, the index of
     // its value and the largest code
-    int mincode[17], maxcode[18], valptr[17];
-    uint8_t vals[256];
+    int mincode[17] = {0}, maxcode[18] = {0}, valptr[17] = {0};
+    uint8_t vals[256] = {0};
     bool present = false;
 
     bool build(const uint8_t *bits, const uint8_t *v, int n)
@@ -410,6 +410,12 @@ struct Decoder {
         ss = u8(); se = u8();
         const int a = u8();
         ah = a >> 4; al = a & 15;
+        // a scan must not select a table no DHT segment defined (T.81 B.2.3): it would decode with empty code books
+        for (int s = 0; s < ns; s++) {
+            const Component &k = comp[order[s]];
+            const bool need_dc = !progressive || (ss == 0 && ah == 0), need_ac = !progressive || se > 0;   // DC refinement scans read raw bits only
+            if ((need_dc && !hdc[k.td].present) || (need_ac && !hac[k.ta].present)) return fail("scan uses an undefined Huffman table");
+        }
         if (progressive) {
             if (ss > 63 || se > 63 || ss > se || ah > 13 || al > 13) return fail("bad progressive SOS");
             if (ss == 0 && se != 0) return fail("bad progressive SOS");

@@ -405,3 +405,70 @@ def test_fraction_accumulation_equals_the_literal_loop():
     assert big == 200_000_000 / 268_435_456            # power-of-two total: every addition is exact
     v = L.deff2d_accumulate_fraction(160_000_000, 268_435_457)
     assert abs(v - 160_000_000 / 268_435_457) < 1e-7
+
+
+def test_tga_and_colour_only_formats_against_reference_decoder(tmp_path):
+    """The reference decoder's remaining formats (cuh:342): gray TGA (raw and RLE, both row orders) is the one that
+    yields a 1-channel image and must decode pixel for pixel; colour TGA, BMP and GIF always come back with 3 / 4
+    channels, which the drivers refuse (cuh:1665-1668) -- the library must report the same size and channel count."""
+    if O.reference("cpu") is None:
+        pytest.skip("oracle/_ref/libref_cpu.so not built")
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(5)
+    g = rng.integers(0, 256, (29, 41), dtype=np.uint8)
+    g[5:20, 3:30] = 200                                   # runs for the RLE encoder
+    rgb = rng.integers(0, 256, (29, 41, 3), dtype=np.uint8)
+
+    def tga(path, arr, rle, top_down, gray=True):
+        h, w = arr.shape[:2]
+        itype = (3 if gray else 2) + (8 if rle else 0)
+        hdr = bytes([0, 0, itype, 0, 0, 0, 0, 0, 0, 0, 0, 0, w & 255, w >> 8, h & 255, h >> 8, 8 if gray else 24, 0x20 if top_down else 0])
+        rows = arr if top_down else arr[::-1]
+        px = rows.reshape(h * w, -1)[:, ::-1] if not gray else rows.reshape(h * w, 1)      # BGR in the file
+        body = bytearray()
+        if not rle:
+            body += px.tobytes()
+        else:
+            k, n = 0, h * w
+            while k < n:
+                run = 1
+                while k + run < n and run < 128 and np.array_equal(px[k + run], px[k]):
+                    run += 1
+                if run > 1:
+                    body += bytes([128 | (run - 1)]) + px[k].tobytes()
+                    k += run
+                else:
+                    lit = 1
+                    while k + lit < n and lit < 128 and not (k + lit + 1 < n and np.array_equal(px[k + lit], px[k + lit + 1])):
+                        lit += 1
+                    body += bytes([lit - 1]) + px[k:k + lit].tobytes()
+                    k += lit
+        path.write_bytes(hdr + bytes(body))
+
+    files = []
+    for rle in (False, True):
+        for top in (False, True):
+            p = tmp_path / ("g_%d_%d.tga" % (rle, top))
+            tga(p, g, rle, top)
+            files.append((p, True))
+    p = tmp_path / "c.tga"
+    tga(p, rgb, True, False, gray=False)
+    files.append((p, True))
+    for name, im, fmt in (("rgb.bmp", Image.fromarray(rgb), "BMP"), ("pal.bmp", Image.fromarray(g).convert("P"), "BMP"),
+                          ("gray.bmp", Image.fromarray(g), "BMP"), ("a.gif", Image.fromarray(g), "GIF")):
+        p = tmp_path / name
+        im.save(p, fmt)
+        files.append((p, False))
+    for p, pixels in files:
+        want, ch2 = O.ref_decode(str(p))
+        L = _lib.lib()
+        ptr = _lib.c_ubyte_p()
+        W, H, ch = C.c_int(0), C.c_int(0), C.c_int(0)
+        assert L.deff2d_load_image(str(p).encode(), C.byref(ptr), C.byref(W), C.byref(H), C.byref(ch)) == 0, p.name
+        try:
+            assert (H.value, W.value) == want.shape and ch.value == ch2, (p.name, H.value, W.value, ch.value, want.shape, ch2)
+            if pixels:
+                got = np.ctypeslib.as_array(ptr, shape=(H.value, W.value)).copy()
+                assert np.array_equal(got, want), p.name
+        finally:
+            L.deff2d_free(ptr)
