@@ -8,8 +8,8 @@ device is present.
 """
 from ._lib import (LIB_PATH, MODE_2PH_BATCH, MODE_2PH_SINGLE, MODE_3PH, Input, Params, Result)
 from .api import (Deff2D, Deff2DError, batch_plan, batch_tile_list, build_tables, default_params, floodfill, load_image,
-                  nccl_unique_id, read_input_file, slab_split_tiles, solve_image_slabs, tile_geometry)
+                  nccl_unique_id, read_input_file, solve_image_slabs, tile_geometry)
 
 __all__ = ["Deff2D", "Deff2DError", "Params", "Result", "Input", "default_params", "read_input_file",
-           "build_tables", "floodfill", "tile_geometry", "slab_split_tiles", "batch_plan", "batch_tile_list", "load_image", "nccl_unique_id", "solve_image_slabs", "MODE_2PH_SINGLE", "MODE_2PH_BATCH",
+           "build_tables", "floodfill", "tile_geometry", "batch_plan", "batch_tile_list", "load_image", "nccl_unique_id", "solve_image_slabs", "MODE_2PH_SINGLE", "MODE_2PH_BATCH",
            "MODE_3PH", "LIB_PATH"]

@@ -114,8 +114,6 @@ def lib():
         "deff2d_build_tables": (i32, [dbl, dbl, dbl, i64, i64, dbl, dbl, dbl, c_double_p, c_ubyte_p]),
         "deff2d_floodfill": (i32, [c_ubyte_p, i64, i64]),
         "deff2d_tile_geometry": (i32, [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
-        "deff2d_slab_split_tiles": (i32, [i64, i64, i64, i64, i64, i64, i32, C.POINTER(C.c_uint32), C.POINTER(i32),
-                                          C.POINTER(C.c_uint32), i32]),
         "deff2d_batch_plan": (i32, [i64, i64, i32, i32, C.POINTER(i32), C.POINTER(i32)]),
         "deff2d_batch_tile_list": (i32, [i64, i64, i32, i32, C.POINTER(i32), i32, i32, C.POINTER(C.c_uint32), i32]),
         "deff2d_read_input_file": (i32, [C.c_char_p, C.POINTER(Input)]),

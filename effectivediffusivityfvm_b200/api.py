@@ -70,20 +70,6 @@ def tile_geometry(T):
     return tuple(x.value for x in v)
 
 
-def slab_split_tiles(Nx, Ny, above, own, below, halo, T):
-    """(boundary, interior) tile ids (ty << 16 | tx) of one slab, as csrc/slab.cu schedules them."""
-    cap = 1 << 20
-    b = np.zeros(cap, dtype=np.uint32)
-    i = np.zeros(cap, dtype=np.uint32)
-    nb = C.c_int(0)
-    u32p = C.POINTER(C.c_uint32)
-    ni = _lib.lib().deff2d_slab_split_tiles(Nx, Ny, above, own, below, halo, T, b.ctypes.data_as(u32p), C.byref(nb),
-                                            i.ctypes.data_as(u32p), cap)
-    if ni < 0:
-        raise Deff2DError("slab_split_tiles failed (%d)" % ni)
-    return b[:nb.value].copy(), i[:ni].copy()
-
-
 def batch_plan(Nx, Ny, count, limit=0):
     """(GX, GY) slot grid of the packed batch mode."""
     gx, gy = C.c_int(0), C.c_int(0)

@@ -407,9 +407,8 @@ static int batch_stream(deff2d_ctx *c, int count, int W, int H, const deff2d_par
     int GX, GY;
     batch_plan(Nx, Ny, count, c->batch_max_slots, &GX, &GY);
     const int nslots = GX * GY;
-    int T = 6;                                           // sweeps per HBM pass: interface-rich small images amortise the
-                                                         // per-tile weight gather best at depth 6 (measured 424 / 436 / 452 / 422 GLUP/s at T = 4 / 5 / 6 / 8)
-    if (const char *e = std::getenv("DEFF2D_BATCH_T")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) T = v; }   // tuning
+    const int T = 6;                                     // sweeps per HBM pass: interface-rich small images amortise the
+                                                         // per-tile weight gather best at depth 6 (measured 699 / 663 / 684 GLUP/s at T = 6 / 7 / 8 on 64 config-3 images)
 
     // FloodFill (cuh:557-713): PathFlag always, pinned mask in 3-phase.  On the device, all images of a refill in the
     // same launches (floodfill.cu); on the host with deff2d_set_floodfill(ctx, 1)

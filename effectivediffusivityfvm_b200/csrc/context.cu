@@ -483,9 +483,6 @@ DEFF2D_EXPORT int deff2d_create(deff2d_ctx **out, int device)
     std::memset(c->h_state, 0, sizeof(SolveState));
     c->kernel = 0;
     c->tblock = 1;
-    if (const char *e = std::getenv("DEFF2D_K2_VAR")) c->k2_variant = std::atoi(e) & 3;          // tuning (A/B runs)
-    if (const char *e = std::getenv("DEFF2D_K2_FAM")) { const int v = std::atoi(e); c->k2_default_family = (v == 4) ? 4 : 3; }
-    if (const char *e = std::getenv("DEFF2D_K2_DEPTH")) { const int v = std::atoi(e); if (v >= 1 && v <= 8) c->k2_default_depth = v; }
     *out = c;
     return DEFF2D_OK;
 }

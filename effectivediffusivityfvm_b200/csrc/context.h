@@ -55,7 +55,6 @@ struct deff2d_ctx {
     int kernel = 0;                  // 0 default, 1 simple, 2 TMA tiled
     int tblock = 1;
     int tile_family = 0;             // sweep_tma.cu thread layout: 3 = 4 x 4 patches, 4 = 2 x 8 patches, else the default
-    int k2_variant = 0;              // sweep_tma.cu: bit 0 selects the row-major 16-byte N / S exchange (tuning)
     int k2_default_family = DEFF2D_DEFAULT_TILE_FAMILY;
     int k2_default_depth = DEFF2D_DEFAULT_DEPTH;   // sweeps per HBM pass of kernel 0
     int64_t launches = 0;

@@ -13,12 +13,11 @@
 // buffer: no pack kernel.  Runs of 16 passes with their exchanges are captured into one CUDA
 // graph.  Once per check the two boundary-flux partial sums are all-reduced (ncclAllReduce,
 // 2 doubles) and every rank applies the identical stop rule (cuh:1263-1276 via k_check).
-// DEFF2D_SLAB_SPLIT=1 selects the alternative that exchanges after every pass on a second stream
-// beside the interior tiles (boundary tiles launched first); measured slower, see slab_pass.  Overlapping only the
-// one exchange per halo cycle the same way (boundary tiles first, NCCL beside the interior tiles with a few SMs left
-// free) was measured in round 2: 1721 vs 1716 GLUP/s on 2 GPUs -- no gain, the remaining scaling loss is the extra
-// wave of tiles the halo rows add (83 instead of 82 rounds of 148 tiles on config 2) -- and it did not complete on 4
-// GPUs, so it was dropped.
+// Measured and removed: exchanging after every pass on a second stream beside the interior tiles (boundary tiles in an
+// own launch first) -- 1 200 vs 1 341 GLUP/s on 2 GPUs in round 1, the two-launch split costs more than the exchange it
+// hides; overlapping only the one exchange per halo cycle the same way (round 2): 1 721 vs 1 716 GLUP/s on 2 GPUs -- no
+// gain, the remaining scaling loss is the extra wave of tiles the halo rows add (83 instead of 82 rounds of 148 tiles on
+// config 2) -- and it did not complete on 4 GPUs.
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2): a process that already loaded NCCL (e.g.
 // through torch) shares that copy, and single-GPU users need no NCCL at all.
@@ -88,25 +87,13 @@ struct SlabGraph {
     int64_t halo_after = 0;       // c->halo_valid at the end of the captured run
     const void *x0 = nullptr, *x1 = nullptr, *idx = nullptr, *lut = nullptr;
     double omega = 0;
-    uint64_t lists = 0;
+    int64_t Ny = 0, above = -1, below = -1;
 };
 
 struct SlabState {
     ncclComm_t comm = nullptr;
     SlabGraph graph[2];           // one per parity of c->cur at the start of the run
-    bool use_graphs = true;
-    bool split = false;           // boundary tiles in an own launch, exchange overlapped with the interior launch
-    uint64_t lists_version = 0;
     int rank = 0, nranks = 1;
-    cudaEvent_t evA = nullptr, evC = nullptr;
-    // per pass depth T (1..8): boundary and interior tile lists (device), built lazily per domain
-    DevBuf<uint32_t> tiles;
-    size_t off_b[9] = {0}, off_i[9] = {0};
-    int cnt_b[9] = {0}, cnt_i[9] = {0};
-    bool lists_ready = false;
-    int64_t key_Nx = 0, key_Ny = 0, key_above = -1, key_below = -1, key_own = -1;
-    int key_family = -1;
-    int reserve_sms = 0;          // SMs the interior launch leaves to the NCCL kernel (measured best on 2 GPUs: 0)
 };
 
 #define NCCLCHECK(call)                                                                      \
@@ -126,54 +113,6 @@ struct SlabState {
             return DEFF2D_ERR_CUDA;                                                          \
         }                                                                                    \
     } while (0)
-
-// Split the tile grid of output boxes ow x oh into the tiles that write a halo row or one of
-// the `H` own rows next to a neighbour (BOUNDARY: must finish before the exchange) and the rest.
-void slab_split_tiles(int64_t Nx, int64_t Ny, int64_t above, int64_t own, int64_t below, int64_t H, int ow, int oh,
-                      std::vector<uint32_t> &boundary, std::vector<uint32_t> &interior)
-{
-    const int tiles_x = (int)((Nx + ow - 1) / ow), tiles_y = (int)((Ny + oh - 1) / oh);
-    boundary.clear();
-    interior.clear();
-    const int64_t top_end = above > 0 ? above + H : 0;                       // rows [0, top_end)
-    const int64_t bot_begin = below > 0 ? above + own - H : Ny;              // rows [bot_begin, Ny)
-    for (int ty = 0; ty < tiles_y; ty++) {
-        const int64_t r0 = (int64_t)ty * oh, r1 = std::min<int64_t>(r0 + oh, Ny);
-        const bool b = (r0 < top_end) || (r1 > bot_begin);
-        for (int tx = 0; tx < tiles_x; tx++) (b ? boundary : interior).push_back(((uint32_t)ty << 16) | (uint32_t)tx);
-    }
-}
-
-static int build_lists(deff2d_ctx *c, SlabState *s)
-{
-    const bool same = s->lists_ready && s->key_Nx == c->Nx && s->key_Ny == c->Ny && s->key_above == c->halo_above &&
-                      s->key_below == c->halo_below && s->key_own == c->own_rows && s->key_family == c->tile_family;
-    if (same) return DEFF2D_OK;
-    const int64_t H = std::max(c->halo_above, c->halo_below);
-    std::vector<uint32_t> all, bd, in;
-    for (int T = 1; T <= 8; T++) {
-        int ow, oh;
-        tma_tile_geometry(c, T, &ow, &oh);
-        slab_split_tiles(c->Nx, c->Ny, c->halo_above, c->own_rows, c->halo_below, H, ow, oh, bd, in);
-        s->off_b[T] = all.size(); s->cnt_b[T] = (int)bd.size();
-        all.insert(all.end(), bd.begin(), bd.end());
-        s->off_i[T] = all.size(); s->cnt_i[T] = (int)in.size();
-        all.insert(all.end(), in.begin(), in.end());
-    }
-    if (s->tiles.cap < all.size() || !s->tiles.p) {
-        if (s->tiles.p) cudaFree(s->tiles.p);
-        s->tiles.p = nullptr;
-        CUS(cudaMalloc((void **)&s->tiles.p, all.size() * sizeof(uint32_t)));
-        s->tiles.cap = all.size();
-    }
-    CUS(cudaMemcpyAsync(s->tiles.p, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-    CUS(cudaStreamSynchronize(c->stream));
-    s->key_Nx = c->Nx; s->key_Ny = c->Ny; s->key_above = c->halo_above; s->key_below = c->halo_below;
-    s->key_own = c->own_rows; s->key_family = c->tile_family;
-    s->lists_ready = true;
-    s->lists_version++;
-    return DEFF2D_OK;
-}
 
 // Halo exchange of the current iterate x[c->cur] on stream `cs`: H whole padded rows to and from
 // each neighbour.  Afterwards every local row is exact again.
@@ -198,37 +137,14 @@ static int slab_exchange(deff2d_ctx *c, SlabState *s, NcclApi *api, double *buf,
     return DEFF2D_OK;
 }
 
-// One pass of depth T on a slab; flips c->cur.  Enqueue only (also used under stream capture).
-//
-// Default (deep halo): a pass of depth T invalidates T more halo rows, so with H halo rows the
-// exchange is only needed every H / T passes -- c->halo_valid counts the halo rows that are
-// still exact.  With H = 16, T = 4 the NCCL latency (~16 us per exchange, measured) is paid
-// once per 4 passes (~740 us of sweeping).
-// Split mode (DEFF2D_SLAB_SPLIT=1): exchange after every pass, boundary tiles launched first
-// and the exchange on a second stream beside the interior tiles.  Measured slower on B200
-// (the two-launch split costs more than the exchange it hides), kept for comparison.
+// One pass of depth T on a slab; flips c->cur.  Enqueue only (also used under stream capture).  A pass of depth T
+// invalidates T more halo rows, so with H halo rows the exchange is only needed every H / T passes -- c->halo_valid
+// counts the halo rows that are still exact.  With H = 32, T = 6 the NCCL latency (~25 us per exchange, measured) is
+// paid once per 5 passes (~1.1 ms of sweeping on config 2).
 static int slab_pass(deff2d_ctx *c, SlabState *s, NcclApi *api, int T)
 {
     const bool comm = (c->halo_above > 0 || c->halo_below > 0);
     int rc;
-    if (s->split) {
-        if ((rc = tma_pass(c, T, s->tiles.p + s->off_b[T], s->cnt_b[T], c->stream))) return rc;
-        if (comm) {
-            CUS(cudaEventRecord(s->evA, c->stream));
-            CUS(cudaStreamWaitEvent(c->comm_stream, s->evA, 0));
-        }
-        c->grid_limit = comm && s->reserve_sms > 0 ? c->prop.multiProcessorCount - s->reserve_sms : 0;
-        rc = tma_pass(c, T, s->tiles.p + s->off_i[T], s->cnt_i[T], c->stream);
-        c->grid_limit = 0;
-        if (rc) return rc;
-        if (comm) {
-            if ((rc = slab_exchange(c, s, api, c->x[c->cur ^ 1].p, c->comm_stream))) return rc;
-            CUS(cudaEventRecord(s->evC, c->comm_stream));
-            CUS(cudaStreamWaitEvent(c->stream, s->evC, 0));
-        }
-        c->cur ^= 1;
-        return DEFF2D_OK;
-    }
     if (comm && c->halo_valid < T) {
         if ((rc = slab_exchange(c, s, api, c->x[c->cur].p, c->stream))) return rc;
         c->halo_valid = std::max(c->halo_above, c->halo_below);
@@ -254,18 +170,17 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
     if (s->nranks > 1 && (H < 1 || c->own_rows < H)) { set_error(c, "slab needs halo rows >= 1 and own rows >= halo rows"); return DEFF2D_ERR_STATE; }
     const int old_family = c->tile_family;
     c->tile_family = 0;                    // the default thread layout
-    int rc = build_lists(c, s);
-    if (rc) { c->tile_family = old_family; return rc; }
+    int rc = DEFF2D_OK;
     int Tmax = c->tblock > 0 ? c->tblock : 4;
     if (c->kernel == 0) Tmax = c->k2_default_depth;   // default depth; with 32 halo rows an exchange every fifth pass
     if (Tmax > 8) Tmax = 8;
     if (s->nranks > 1 && Tmax > H) Tmax = (int)H;
     while (n > 0 && !rc) {
         const int T = (int)std::min<int64_t>(n, Tmax);
-        if (c->use_graphs && s->use_graphs && n >= (int64_t)T * SLAB_GRAPH_PASSES) {
+        if (c->use_graphs && n >= (int64_t)T * SLAB_GRAPH_PASSES) {
             SlabGraph &g = s->graph[c->cur];
             const bool valid = g.exec && g.T == T && g.x0 == c->x[0].p && g.x1 == c->x[1].p && g.idx == c->idx16.p &&
-                               g.lut == c->clut.p && g.omega == c->omega && g.lists == s->lists_version;
+                               g.lut == c->clut.p && g.omega == c->omega && g.Ny == c->Ny && g.above == c->halo_above && g.below == c->halo_below;
             if (!valid) {
                 if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
                 // one direct pass pair first: encodes the tensor maps outside the capture
@@ -288,7 +203,7 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
                 cudaGraphDestroy(graph);
                 if (e != cudaSuccess) { g.exec = nullptr; set_error(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
                 g.T = T; g.x0 = c->x[0].p; g.x1 = c->x[1].p; g.idx = c->idx16.p; g.lut = c->clut.p; g.omega = c->omega;
-                g.lists = s->lists_version;
+                g.Ny = c->Ny; g.above = c->halo_above; g.below = c->halo_below;
             }
             cudaError_t e = cudaGraphLaunch(s->graph[c->cur].exec, c->stream);
             if (e != cudaSuccess) { set_error(c, "cudaGraphLaunch failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
@@ -331,9 +246,6 @@ void slab_destroy(deff2d_ctx *c)
     NcclApi *api = nccl_api();
     for (auto &g : s->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
     if (s->comm && api->CommDestroy) api->CommDestroy(s->comm);
-    if (s->evA) cudaEventDestroy(s->evA);
-    if (s->evC) cudaEventDestroy(s->evC);
-    if (s->tiles.p) cudaFree(s->tiles.p);
     delete s;
     c->slab = nullptr;
 }
@@ -363,12 +275,7 @@ DEFF2D_EXPORT int deff2d_nccl_init(deff2d_ctx *c, const uint8_t id[DEFF2D_NCCL_I
     SlabState *s = new SlabState();
     c->slab = s;
     s->rank = rank; s->nranks = nranks;
-    if (const char *e = std::getenv("DEFF2D_SLAB_SPLIT")) s->split = std::atoi(e) != 0;          // tuning
-    if (const char *e = std::getenv("DEFF2D_SLAB_GRAPHS")) s->use_graphs = std::atoi(e) != 0;   // tuning
-    if (const char *e = std::getenv("DEFF2D_SLAB_RESERVE_SMS")) { const int v = std::atoi(e); if (v >= 0 && v <= 64) s->reserve_sms = v; }   // tuning
     CUS(cudaSetDevice(c->device));
-    CUS(cudaEventCreateWithFlags(&s->evA, cudaEventDisableTiming));
-    CUS(cudaEventCreateWithFlags(&s->evC, cudaEventDisableTiming));
     ncclUniqueId u;
     std::memcpy(&u, id, sizeof(u));
     NCCLCHECK(api->CommInitRank(&s->comm, nranks, u, rank));
@@ -425,20 +332,4 @@ DEFF2D_EXPORT int deff2d_tile_geometry(int T, int *ow, int *oh, int *tw, int *th
     if (tw) *tw = a + 2 * ((T + 1) & ~1);
     if (th) *th = b + 2 * T;
     return DEFF2D_OK;
-}
-
-DEFF2D_EXPORT int deff2d_slab_split_tiles(int64_t Nx, int64_t Ny, int64_t above, int64_t own, int64_t below,
-                                          int64_t halo, int T, uint32_t *boundary_tiles, int *nboundary,
-                                          uint32_t *interior_tiles, int cap)
-{
-    if (T < 1 || T > 8 || Nx < 1 || Ny < 1 || above + own + below != Ny || !nboundary) return DEFF2D_ERR_ARG;
-    int ow, oh;
-    tma_tile_geometry(nullptr, T, &ow, &oh);
-    std::vector<uint32_t> bd, in;
-    slab_split_tiles(Nx, Ny, above, own, below, halo, ow, oh, bd, in);
-    if ((int)bd.size() > cap || (int)in.size() > cap) return DEFF2D_ERR_ARG;
-    if (boundary_tiles) std::memcpy(boundary_tiles, bd.data(), bd.size() * sizeof(uint32_t));
-    if (interior_tiles) std::memcpy(interior_tiles, in.data(), in.size() * sizeof(uint32_t));
-    *nboundary = (int)bd.size();
-    return (int)in.size();
 }

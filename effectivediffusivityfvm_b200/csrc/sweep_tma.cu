@@ -138,7 +138,6 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
 {
     constexpr int T = C::T, TE = C::TE, PX = C::PX, PY = C::PY, TW = C::TW, TH = C::TH, OW = C::OW, OH = C::OH;
     constexpr int PW = C::PLANE_W, IW = C::IW;
-    constexpr bool ROWEX = (VAR & 1) != 0 && PX == 2;   // N / S row exchange row-major with 16-byte accesses instead of planar 8-byte ones
     // NON-PARITY Chebyshev mode: sweep s of the pass is the Richardson step x' = x + tau_s (sum_f u_f x_f - x) with the
     // omega = 1 table u; ghost columns keep their value (factor 0)
     constexpr bool CHEB = (VAR & 2) != 0;
@@ -301,15 +300,10 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         // The W / E halo comes from the neighbouring lanes by warp shuffles (a warp spans the tile
         // width), so only the top and bottom patch rows go through shared memory.
         auto publish_rows = [&](double *pb, const double (&top)[PX], const double (&bot)[PX]) {
-            if constexpr (ROWEX) {
-                *reinterpret_cast<double2 *>(pb + r0 * TW + c0) = make_double2(top[0], top[1]);
-                *reinterpret_cast<double2 *>(pb + (r0 + PY - 1) * TW + c0) = make_double2(bot[0], bot[1]);
-            } else {
 #pragma unroll
-                for (int px = 0; px < PX; px++) {
-                    pb[(px * TH + r0) * PW + g] = top[px];
-                    pb[(px * TH + r0 + PY - 1) * PW + g] = bot[px];
-                }
+            for (int px = 0; px < PX; px++) {
+                pb[(px * TH + r0) * PW + g] = top[px];
+                pb[(px * TH + r0 + PY - 1) * PW + g] = bot[px];
             }
         };
         // x' = (1-w) x + wW xW + wE xE + wS xS + wN xN   (cuh:76-89, A and b folded into w): one patch row
@@ -362,16 +356,10 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
                 hW[py] = __shfl_up_sync(0xffffffffu, x[py][PX - 1], 1, C::LX);
                 hE[py] = __shfl_down_sync(0xffffffffu, x[py][0], 1, C::LX);
             }
-            if constexpr (ROWEX) {
-                const double2 n2 = *reinterpret_cast<const double2 *>(pr + rN * TW + c0);
-                const double2 s2 = *reinterpret_cast<const double2 *>(pr + rS * TW + c0);
-                hN[0] = n2.x; hN[1] = n2.y; hS[0] = s2.x; hS[1] = s2.y;
-            } else {
 #pragma unroll
-                for (int px = 0; px < PX; px++) {
-                    hN[px] = pr[(px * TH + rN) * PW + g];
-                    hS[px] = pr[(px * TH + rS) * PW + g];
-                }
+            for (int px = 0; px < PX; px++) {
+                hN[px] = pr[(px * TH + rN) * PW + g];
+                hS[px] = pr[(px * TH + rS) * PW + g];
             }
             // in-place update; `up[px]` carries the old value of the row above
             double up[PX], fac[PX];
@@ -583,12 +571,10 @@ static int pass_from(deff2d_ctx *c, int T, int src, const uint32_t *list, int co
     if (T < 1 || T > 8) { set_error(c, "temporal depth %d out of range", T); return DEFF2D_ERR_ARG; }
     int rc = DEFF2D_OK;
     const int fam = k2_family(c);
-    const int var = c->k2_variant & 3;
 #define DEFF2D_VAR(TT, FF)                                                                                     \
     {                                                                                                          \
         if ((rc = prepare_T<TT, FF>(c, ts))) return rc;                                                        \
-        if (var & 1) rc = launch_T<TT, FF, 1>(c, ts, src, list, count, stream);                                \
-        else rc = launch_T<TT, FF, 0>(c, ts, src, list, count, stream);                                        \
+        rc = launch_T<TT, FF, 0>(c, ts, src, list, count, stream);                                             \
         if (rc) return rc;                                                                                     \
     }
 #define DEFF2D_CASE(TT)                                                                   \
@@ -650,7 +636,7 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
         }
         GraphEntry *g = nullptr;
         for (auto &e : ts->graphs)
-            if (e.exec && e.version == ts->version && e.T == T && e.fam == (k2_family(c) * 8 + (c->k2_variant & 3)) && e.src == c->cur && e.list == list &&
+            if (e.exec && e.version == ts->version && e.T == T && e.fam == k2_family(c) && e.src == c->cur && e.list == list &&
                 e.count == count && e.grid_limit == c->grid_limit && e.lut == c->clut.p && e.omega == c->omega) { g = &e; break; }
         if (!g) {
             // drop stale graphs, then capture GRAPH_PASSES passes
@@ -673,7 +659,7 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
             e = cudaGraphInstantiate(&slot->exec, graph, 0);
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) { slot->exec = nullptr; set_error(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
-            slot->version = ts->version; slot->T = T; slot->fam = k2_family(c) * 8 + (c->k2_variant & 3); slot->src = c->cur; slot->list = list;
+            slot->version = ts->version; slot->T = T; slot->fam = k2_family(c); slot->src = c->cur; slot->list = list;
             slot->count = count; slot->grid_limit = c->grid_limit; slot->lut = c->clut.p; slot->omega = c->omega;
             g = slot;
         }

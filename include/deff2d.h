@@ -252,18 +252,12 @@ int deff2d_build_tables(double Ds, double Df, double Dg, int64_t Nx, int64_t Ny,
  * right-column seeding quirk (cuh:601).  grid: Ny*Nx bytes in/out (unreached non-solid
  * cells become 2).  Returns PathFlag (0/1) or a negative status. */
 int deff2d_floodfill(uint8_t *grid, int64_t Nx, int64_t Ny);
-
-/* Tile planning of the tiled sweep, as the library does it (host code).  A pass of depth T
- * (1..8) writes output boxes of ow x oh cells from input tiles of tw x th cells; tile ids are
- * ty << 16 | tx.  deff2d_slab_split_tiles: the tiles of a slab (above / own / below rows, halo
- * depth `halo`) that must finish before the halo exchange, and the rest.  deff2d_batch_plan:
- * slot grid of the packed batch mode; deff2d_batch_tile_list: tiles whose output touches an
- * active slot.  The *_tiles arrays hold `cap` entries; the functions return the number of tiles
- * (boundary count in *nboundary, interior count as return value for the split) or a negative
- * status when `cap` is too small. */
+/* Tile planning of the TMA kernel, exposed so that the decomposition logic is testable on a CPU box.
+ * deff2d_tile_geometry: output box (ow x oh) and input tile (tw x th) of a pass of depth T.
+ * deff2d_batch_plan: slot grid of the packed batch mode.  deff2d_batch_tile_list: tiles whose output touches an
+ * active slot; `tiles` holds `cap` entries, the function returns the number of tiles or a negative status when
+ * `cap` is too small. */
 int deff2d_tile_geometry(int T, int *ow, int *oh, int *tw, int *th);
-int deff2d_slab_split_tiles(int64_t Nx, int64_t Ny, int64_t above, int64_t own, int64_t below, int64_t halo,
-                            int T, uint32_t *boundary_tiles, int *nboundary, uint32_t *interior_tiles, int cap);
 int deff2d_batch_plan(int64_t Nx, int64_t Ny, int count, int limit, int *GX, int *GY);
 int deff2d_batch_tile_list(int64_t Nx, int64_t Ny, int GX, int GY, const int *active, int nactive, int T,
                            uint32_t *tiles, int cap);

@@ -27,31 +27,9 @@ def _boxes(tiles, ow, oh):
 @pytest.mark.parametrize("T", [1, 2, 3, 4, 6, 8])
 def test_tile_geometry(T):
     ow, oh, tw, th = E.tile_geometry(T)
-    assert (tw, th) == (64, 64)             # the default tile family: square tiles, 4 x 4 cells per thread
+    assert (tw, th) == (64, 64)             # square tiles in both thread layouts
     assert oh == th - 2 * T and ow == tw - 2 * ((T + 1) // 2 * 2)
     assert ow % 2 == 0                      # TMA needs 16-byte aligned FP64 box origins
-
-
-@pytest.mark.parametrize("Nx,above,own,below,halo,T", [(500, 0, 100, 4, 4, 4), (500, 4, 100, 4, 4, 4), (130, 8, 64, 0, 8, 3),
-                                                       (4008, 4, 2007, 4, 4, 4), (64, 0, 50, 0, 4, 4), (300, 4, 4, 4, 4, 2)])
-def test_slab_tile_split_covers_domain_once_and_orders_halo_writes(Nx, above, own, below, halo, T):
-    Ny = above + own + below
-    ow, oh, _, _ = E.tile_geometry(T)
-    bd, it = E.slab_split_tiles(Nx, Ny, above, own, below, halo, T)
-    cover = np.zeros((Ny, Nx), dtype=np.int32)
-    kind = np.zeros((Ny, Nx), dtype=np.int32)
-    for k, tiles in ((1, bd), (2, it)):
-        for x0, y0 in _boxes(tiles, ow, oh):
-            cover[y0:y0 + oh, x0:x0 + ow] += 1
-            kind[y0:y0 + oh, x0:x0 + ow] = k
-    assert np.all(cover == 1)               # every cell is written by exactly one tile
-    # rows the exchange touches (halo rows it overwrites, own rows it sends) belong to boundary tiles
-    if above:
-        assert np.all(kind[:above + halo] == 1)
-    if below:
-        assert np.all(kind[above + own - halo:] == 1)
-    if not above and not below:
-        assert len(bd) == 0
 
 
 def test_batch_plan_and_tile_list():
