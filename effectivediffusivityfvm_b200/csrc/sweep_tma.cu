@@ -474,6 +474,8 @@ template <int T, int F> struct Family;
 template <int T> struct Family<T, 3> { using type = Cfg<T, 4, 4, 1, 8, 16>; };
 template <int T> struct Family<T, 4> { using type = Cfg<T, 2, 8, 1, 8, 32>; };
 // (nine warps on 64 x 72 tiles do not work: registers are allocated per four warps, so 288 threads get 168 each)
+// (the 2 x 8 layout with four warps on 64 x 32 tiles and two CTAs per SM, each in its own phase of its own tile: 736
+//  GLUP/s at its best depth 4 against 871 -- the per-tile prologue weighs more on half-size tiles than the overlap gains)
 
 static bool attr_done(TmaState *ts, const void *fn)
 {
