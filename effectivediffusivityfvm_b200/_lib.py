@@ -8,6 +8,7 @@ LIB_PATH = os.environ.get("DEFF2D_LIB") or os.path.join(PKG_DIR, "libdeff2d.so")
 
 MAX_STAGES = 16
 NCCL_ID_BYTES = 128
+PEER_HANDLE_BYTES = 320
 
 MODE_2PH_SINGLE, MODE_2PH_BATCH, MODE_3PH = 0, 1, 2
 
@@ -109,6 +110,8 @@ def lib():
         "deff2d_slab_sweeps": (i32, [vp, i64]),
         "deff2d_slab_flux": (i32, [vp, c_double_p]),
         "deff2d_slab_abort": (i32, [vp]),
+        "deff2d_slab_peer_export": (i32, [vp, c_ubyte_p]),
+        "deff2d_slab_peer_attach": (i32, [vp, c_ubyte_p, c_ubyte_p]),
         "deff2d_domain_load_slab_global": (i32, [vp, c_ubyte_p, i32, i32, i32, C.POINTER(Params), i64, i64, i32]),
         "deff2d_accumulate_fraction": (dbl, [i64, i64]),
         "deff2d_build_tables": (i32, [dbl, dbl, dbl, i64, i64, dbl, dbl, dbl, c_double_p, c_ubyte_p]),

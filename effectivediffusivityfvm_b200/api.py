@@ -356,6 +356,17 @@ class Deff2D:
         buf = (C.c_ubyte * _lib.NCCL_ID_BYTES).from_buffer_copy(bytes(unique_id))
         self._ck(self._L.deff2d_nccl_init(self._h, buf, int(rank), int(nranks)))
 
+    def slab_peer_export(self):
+        buf = (C.c_ubyte * _lib.PEER_HANDLE_BYTES)()
+        self._ck(self._L.deff2d_slab_peer_export(self._h, buf))
+        return bytes(buf)
+
+    def slab_peer_attach(self, above, below):
+        """Handles (bytes) of the ranks above / below, None at the ends.  Collective: ends in a barrier."""
+        def arg(h):
+            return None if h is None else (C.c_ubyte * _lib.PEER_HANDLE_BYTES).from_buffer_copy(bytes(h))
+        self._ck(self._L.deff2d_slab_peer_attach(self._h, arg(above), arg(below)))
+
     def slab_sweeps(self, n):
         self._ck(self._L.deff2d_slab_sweeps(self._h, int(n)))
 

@@ -222,6 +222,7 @@ static int domain_load_impl(deff2d_ctx *c, const uint8_t *gray, int W, int Hsrc,
         return DEFF2D_ERR_ARG;
     }
     CU(cudaSetDevice(c->device));
+    slab_peer_reset(c);
     const int64_t Nx = (int64_t)W * p->amp_x;
     const int64_t Ny = NyLocal;
     if (Nx * (NyG > Ny ? NyG : Ny) >= ((int64_t)1 << 40)) { set_error(c, "domain too large"); return DEFF2D_ERR_ARG; }

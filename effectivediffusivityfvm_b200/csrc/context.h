@@ -83,6 +83,7 @@ struct deff2d_ctx {
     void *slab = nullptr;
     int64_t halo_valid = 0;          // slab mode: halo rows that are still exact (a pass of depth T consumes T)
     bool slab_domain = false;        // the resident domain is one slab of a decomposed global domain
+    int64_t store_row0 = 0, store_rows = 0;   // rows the tiled sweep's store maps cover (0 rows: all); slab peer mode: the own rows
 };
 
 namespace deff2d {
@@ -102,11 +103,14 @@ int tma_pass(deff2d_ctx *c, int T, const uint32_t *list, int count, cudaStream_t
 // npasses passes of depth T on c->stream, flipping c->cur after each (CUDA graphs for long runs)
 int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int count);
 void tma_tile_geometry(const deff2d_ctx *c, int T, int *ow, int *oh);
-int tma_cheb_pass(deff2d_ctx *c, const double tau[8]);   // chebyshev.cu: 8 Richardson steps with per-sweep factors (omega = 1 table)
+int tma_cheb_pass(deff2d_ctx *c, const double tau[8]);
+// slab peer mode: one pass with the halo push fused in; peer_args points to a PeerArgs (kernels.cuh)
+int tma_peer_pass(deff2d_ctx *c, int T, const uint32_t *list, int count, const void *peer_args);   // chebyshev.cu: 8 Richardson steps with per-sweep factors (omega = 1 table)
 void tma_destroy(deff2d_ctx *c);
 
 // slab.cu
 int slab_allreduce_q(deff2d_ctx *c);     // no-op unless the resident domain is a slab of a multi-rank group
+void slab_peer_reset(deff2d_ctx *c);              // a (re)load ends the peer-memory exchange mode until it is attached again
 bool slab_is_distributed(const deff2d_ctx *c);   // the resident domain is one slab of a group of >= 2 ranks
 int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n);
 void slab_destroy(deff2d_ctx *c);

@@ -22,6 +22,7 @@
 // NCCL is bound at run time (dlopen of libnccl.so.2): a process that already loaded NCCL (e.g.
 // through torch) shares that copy, and single-GPU users need no NCCL at all.
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include <algorithm>
@@ -88,10 +89,42 @@ struct SlabGraph {
     const void *x0 = nullptr, *x1 = nullptr, *idx = nullptr, *lut = nullptr;
     double omega = 0;
     int64_t Ny = 0, above = -1, below = -1;
+    bool peer = false;
+    const void *peer_up = nullptr, *peer_down = nullptr;
+};
+
+// Peer-memory halo exchange (the sweep kernel pushes the boundary rows into the neighbours' halo rows itself):
+// what one rank publishes about itself, and what it has mapped of its neighbours.
+struct PeerHandle {                  // DEFF2D_PEER_HANDLE_BYTES
+    cudaIpcMemHandle_t x[2], sync;
+    uint64_t ptr_x[2], ptr_sync;     // the raw device pointers (same-process neighbours use them directly)
+    int64_t above, own, below, pitch, Nx;
+    int32_t pid, device;
+};
+static_assert(sizeof(PeerHandle) <= DEFF2D_PEER_HANDLE_BYTES, "peer handle size");
+
+struct PeerSide {
+    bool present = false;
+    PeerHandle h;                    // what is currently mapped
+    double *x[2] = {nullptr, nullptr};
+    long long *sync = nullptr;
+    bool ipc = false;                // mapped with cudaIpcOpenMemHandle (must be closed), else same-process pointers
+};
+
+struct PeerState {
+    bool active = false;
+    long long *sync = nullptr;       // own block: [0] flag from above, [1] flag from below, [2] boundary tiles done,
+                                     //            [3] CTAs done, [4] passes done
+    PeerSide up, down;
+    DevBuf<uint32_t> tiles;          // per depth T: boundary tiles first, then the other tiles that touch own rows
+    size_t off[9] = {0};
+    int cnt[9] = {0}, nb[9] = {0};
+    int64_t key_Nx = -1, key_Ny = -1, key_above = -1, key_own = -1;
 };
 
 struct SlabState {
     ncclComm_t comm = nullptr;
+    PeerState peer;
     SlabGraph graph[2];           // one per parity of c->cur at the start of the run
     int rank = 0, nranks = 1;
 };
@@ -137,6 +170,116 @@ static int slab_exchange(deff2d_ctx *c, SlabState *s, NcclApi *api, double *buf,
     return DEFF2D_OK;
 }
 
+static void peer_close_side(PeerSide &sd)
+{
+    if (sd.present && sd.ipc) {
+        for (int k = 0; k < 2; k++) if (sd.x[k]) cudaIpcCloseMemHandle(sd.x[k]);
+        if (sd.sync) cudaIpcCloseMemHandle(sd.sync);
+    }
+    sd = PeerSide();
+}
+
+static int peer_open_side(deff2d_ctx *c, PeerSide &sd, const PeerHandle *h)
+{
+    if (!h) { peer_close_side(sd); return DEFF2D_OK; }
+    if (sd.present && !std::memcmp(&sd.h, h, sizeof(*h))) return DEFF2D_OK;      // same buffers as last time: keep the mapping
+    peer_close_side(sd);
+    sd.h = *h;
+    if (h->pid == (int32_t)getpid()) {
+        // a neighbour in this process (multi.cpp: one thread per device): its pointers are valid here once peer access is on
+        if (h->device != c->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(h->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                set_error(c, "cudaDeviceEnablePeerAccess(%d) failed: %s", h->device, cudaGetErrorString(e));
+                (void)cudaGetLastError();
+                return DEFF2D_ERR_CUDA;
+            }
+            (void)cudaGetLastError();
+        }
+        sd.x[0] = reinterpret_cast<double *>(h->ptr_x[0]);
+        sd.x[1] = reinterpret_cast<double *>(h->ptr_x[1]);
+        sd.sync = reinterpret_cast<long long *>(h->ptr_sync);
+        sd.ipc = false;
+    } else {
+        void *p0 = nullptr, *p1 = nullptr, *ps = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p0, h->x[0], cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&p1, h->x[1], cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) e = cudaIpcOpenMemHandle(&ps, h->sync, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            set_error(c, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            if (p0) cudaIpcCloseMemHandle(p0);
+            if (p1) cudaIpcCloseMemHandle(p1);
+            return DEFF2D_ERR_CUDA;
+        }
+        sd.x[0] = static_cast<double *>(p0); sd.x[1] = static_cast<double *>(p1); sd.sync = static_cast<long long *>(ps);
+        sd.ipc = true;
+    }
+    sd.present = true;
+    return DEFF2D_OK;
+}
+
+// Tile lists of the peer mode for every depth: tiles whose output box touches the first / last H own rows next to a
+// neighbour first (they feed the neighbours), then the other tiles that touch own rows; tiles inside the halo rows only
+// are not swept at all (the neighbours write those rows).
+static int peer_build_lists(deff2d_ctx *c, PeerState &ps)
+{
+    if (ps.key_Nx == c->Nx && ps.key_Ny == c->Ny && ps.key_above == c->halo_above && ps.key_own == c->own_rows && ps.tiles.p) return DEFF2D_OK;
+    const int64_t H = std::max(c->halo_above, c->halo_below);
+    const int64_t own0 = c->halo_above, own1 = c->halo_above + c->own_rows;
+    std::vector<uint32_t> all, bd, in;
+    for (int T = 1; T <= 8; T++) {
+        int ow, oh;
+        tma_tile_geometry(c, T, &ow, &oh);
+        const int tiles_x = (int)((c->Nx + ow - 1) / ow), tiles_y = (int)((c->Ny + oh - 1) / oh);
+        bd.clear(); in.clear();
+        for (int ty = 0; ty < tiles_y; ty++) {
+            const int64_t r0 = (int64_t)ty * oh, r1 = std::min<int64_t>(r0 + oh, c->Ny);
+            if (r1 <= own0 || r0 >= own1) continue;                               // halo rows only
+            const bool b = (c->halo_above > 0 && r0 < own0 + H) || (c->halo_below > 0 && r1 > own1 - H);
+            for (int tx = 0; tx < tiles_x; tx++) (b ? bd : in).push_back(((uint32_t)ty << 16) | (uint32_t)tx);
+        }
+        ps.off[T] = all.size(); ps.nb[T] = (int)bd.size(); ps.cnt[T] = (int)(bd.size() + in.size());
+        all.insert(all.end(), bd.begin(), bd.end());
+        all.insert(all.end(), in.begin(), in.end());
+    }
+    if (ps.tiles.cap < all.size() || !ps.tiles.p) {
+        if (ps.tiles.p) cudaFree(ps.tiles.p);
+        ps.tiles.p = nullptr;
+        CUS(cudaMalloc((void **)&ps.tiles.p, all.size() * sizeof(uint32_t)));
+        ps.tiles.cap = all.size();
+    }
+    CUS(cudaMemcpyAsync(ps.tiles.p, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    CUS(cudaStreamSynchronize(c->stream));
+    ps.key_Nx = c->Nx; ps.key_Ny = c->Ny; ps.key_above = c->halo_above; ps.key_own = c->own_rows;
+    return DEFF2D_OK;
+}
+
+// One pass of depth T in peer mode; flips c->cur.  No NCCL: the kernel pushes and waits itself (sweep_tma.cu, PEER).
+static int peer_pass(deff2d_ctx *c, SlabState *s, int T)
+{
+    PeerState &ps = s->peer;
+    const int64_t H = std::max(c->halo_above, c->halo_below);
+    PeerArgs pa;
+    std::memset(&pa, 0, sizeof(pa));
+    for (int b = 0; b < 2; b++) {
+        // the neighbour's halo rows that mirror my first / last H own rows: its interior rows [above_p + own_p, +H) / [above_q - H, above_q)
+        if (ps.up.present) pa.up[b] = ps.up.x[b] + (1 + ps.up.h.above + ps.up.h.own) * ps.up.h.pitch + DEFF2D_XOFF;
+        if (ps.down.present) pa.down[b] = ps.down.x[b] + (1 + ps.down.h.above - H) * ps.down.h.pitch + DEFF2D_XOFF;
+    }
+    pa.flag_up = ps.up.present ? ps.up.sync + 1 : nullptr;         // I am the lower neighbour of the rank above
+    pa.flag_down = ps.down.present ? ps.down.sync + 0 : nullptr;   // ... and the upper neighbour of the rank below
+    pa.flag_local = ps.sync;
+    pa.counters = reinterpret_cast<unsigned long long *>(ps.sync + 2);
+    pa.pass_no = ps.sync + 4;
+    pa.pitch = c->pitch;
+    pa.above = (int)c->halo_above; pa.own = (int)c->own_rows; pa.H = (int)H; pa.nboundary = ps.nb[T]; pa.Nx = (int)c->Nx;
+    c->store_row0 = c->halo_above; c->store_rows = c->own_rows;
+    const int rc = tma_peer_pass(c, T, ps.tiles.p + ps.off[T], ps.cnt[T], &pa);
+    c->store_row0 = 0; c->store_rows = 0;
+    return rc;
+}
+
 // One pass of depth T on a slab; flips c->cur.  Enqueue only (also used under stream capture).  A pass of depth T
 // invalidates T more halo rows, so with H halo rows the exchange is only needed every H / T passes -- c->halo_valid
 // counts the halo rows that are still exact.  With H = 32, T = 6 the NCCL latency (~25 us per exchange, measured) is
@@ -145,6 +288,7 @@ static int slab_pass(deff2d_ctx *c, SlabState *s, NcclApi *api, int T)
 {
     const bool comm = (c->halo_above > 0 || c->halo_below > 0);
     int rc;
+    if (s->peer.active && comm) return peer_pass(c, s, T);
     if (comm && c->halo_valid < T) {
         if ((rc = slab_exchange(c, s, api, c->x[c->cur].p, c->stream))) return rc;
         c->halo_valid = std::max(c->halo_above, c->halo_below);
@@ -180,7 +324,8 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
         if (c->use_graphs && n >= (int64_t)T * SLAB_GRAPH_PASSES) {
             SlabGraph &g = s->graph[c->cur];
             const bool valid = g.exec && g.T == T && g.x0 == c->x[0].p && g.x1 == c->x[1].p && g.idx == c->idx16.p &&
-                               g.lut == c->clut.p && g.omega == c->omega && g.Ny == c->Ny && g.above == c->halo_above && g.below == c->halo_below;
+                               g.lut == c->clut.p && g.omega == c->omega && g.Ny == c->Ny && g.above == c->halo_above && g.below == c->halo_below && g.peer == s->peer.active &&
+                               g.peer_up == (const void *)s->peer.up.x[0] && g.peer_down == (const void *)s->peer.down.x[0];
             if (!valid) {
                 if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
                 // one direct pass pair first: encodes the tensor maps outside the capture
@@ -203,7 +348,8 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
                 cudaGraphDestroy(graph);
                 if (e != cudaSuccess) { g.exec = nullptr; set_error(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
                 g.T = T; g.x0 = c->x[0].p; g.x1 = c->x[1].p; g.idx = c->idx16.p; g.lut = c->clut.p; g.omega = c->omega;
-                g.Ny = c->Ny; g.above = c->halo_above; g.below = c->halo_below;
+                g.Ny = c->Ny; g.above = c->halo_above; g.below = c->halo_below; g.peer = s->peer.active;
+                g.peer_up = s->peer.up.x[0]; g.peer_down = s->peer.down.x[0];
             }
             cudaError_t e = cudaGraphLaunch(s->graph[c->cur].exec, c->stream);
             if (e != cudaSuccess) { set_error(c, "cudaGraphLaunch failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
@@ -233,6 +379,12 @@ int slab_allreduce_q(deff2d_ctx *c)
     return DEFF2D_OK;
 }
 
+// a new domain is loaded: the peer mode has to be attached again (flags, counters and tile lists belong to a load)
+void slab_peer_reset(deff2d_ctx *c)
+{
+    if (SlabState *s = static_cast<SlabState *>(c->slab)) s->peer.active = false;
+}
+
 bool slab_is_distributed(const deff2d_ctx *c)
 {
     const SlabState *s = static_cast<const SlabState *>(c->slab);
@@ -245,6 +397,10 @@ void slab_destroy(deff2d_ctx *c)
     if (!s) return;
     NcclApi *api = nccl_api();
     for (auto &g : s->graph) if (g.exec) cudaGraphExecDestroy(g.exec);
+    peer_close_side(s->peer.up);
+    peer_close_side(s->peer.down);
+    if (s->peer.sync) cudaFree(s->peer.sync);
+    if (s->peer.tiles.p) cudaFree(s->peer.tiles.p);
     if (s->comm && api->CommDestroy) api->CommDestroy(s->comm);
     delete s;
     c->slab = nullptr;
@@ -293,6 +449,65 @@ DEFF2D_EXPORT int deff2d_slab_abort(deff2d_ctx *c)
     ncclComm_t comm = s->comm;
     s->comm = nullptr;
     api->CommAbort(comm);
+    return DEFF2D_OK;
+}
+
+// ---- peer-memory halo exchange -----------------------------------------------------------------------------------
+
+DEFF2D_EXPORT int deff2d_slab_peer_export(deff2d_ctx *c, uint8_t handle[DEFF2D_PEER_HANDLE_BYTES])
+{
+    if (!c || !handle) return DEFF2D_ERR_ARG;
+    SlabState *s = static_cast<SlabState *>(c->slab);
+    if (!s || !s->comm) { set_error(c, "peer export before deff2d_nccl_init"); return DEFF2D_ERR_STATE; }
+    if (!c->loaded || !c->slab_domain) { set_error(c, "peer export needs a loaded slab"); return DEFF2D_ERR_STATE; }
+    CUS(cudaSetDevice(c->device));
+    PeerState &ps = s->peer;
+    if (!ps.sync) CUS(cudaMalloc((void **)&ps.sync, 64));
+    PeerHandle h;
+    std::memset(&h, 0, sizeof(h));
+    CUS(cudaIpcGetMemHandle(&h.x[0], c->x[0].p));
+    CUS(cudaIpcGetMemHandle(&h.x[1], c->x[1].p));
+    CUS(cudaIpcGetMemHandle(&h.sync, ps.sync));
+    h.ptr_x[0] = (uint64_t)(uintptr_t)c->x[0].p; h.ptr_x[1] = (uint64_t)(uintptr_t)c->x[1].p; h.ptr_sync = (uint64_t)(uintptr_t)ps.sync;
+    h.above = c->halo_above; h.own = c->own_rows; h.below = c->halo_below; h.pitch = c->pitch; h.Nx = c->Nx;
+    h.pid = (int32_t)getpid(); h.device = c->device;
+    std::memset(handle, 0, DEFF2D_PEER_HANDLE_BYTES);
+    std::memcpy(handle, &h, sizeof(h));
+    return DEFF2D_OK;
+}
+
+DEFF2D_EXPORT int deff2d_slab_peer_attach(deff2d_ctx *c, const uint8_t *above, const uint8_t *below)
+{
+    if (!c) return DEFF2D_ERR_ARG;
+    SlabState *s = static_cast<SlabState *>(c->slab);
+    NcclApi *api = nccl_api();
+    if (!s || !s->comm) { set_error(c, "peer attach before deff2d_nccl_init"); return DEFF2D_ERR_STATE; }
+    if (!c->loaded || !c->slab_domain || !s->peer.sync) { set_error(c, "peer attach needs deff2d_slab_peer_export on a loaded slab first"); return DEFF2D_ERR_STATE; }
+    CUS(cudaSetDevice(c->device));
+    PeerState &ps = s->peer;
+    ps.active = false;
+    const int64_t H = std::max(c->halo_above, c->halo_below);
+    if ((c->halo_above > 0) != (above != nullptr) || (c->halo_below > 0) != (below != nullptr)) {
+        set_error(c, "peer attach: a handle is needed exactly where the slab has a neighbour");
+        return DEFF2D_ERR_ARG;
+    }
+    if (H < 1 || H > 64 || c->own_rows < 2 * H) { set_error(c, "peer mode needs 1..64 halo rows and at least twice as many own rows"); return DEFF2D_ERR_ARG; }
+    PeerHandle hu, hd;
+    if (above) { std::memcpy(&hu, above, sizeof(hu)); if (hu.Nx != c->Nx || hu.pitch != c->pitch || hu.below != H) { set_error(c, "peer attach: the upper neighbour's slab does not match"); return DEFF2D_ERR_ARG; } }
+    if (below) { std::memcpy(&hd, below, sizeof(hd)); if (hd.Nx != c->Nx || hd.pitch != c->pitch || hd.above != H) { set_error(c, "peer attach: the lower neighbour's slab does not match"); return DEFF2D_ERR_ARG; } }
+    int rc;
+    if ((rc = peer_open_side(c, ps.up, above ? &hu : nullptr))) return rc;
+    if ((rc = peer_open_side(c, ps.down, below ? &hd : nullptr))) return rc;
+    if ((rc = peer_build_lists(c, ps))) return rc;
+    // flags -1 ("no pass yet"), counters 0, pass 0 -- then every rank must have got here before anyone pushes a row
+    // into a neighbour (whose load may still be writing its buffers): one all-reduce as a barrier
+    const long long init[8] = {-1, -1, 0, 0, 0, 0, 0, 0};
+    CUS(cudaMemcpyAsync(ps.sync, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    NCCLCHECK(api->AllReduce(ps.sync + 6, ps.sync + 6, 1, ncclInt64, ncclSum, s->comm, c->stream));
+    CUS(cudaStreamSynchronize(c->stream));
+    c->launches++;
+    ps.active = true;
+    for (auto &g : s->graph) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     return DEFF2D_OK;
 }
 

@@ -134,13 +134,15 @@ struct Cfg {
 template <class C, bool LIST, int VAR>
 __global__ void __launch_bounds__(C::NT, 1)
 k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, double om,
-            int tiles_x, int ntiles, const uint32_t *__restrict__ tile_list, const ChebTaus taus)
+            int tiles_x, int ntiles, const uint32_t *__restrict__ tile_list, const ChebTaus taus, const PeerArgs peer)
 {
     constexpr int T = C::T, TE = C::TE, PX = C::PX, PY = C::PY, TW = C::TW, TH = C::TH, OW = C::OW, OH = C::OH;
     constexpr int PW = C::PLANE_W, IW = C::IW;
     // NON-PARITY Chebyshev mode: sweep s of the pass is the Richardson step x' = x + tau_s (sum_f u_f x_f - x) with the
     // omega = 1 table u; ghost columns keep their value (factor 0)
     constexpr bool CHEB = (VAR & 2) != 0;
+    constexpr bool PEER = (VAR & 1) != 0;     // peer-memory halo exchange fused into the pass (needs LIST)
+    static_assert(!PEER || LIST, "the peer variant walks a tile list (boundary tiles first)");
     static_assert(C::NWX == 1, "a warp spans the tile width (W / E halo by shuffles)");
 
     // No integer round trip on the base pointer: the compiler must keep seeing the shared
@@ -191,6 +193,21 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     __syncthreads();
     int tile = blockIdx.x;
     const double *wtab = lut;
+    long long pass = 0;
+    if constexpr (PEER) {
+        if (tid == 0) {
+            // the halo rows this pass reads were written by the neighbours' previous pass; the halo rows this pass
+            // writes were read by it: both are over once their flags show that pass
+            pass = *reinterpret_cast<volatile long long *>(peer.pass_no);
+            auto flag_at_least = [&](const long long *f, long long want) {
+                long long v;
+                do { asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(f) : "memory"); } while (v < want);
+            };
+            if (peer.up[0]) flag_at_least(peer.flag_local + 0, pass - 1);
+            if (peer.down[0]) flag_at_least(peer.flag_local + 1, pass - 1);
+            fence_proxy_async();
+        }
+    }
     if (tid == 0) {
         if (tile < ntiles) issue_load(tile, 0);
         if (tile + (int)gridDim.x < ntiles) issue_load(tile + gridDim.x, 1);
@@ -410,11 +427,55 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         fence_proxy_async();                   // generic-proxy writes -> visible to the TMA engine
         __syncthreads();
         if (tid == 0) {
-            tma_store_2d(map_out, ox, oy, OUT);
+            // PEER: the store map covers the own rows only (halo rows belong to the neighbours' pushes)
+            tma_store_2d(map_out, ox, PEER ? oy - peer.above : oy, OUT);
             tma_commit();
+        }
+        if constexpr (PEER) {
+            if (k * (int)gridDim.x + (int)blockIdx.x < peer.nboundary) {     // boundary tiles come first in the list
+                // rows of the output box among the first / last H own rows -> the neighbour's halo rows, 16 bytes per store
+                const int dst = src ^ 1;
+                for (int e = tid; e < OH * (OW / 2); e += C::NT) {
+                    const int r = e / (OW / 2), cpair = (e - r * (OW / 2)) * 2;
+                    const int row_own = oy + r - peer.above, col = ox + cpair;
+                    if (col >= peer.Nx) continue;
+                    const double2 v = *reinterpret_cast<const double2 *>(OUT + r * OW + cpair);
+                    const bool one = (col + 1 >= peer.Nx);
+                    if (peer.up[dst] && row_own >= 0 && row_own < peer.H) {
+                        double *q = peer.up[dst] + (long long)row_own * peer.pitch + col;
+                        if (one) *q = v.x; else *reinterpret_cast<double2 *>(q) = v;
+                    }
+                    const int rd = row_own - (peer.own - peer.H);
+                    if (peer.down[dst] && rd >= 0 && rd < peer.H && row_own < peer.own) {
+                        double *q = peer.down[dst] + (long long)rd * peer.pitch + col;
+                        if (one) *q = v.x; else *reinterpret_cast<double2 *>(q) = v;
+                    }
+                }
+                __threadfence_system();
+                __syncthreads();
+                if (tid == 0) {
+                    const unsigned long long done = atomicAdd(peer.counters + 0, 1ull) + 1ull;
+                    if (done == (unsigned long long)peer.nboundary) {          // (the counter is reset when the pass closes)
+                        __threadfence_system();
+                        if (peer.flag_up) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer.flag_up), "l"(pass) : "memory");
+                        if (peer.flag_down) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer.flag_down), "l"(pass) : "memory");
+                    }
+                }
+            }
         }
     }
     if (tid == 0) tma_wait_all0();             // stores complete before the CTA's smem goes away
+    if constexpr (PEER) {
+        if (tid == 0) {                         // the last CTA to leave closes the pass
+            const unsigned long long done = atomicAdd(peer.counters + 1, 1ull) + 1ull;
+            if (done == (unsigned long long)gridDim.x) {
+                peer.counters[0] = 0ull;        // every boundary tile of this pass has been counted
+                peer.counters[1] = 0ull;
+                __threadfence();
+                *reinterpret_cast<volatile long long *>(peer.pass_no) = pass + 1;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -443,6 +504,7 @@ struct TmaState {
     void *key_x0 = nullptr, *key_x1 = nullptr, *key_code = nullptr;
     int64_t key_Nx = 0, key_Ny = 0, key_pitch = 0;
     int cfg_TH = 0;              // tile height the maps were encoded for
+    int64_t key_srow0 = 0, key_srows = 0;   // rows the store maps cover (slab peer mode: the own rows only)
     std::vector<const void *> attr_fns;   // kernels whose dynamic shared-memory limit has been raised
     int max_smem_optin = 0;
 };
@@ -486,7 +548,7 @@ static bool attr_done(TmaState *ts, const void *fn)
 
 template <int T, int F, int VAR>
 static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, int count, cudaStream_t stream,
-                    const ChebTaus &taus = ChebTaus())
+                    const ChebTaus &taus = ChebTaus(), const PeerArgs &peer = PeerArgs())
 {
     using C = typename Family<T, F>::type;
     auto kern = list ? k_sweep_tma<C, true, VAR> : k_sweep_tma<C, false, VAR>;
@@ -501,7 +563,7 @@ static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, 
     if (c->grid_limit > 0 && grid > c->grid_limit) grid = c->grid_limit;
     if (grid > ntiles) grid = ntiles;
     const double *table = c->clut.p;
-    kern<<<grid, C::NT, smem, stream>>>(ts->maps, src, table, 1.0 - c->omega, ts->tiles_x, ntiles, list, taus);
+    kern<<<grid, C::NT, smem, stream>>>(ts->maps, src, table, 1.0 - c->omega, ts->tiles_x, ntiles, list, taus, peer);
     return DEFF2D_OK;
 }
 
@@ -510,7 +572,8 @@ static int prepare_T(deff2d_ctx *c, TmaState *ts)
 {
     using C = typename Family<T, F>::type;
     if ((int)C::SMEM > ts->max_smem_optin) { set_error(c, "tile needs %zu B smem > %d", C::SMEM, ts->max_smem_optin); return DEFF2D_ERR_STATE; }
-    const bool same = ts->cfg_T == T && ts->cfg_TH == C::TH && ts->key_x0 == c->x[0].p && ts->key_x1 == c->x[1].p && ts->key_code == c->idx16.p &&
+    const int64_t srow0 = c->store_row0, srows = (c->store_rows > 0) ? c->store_rows : c->Ny;
+    const bool same = ts->cfg_T == T && ts->cfg_TH == C::TH && ts->key_srow0 == srow0 && ts->key_srows == srows && ts->key_x0 == c->x[0].p && ts->key_x1 == c->x[1].p && ts->key_code == c->idx16.p &&
                       ts->key_Nx == c->Nx && ts->key_Ny == c->Ny && ts->key_pitch == c->pitch;
     if (same) return DEFF2D_OK;
     int rc;
@@ -518,7 +581,7 @@ static int prepare_T(deff2d_ctx *c, TmaState *ts)
         if ((rc = encode_2d(c, ts, &ts->maps.x_load[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8, c->x[b].p, (uint64_t)c->pitch,
                             (uint64_t)c->rows, (uint64_t)c->pitch * 8, C::TW, C::TH))) return rc;
         if ((rc = encode_2d(c, ts, &ts->maps.x_store[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 8,
-                            c->x[b].p + c->pitch + DEFF2D_XOFF, (uint64_t)c->Nx, (uint64_t)c->Ny, (uint64_t)c->pitch * 8,
+                            c->x[b].p + (1 + srow0) * c->pitch + DEFF2D_XOFF, (uint64_t)c->Nx, (uint64_t)srows, (uint64_t)c->pitch * 8,
                             C::OW, C::OH))) return rc;
     }
     if (!c->idx16.p) { set_error(c, "tiled sweep: the per-cell table indices have not been built"); return DEFF2D_ERR_STATE; }
@@ -532,6 +595,7 @@ static int prepare_T(deff2d_ctx *c, TmaState *ts)
     ts->tiles_y = (int)((c->Ny + C::OH - 1) / C::OH);
     ts->key_x0 = c->x[0].p; ts->key_x1 = c->x[1].p; ts->key_code = c->idx16.p;
     ts->key_Nx = c->Nx; ts->key_Ny = c->Ny; ts->key_pitch = c->pitch;
+    ts->key_srow0 = srow0; ts->key_srows = srows;
     return DEFF2D_OK;
 }
 
@@ -607,6 +671,48 @@ int tma_cheb_pass(deff2d_ctx *c, const double tau[8])
     return DEFF2D_OK;
 }
 
+// Slab peer mode (slab.cu): one pass of depth T over `list` (boundary tiles first, `nboundary` of them) with the halo
+// push fused into the kernel; flips c->cur.  c->store_row0 / store_rows select the own rows for the local store.
+template <int T>
+static int peer_launch(deff2d_ctx *c, TmaState *ts, const uint32_t *list, int count, const PeerArgs &pa)
+{
+    using C = typename Family<T, 4>::type;
+    int rc;
+    if ((rc = prepare_T<T, 4>(c, ts))) return rc;
+    auto kern = k_sweep_tma<C, true, 1>;
+    if (!attr_done(ts, (const void *)kern)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) { set_error(c, "cudaFuncSetAttribute(smem %zu) failed: %s", (size_t)C::SMEM, cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
+    }
+    int grid = c->prop.multiProcessorCount;
+    if (grid > count) grid = count;
+    kern<<<grid, C::NT, C::SMEM, c->stream>>>(ts->maps, c->cur, c->clut.p, 1.0 - c->omega, ts->tiles_x, count, list, ChebTaus(), pa);
+    return DEFF2D_OK;
+}
+
+int tma_peer_pass(deff2d_ctx *c, int T, const uint32_t *list, int count, const void *peer_args)
+{
+    TmaState *ts = tma_state(c);
+    if (!ts->encode) { set_error(c, "cuTensorMapEncodeTiled is not available from this driver"); return DEFF2D_ERR_CUDA; }
+    if (T < 1 || T > 8 || count < 1) { set_error(c, "peer pass: bad depth / tile count"); return DEFF2D_ERR_ARG; }
+    const PeerArgs &pa = *static_cast<const PeerArgs *>(peer_args);
+    int rc = DEFF2D_OK;
+    switch (T) {
+    case 1: rc = peer_launch<1>(c, ts, list, count, pa); break;
+    case 2: rc = peer_launch<2>(c, ts, list, count, pa); break;
+    case 3: rc = peer_launch<3>(c, ts, list, count, pa); break;
+    case 4: rc = peer_launch<4>(c, ts, list, count, pa); break;
+    case 5: rc = peer_launch<5>(c, ts, list, count, pa); break;
+    case 6: rc = peer_launch<6>(c, ts, list, count, pa); break;
+    case 7: rc = peer_launch<7>(c, ts, list, count, pa); break;
+    default: rc = peer_launch<8>(c, ts, list, count, pa); break;
+    }
+    if (rc) return rc;
+    c->cur ^= 1;
+    c->launches++;
+    return DEFF2D_OK;
+}
+
 // One pass from x[c->cur] into x[c->cur ^ 1]; does not flip c->cur.
 int tma_pass(deff2d_ctx *c, int T, const uint32_t *list, int count, cudaStream_t stream)
 {
@@ -628,7 +734,7 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
     int rc;
     while (npasses >= GRAPH_PASSES && c->use_graphs) {
         // make sure the tensor maps are current before looking a graph up (re-encoding bumps the version)
-        if (ts->cfg_T != T || ts->cfg_TH != 64 || ts->key_x0 != c->x[0].p || ts->key_x1 != c->x[1].p ||
+        if (ts->cfg_T != T || ts->cfg_TH != 64 || ts->key_srow0 != c->store_row0 || ts->key_srows != ((c->store_rows > 0) ? c->store_rows : c->Ny) || ts->key_x0 != c->x[0].p || ts->key_x1 != c->x[1].p ||
             ts->key_code != c->idx16.p || ts->key_Nx != c->Nx || ts->key_Ny != c->Ny || ts->key_pitch != c->pitch) {
             // a direct pass re-encodes the maps; then the graphs of the old maps are dropped below
             if ((rc = tma_pass(c, T, list, count, c->stream))) return rc;

@@ -81,10 +81,15 @@ class SlabDomain:
              only the slab's rows of the image and of the mask are uploaded then (deff2d_domain_load_slab).
     """
 
-    def __init__(self, ctx, img, params, rank, world, nphase=3, halo=32, pinned=None, weak=False, nccl_id=None):
+    def __init__(self, ctx, img, params, rank, world, nphase=3, halo=None, pinned=None, weak=False, nccl_id=None, peer=True):
         img = np.ascontiguousarray(img, dtype=np.uint8)
         Hbase, W = img.shape
         self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        # peer=True (default, ranks of one box): the sweep kernel pushes the boundary rows into the neighbours' halo rows
+        # itself (8 halo rows are enough); peer=False: NCCL send/recv of deep halos (32 rows, one exchange per 5 passes)
+        self.peer = bool(peer) and world > 1
+        if halo is None:
+            halo = 8 if self.peer else 32
         H = Hbase * world if weak else Hbase
         period_src = Hbase if weak else None
         self.layout = L = SlabLayout(H, rank, world, params.amp_y, halo)
@@ -110,13 +115,26 @@ class SlabDomain:
             self._loader, self._load_args = ctx.domain_load_slab, (gray, nphase, params, L.row0, L.ny_global, L.halo, L.src_rows, pin)
             self.h2d_bytes = int(gray.size + (pin.size if pin is not None else 0))
         self._loader(*self._load_args)
+        self._attach()
         if pinned is None:
             self.pathflag = ctx.info()["pathflag"]
 
+    def _attach(self):
+        """Peer mode: every rank publishes the IPC handles of its buffers, takes its neighbours' and attaches."""
+        if not self.peer:
+            return
+        import torch.distributed as dist
+        mine = self.ctx.slab_peer_export()
+        handles = [None] * self.world
+        dist.all_gather_object(handles, mine)
+        self.ctx.slab_peer_attach(handles[self.rank - 1] if self.rank > 0 else None,
+                                  handles[self.rank + 1] if self.rank < self.world - 1 else None)
+
     def reload(self):
         """Upload again from the host buffers and reset the iterate to x0: what a fresh solve of the same domain
-        costs end to end (image upload, FloodFill, assembly)."""
+        costs end to end (image upload, FloodFill, assembly, and in peer mode the handle exchange)."""
         self._loader(*self._load_args)
+        self._attach()
 
     def _broadcast_id(self):
         import torch.distributed as dist

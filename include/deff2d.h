@@ -232,6 +232,15 @@ int deff2d_nccl_init(deff2d_ctx *ctx, const uint8_t id[DEFF2D_NCCL_ID_BYTES], in
 int deff2d_slab_sweeps(deff2d_ctx *ctx, int64_t n);
 /* Global Deff: local {Q1,Q2} -> ncclAllReduce(sum) -> same value on every rank; blocks. */
 int deff2d_slab_flux(deff2d_ctx *ctx, double *deff_raw);
+/* Peer-memory halo exchange, fused into the sweep kernel (one process or thread per GPU of one box): a rank sweeps
+ * only its own rows; the tiles next to a neighbour run first and copy the rows that neighbour needs straight into its
+ * halo rows over NVLink; flags in peer memory order the passes of neighbouring ranks.  No NCCL call between passes,
+ * no recomputed halo rows.  After every slab load: each rank exports its handle, the host layer hands every rank the
+ * handles of the ranks above / below (NULL at the ends), attach (collective: it ends in a barrier).  Without it the
+ * slab runs the NCCL deep-halo exchange.  Halo rows: 8 is enough (>= the pass depth). */
+#define DEFF2D_PEER_HANDLE_BYTES 320
+int deff2d_slab_peer_export(deff2d_ctx *ctx, uint8_t handle[DEFF2D_PEER_HANDLE_BYTES]);
+int deff2d_slab_peer_attach(deff2d_ctx *ctx, const uint8_t *above, const uint8_t *below);
 /* Another rank of the group failed: abort this context's communicator so that its pending NCCL work returns
  * instead of waiting for a peer that will never arrive.  deff2d_nccl_init is needed again afterwards. */
 int deff2d_slab_abort(deff2d_ctx *ctx);

@@ -42,14 +42,18 @@ def main():
     ap.add_argument("--sweeps", type=int, default=2000)
     ap.add_argument("--skip-check", action="store_true")
     ap.add_argument("--c4", action="store_true", help="strong scaling of BASELINE config 4: one 16384^2 two-phase domain over all ranks")
+    ap.add_argument("--peer", default="1,0", help="exchange modes to check: 1 = peer-memory push fused into the kernel, 0 = NCCL deep halos")
     args = ap.parse_args()
+    import faulthandler
+    faulthandler.dump_traceback_later(240, exit=True)
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     H, W = (int(v) for v in args.size.split("x"))
     ok = True
     report = {}
-    for nphase, amp, halo in (() if args.skip_check else ((3, (2, 2), 4), (2, (1, 1), 16), (3, (1, 1), 12))):
+    modes = [bool(int(v)) for v in args.peer.split(",")]
+    for peer, (nphase, amp, halo) in (() if args.skip_check else [(pm, cs) for pm in modes for cs in ((3, (2, 2), 4), (2, (1, 1), 16), (3, (1, 1), 12))]):
         img = blobs(11 + nphase, (H, W))
         p = E.default_params(Ds=0.0 if nphase == 3 else 1e-3, Df=1.0, Dg=80.0, amp_x=amp[0], amp_y=amp[1],
                              CL=0.25, CR=1.5, check_every=400)
@@ -59,7 +63,7 @@ def main():
         ctx = E.Deff2D(local)
         if halo != 16:
             ctx.set_kernel(2, 4)                               # halo 16 runs the library's default kernel and depth
-        dom = SlabDomain(ctx, img, p, rank, world, nphase=nphase, halo=halo)
+        dom = SlabDomain(ctx, img, p, rank, world, nphase=nphase, halo=halo, peer=peer)
         L = dom.layout
         for n in (1, 4, 203):
             ref.sweeps(n)
@@ -70,16 +74,16 @@ def main():
             d_ref, d = ref.flux()[0], dom.flux()
             rel = abs(d - d_ref) / abs(d_ref)
             ok = ok and same and rel < 1e-12
-            report["p%d_h%d_n%d" % (nphase, halo, n)] = {"field_equal": bool(same), "deff_rel": rel}
+            report["peer%d_p%d_h%d_n%d" % (peer, nphase, halo, n)] = {"field_equal": bool(same), "deff_rel": rel}
         # the reference loop on the decomposed domain: same sweep count, same Deff on every rank
         ref.domain_load(img, nphase, p)
         r_ref = ref.solve(1e-4, 6000)
         ctx2 = ctx
-        dom = SlabDomain(ctx2, img, p, rank, world, nphase=nphase, halo=halo)
+        dom = SlabDomain(ctx2, img, p, rank, world, nphase=nphase, halo=halo, peer=peer)
         r = dom.solve(1e-4, 6000)
         rel = abs(r["deff_raw"] - r_ref["deff_raw"]) / abs(r_ref["deff_raw"])
         ok = ok and r["iters"] == r_ref["iters"] and rel < 1e-12
-        report["p%d_h%d_solve" % (nphase, halo)] = {"iters": r["iters"], "iters_ref": r_ref["iters"], "deff_rel": rel}
+        report["peer%d_p%d_h%d_solve" % (peer, nphase, halo)] = {"iters": r["iters"], "iters_ref": r_ref["iters"], "deff_rel": rel}
         ref.close()
         ctx.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
@@ -90,7 +94,7 @@ def main():
         img = np.load(os.path.join(ROOT, "tests", "golden", "images.npz"))["img00042"]
         p = E.default_params(amp_x=4, amp_y=4)
         ctx = E.Deff2D(local)
-        dom = SlabDomain(ctx, img, p, rank, world, weak=True)
+        dom = SlabDomain(ctx, img, p, rank, world, weak=True, peer=modes[0])
         dom.sweeps(400)                                       # warm-up incl. the CUDA-graph capture
         dom.flux()
         dist.barrier()
@@ -114,7 +118,7 @@ def main():
         img = np.tile(c4_image(4096), (4, 4))                  # periodic generator: a seamless 16384^2 medium
         p = E.default_params(Ds=1e-3, Df=1.0, mode=E.MODE_2PH_BATCH)
         ctx = E.Deff2D(local)
-        dom = SlabDomain(ctx, img, p, rank, world, nphase=2)
+        dom = SlabDomain(ctx, img, p, rank, world, nphase=2, peer=modes[0])
         dom.sweeps(400)                                       # warm-up incl. the CUDA-graph capture
         dom.flux()
         dist.barrier()
