@@ -219,24 +219,23 @@ static int peer_open_side(deff2d_ctx *c, PeerSide &sd, const PeerHandle *h)
     return DEFF2D_OK;
 }
 
-// Tile lists of the peer mode for every depth: tiles whose output box touches the first / last H own rows next to a
-// neighbour first (they feed the neighbours), then the other tiles that touch own rows; tiles inside the halo rows only
-// are not swept at all (the neighbours write those rows).
+// Tile lists of the peer mode for every depth: the tile grid covers the own rows only (the neighbours write the halo
+// rows); tiles whose output box touches the first / last H own rows next to a neighbour come first (they feed the
+// neighbours), then the rest.
 static int peer_build_lists(deff2d_ctx *c, PeerState &ps)
 {
     if (ps.key_Nx == c->Nx && ps.key_Ny == c->Ny && ps.key_above == c->halo_above && ps.key_own == c->own_rows && ps.tiles.p) return DEFF2D_OK;
     const int64_t H = std::max(c->halo_above, c->halo_below);
-    const int64_t own0 = c->halo_above, own1 = c->halo_above + c->own_rows;
     std::vector<uint32_t> all, bd, in;
     for (int T = 1; T <= 8; T++) {
         int ow, oh;
         tma_tile_geometry(c, T, &ow, &oh);
-        const int tiles_x = (int)((c->Nx + ow - 1) / ow), tiles_y = (int)((c->Ny + oh - 1) / oh);
+        // the tile grid covers the own rows only, tile row 0 starts at the first own row (the kernel adds `above`)
+        const int tiles_x = (int)((c->Nx + ow - 1) / ow), tiles_y = (int)((c->own_rows + oh - 1) / oh);
         bd.clear(); in.clear();
         for (int ty = 0; ty < tiles_y; ty++) {
-            const int64_t r0 = (int64_t)ty * oh, r1 = std::min<int64_t>(r0 + oh, c->Ny);
-            if (r1 <= own0 || r0 >= own1) continue;                               // halo rows only
-            const bool b = (c->halo_above > 0 && r0 < own0 + H) || (c->halo_below > 0 && r1 > own1 - H);
+            const int64_t r0 = (int64_t)ty * oh, r1 = std::min<int64_t>(r0 + oh, c->own_rows);
+            const bool b = (c->halo_above > 0 && r0 < H) || (c->halo_below > 0 && r1 > c->own_rows - H);
             for (int tx = 0; tx < tiles_x; tx++) (b ? bd : in).push_back(((uint32_t)ty << 16) | (uint32_t)tx);
         }
         ps.off[T] = all.size(); ps.nb[T] = (int)bd.size(); ps.cnt[T] = (int)(bd.size() + in.size());

@@ -172,6 +172,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         if constexpr (LIST) { const uint32_t v = __ldg(tile_list + t); tx = (int)(v & 0xffffu); ty = (int)(v >> 16); }
         else { ty = t / tiles_x; tx = t - ty * tiles_x; }
         ox = tx * OW; oy = ty * OH;
+        if constexpr (PEER) oy += peer.above;        // peer mode: the tile grid starts at the first own row
     };
     auto issue_load = [&](int t, int b) {
         int ox, oy;
