@@ -195,6 +195,17 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     int tile = blockIdx.x;
     const double *wtab = lut;
     long long pass = 0;
+    int pushed = 0;                             // PEER, thread 0: boundary tiles of this CTA whose pushes are not counted yet
+    auto count_pushes = [&]() {
+        __threadfence_system();
+        const unsigned long long done = atomicAdd(peer.counters + 0, (unsigned long long)pushed) + (unsigned long long)pushed;
+        pushed = 0;
+        if (done == (unsigned long long)peer.nboundary) {          // (the counter is reset when the pass closes)
+            __threadfence_system();
+            if (peer.flag_up) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer.flag_up), "l"(pass) : "memory");
+            if (peer.flag_down) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer.flag_down), "l"(pass) : "memory");
+        }
+    };
     if constexpr (PEER) {
         if (tid == 0) {
             // the halo rows this pass reads were written by the neighbours' previous pass; the halo rows this pass
@@ -452,19 +463,16 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
                         if (one) *q = v.x; else *reinterpret_cast<double2 *>(q) = v;
                     }
                 }
-                __threadfence_system();
-                __syncthreads();
-                if (tid == 0) {
-                    const unsigned long long done = atomicAdd(peer.counters + 0, 1ull) + 1ull;
-                    if (done == (unsigned long long)peer.nboundary) {          // (the counter is reset when the pass closes)
-                        __threadfence_system();
-                        if (peer.flag_up) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer.flag_up), "l"(pass) : "memory");
-                        if (peer.flag_down) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer.flag_down), "l"(pass) : "memory");
-                    }
-                }
+                __syncthreads();               // every thread's push stores are issued (ordered before thread 0's fence below)
+                if (tid == 0) pushed++;
+            } else if (tid == 0 && pushed > 0) {
+                // One tile later the pushed rows have long landed: a single system fence per CTA and pass, not one per
+                // boundary tile on the critical path (a MEMBAR.SYS behind fresh peer stores waits an NVLink round trip).
+                count_pushes();
             }
         }
     }
+    if constexpr (PEER) { if (tid == 0 && pushed > 0) count_pushes(); }
     if (tid == 0) tma_wait_all0();             // stores complete before the CTA's smem goes away
     if constexpr (PEER) {
         if (tid == 0) {                         // the last CTA to leave closes the pass

@@ -81,12 +81,13 @@ class SlabDomain:
              only the slab's rows of the image and of the mask are uploaded then (deff2d_domain_load_slab).
     """
 
-    def __init__(self, ctx, img, params, rank, world, nphase=3, halo=None, pinned=None, weak=False, nccl_id=None, peer=True):
+    def __init__(self, ctx, img, params, rank, world, nphase=3, halo=None, pinned=None, weak=False, nccl_id=None, peer=False):
         img = np.ascontiguousarray(img, dtype=np.uint8)
         Hbase, W = img.shape
         self.ctx, self.rank, self.world = ctx, int(rank), int(world)
-        # peer=True (default, ranks of one box): the sweep kernel pushes the boundary rows into the neighbours' halo rows
-        # itself (8 halo rows are enough); peer=False: NCCL send/recv of deep halos (32 rows, one exchange per 5 passes)
+        # peer=False (default): NCCL send/recv of deep halos (32 rows, one exchange per 5 passes).  peer=True (ranks of
+        # one box): the sweep kernel pushes the boundary rows into the neighbours' halo rows itself (8 halo rows are
+        # enough); bit-identical, measured 1 586-1 595 GLUP/s on 2 GPUs against 1 691-1 716 for the NCCL path
         self.peer = bool(peer) and world > 1
         if halo is None:
             halo = 8 if self.peer else 32

@@ -237,7 +237,8 @@ int deff2d_slab_flux(deff2d_ctx *ctx, double *deff_raw);
  * halo rows over NVLink; flags in peer memory order the passes of neighbouring ranks.  No NCCL call between passes,
  * no recomputed halo rows.  After every slab load: each rank exports its handle, the host layer hands every rank the
  * handles of the ranks above / below (NULL at the ends), attach (collective: it ends in a barrier).  Without it the
- * slab runs the NCCL deep-halo exchange.  Halo rows: 8 is enough (>= the pass depth). */
+ * slab runs the NCCL deep-halo exchange (the default of the host layers: measured on 2 B200s the fused path gives the
+ * same bits at 1 586-1 595 GLUP/s against 1 691-1 716).  Halo rows: 8 is enough (>= the pass depth). */
 #define DEFF2D_PEER_HANDLE_BYTES 320
 int deff2d_slab_peer_export(deff2d_ctx *ctx, uint8_t handle[DEFF2D_PEER_HANDLE_BYTES]);
 int deff2d_slab_peer_attach(deff2d_ctx *ctx, const uint8_t *above, const uint8_t *below);
