@@ -112,6 +112,7 @@ def lib():
         "deff2d_slab_abort": (i32, [vp]),
         "deff2d_slab_peer_export": (i32, [vp, c_ubyte_p]),
         "deff2d_slab_peer_attach": (i32, [vp, c_ubyte_p, c_ubyte_p]),
+        "deff2d_slab_peer_detach": (i32, [vp]),
         "deff2d_domain_load_slab_global": (i32, [vp, c_ubyte_p, i32, i32, i32, C.POINTER(Params), i64, i64, i32]),
         "deff2d_accumulate_fraction": (dbl, [i64, i64]),
         "deff2d_build_tables": (i32, [dbl, dbl, dbl, i64, i64, dbl, dbl, dbl, c_double_p, c_ubyte_p]),

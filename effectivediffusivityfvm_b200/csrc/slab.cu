@@ -510,6 +510,17 @@ DEFF2D_EXPORT int deff2d_slab_peer_attach(deff2d_ctx *c, const uint8_t *above, c
     return DEFF2D_OK;
 }
 
+DEFF2D_EXPORT int deff2d_slab_peer_detach(deff2d_ctx *c)
+{
+    if (!c) return DEFF2D_ERR_ARG;
+    SlabState *s = static_cast<SlabState *>(c->slab);
+    if (!s) return DEFF2D_OK;
+    s->peer.active = false;                       // back to the NCCL exchange; the mappings stay for the next attach
+    c->halo_valid = 0;
+    for (auto &g : s->graph) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    return DEFF2D_OK;
+}
+
 DEFF2D_EXPORT int deff2d_slab_sweeps(deff2d_ctx *c, int64_t n)
 {
     if (!c || n < 0) return DEFF2D_ERR_ARG;

@@ -167,16 +167,18 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
 
     // interior-coordinate origin of the OUTPUT box of tile t: the whole tile grid, or -- packed
     // batches and slab boundary/interior splits -- the entries of an explicit tile list
-    auto tile_origin = [&](int t, int &ox, int &oy) {
+    // `entry`: the tile's list entry (LIST only; thread 0 fetches it a whole tile visit before it is needed, so the
+    // L2 latency of the read is not paid in front of the sweeps -- the other seven warps wait for warp 0 at every barrier)
+    auto tile_origin = [&](int t, uint32_t entry, int &ox, int &oy) {
         int tx, ty;
-        if constexpr (LIST) { const uint32_t v = __ldg(tile_list + t); tx = (int)(v & 0xffffu); ty = (int)(v >> 16); }
+        if constexpr (LIST) { tx = (int)(entry & 0xffffu); ty = (int)(entry >> 16); }
         else { ty = t / tiles_x; tx = t - ty * tiles_x; }
         ox = tx * OW; oy = ty * OH;
         if constexpr (PEER) oy += peer.above;        // peer mode: the tile grid starts at the first own row
     };
-    auto issue_load = [&](int t, int b) {
+    auto issue_load = [&](int t, uint32_t entry, int b) {
         int ox, oy;
-        tile_origin(t, ox, oy);
+        tile_origin(t, entry, ox, oy);
         if constexpr (LIST) { org[2 * b] = ox; org[2 * b + 1] = oy; }   // released to the consumers by the arrive below
         mbar_expect_tx(&bar[b], TX_BYTES);
         // padded coordinates of the input box: interior (ox-TE, oy-T) -> (+XOFF, +1); even
@@ -221,8 +223,13 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         }
     }
     if (tid == 0) {
-        if (tile < ntiles) issue_load(tile, 0);
-        if (tile + (int)gridDim.x < ntiles) issue_load(tile + gridDim.x, 1);
+        uint32_t e0 = 0, e1 = 0;
+        if constexpr (LIST) {
+            if (tile < ntiles) e0 = __ldg(tile_list + tile);
+            if (tile + (int)gridDim.x < ntiles) e1 = __ldg(tile_list + tile + gridDim.x);
+        }
+        if (tile < ntiles) issue_load(tile, e0, 0);
+        if (tile + (int)gridDim.x < ntiles) issue_load(tile + gridDim.x, e1, 1);
     }
 
     // clamped neighbour positions (tile-edge patches produce halo garbage that is never stored)
@@ -232,6 +239,10 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     int k = 0;
     for (; tile < ntiles; tile += gridDim.x, k++) {
         const int b = k & 1;
+        uint32_t next_entry = 0;               // list entry of the tile after next: in flight during the prologue
+        if constexpr (LIST) {
+            if (tid == 0 && tile + 2 * (int)gridDim.x < ntiles) next_entry = __ldg(tile_list + tile + 2 * (int)gridDim.x);
+        }
         mbar_wait(&bar[b], (uint32_t)((k >> 1) & 1));
 
         // ---- patch values and weights into registers --------------------------------------
@@ -240,7 +251,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         double omc[PX];
         int ox, oy;
         if constexpr (LIST) { ox = org[2 * b]; oy = org[2 * b + 1]; }      // one global read per tile (thread 0), not 256
-        else tile_origin(tile, ox, oy);
+        else tile_origin(tile, 0u, ox, oy);
         {
             const double *in = IN0 + b * C::CELLS;
             // table index of every cell of the patch: precomputed per cell (k_build_idx, kernels.cu),
@@ -371,7 +382,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
         // prefetch the tile after next into the buffer just consumed: loads run two tiles ahead
         if (tid == 0) {
             const int nt = tile + 2 * (int)gridDim.x;
-            if (nt < ntiles) issue_load(nt, b);
+            if (nt < ntiles) issue_load(nt, next_entry, b);
         }
 
         // ---- T sweeps on chip --------------------------------------------------------------
@@ -544,6 +555,10 @@ static int encode_2d(deff2d_ctx *c, TmaState *ts, CUtensorMap *m, CUtensorMapDat
 template <int T, int F> struct Family;
 template <int T> struct Family<T, 3> { using type = Cfg<T, 4, 4, 1, 8, 16>; };
 template <int T> struct Family<T, 4> { using type = Cfg<T, 2, 8, 1, 8, 32>; };
+// (twelve warps with 2 x 6 cells per thread on 64 x 72 tiles -- 166 registers, three warps per scheduler instead of two:
+//  866 / 816 / 612 GLUP/s on config 2 / blob 4096^2 / percolation 2048^2 at depth 6 against 874 / 821 / 644: the sweep is
+//  bound by instruction dispatch (a DFMA holds a scheduler's dispatch port for two cycles) and the prologue by the LSU
+//  pipe, not by latency, so a third warp buys nothing; scripts/probe/pipe_probe.cu has the measured pipe rates)
 // (nine warps on 64 x 72 tiles do not work: registers are allocated per four warps, so 288 threads get 168 each)
 // (the 2 x 8 layout with four warps on 64 x 32 tiles and two CTAs per SM, each in its own phase of its own tile: 736
 //  GLUP/s at its best depth 4 against 871 -- the per-tile prologue weighs more on half-size tiles than the overlap gains)
@@ -627,15 +642,15 @@ static TmaState *tma_state(deff2d_ctx *c)
 }
 
 // Output-box size of the tiles of temporal depth T (64 x 64 tiles in both families).
+static int k2_family(const deff2d_ctx *c) { return (c->tile_family >= 3 && c->tile_family <= 4) ? c->tile_family : c->k2_default_family; }
+static int family_th(int fam) { (void)fam; return 64; }      // both layouts use 64 x 64 tiles
+
 void tma_tile_geometry(const deff2d_ctx *c, int T, int *ow, int *oh)
 {
     const int te = (T + 1) & ~1;
     *ow = 64 - 2 * te;
-    (void)c;
-    *oh = 64 - 2 * T;
+    *oh = family_th(c ? k2_family(c) : DEFF2D_DEFAULT_TILE_FAMILY) - 2 * T;
 }
-
-static int k2_family(const deff2d_ctx *c) { return (c->tile_family >= 3 && c->tile_family <= 4) ? c->tile_family : c->k2_default_family; }
 
 // One pass of depth T (1..8) from x[src] into x[src ^ 1] over the tiles of `list` (NULL: the whole
 // tile grid) on `stream`.
@@ -743,7 +758,7 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
     int rc;
     while (npasses >= GRAPH_PASSES && c->use_graphs) {
         // make sure the tensor maps are current before looking a graph up (re-encoding bumps the version)
-        if (ts->cfg_T != T || ts->cfg_TH != 64 || ts->key_srow0 != c->store_row0 || ts->key_srows != ((c->store_rows > 0) ? c->store_rows : c->Ny) || ts->key_x0 != c->x[0].p || ts->key_x1 != c->x[1].p ||
+        if (ts->cfg_T != T || ts->cfg_TH != family_th(k2_family(c)) || ts->key_srow0 != c->store_row0 || ts->key_srows != ((c->store_rows > 0) ? c->store_rows : c->Ny) || ts->key_x0 != c->x[0].p || ts->key_x1 != c->x[1].p ||
             ts->key_code != c->idx16.p || ts->key_Nx != c->Nx || ts->key_Ny != c->Ny || ts->key_pitch != c->pitch) {
             // a direct pass re-encodes the maps; then the graphs of the old maps are dropped below
             if ((rc = tma_pass(c, T, list, count, c->stream))) return rc;

@@ -242,6 +242,7 @@ int deff2d_slab_flux(deff2d_ctx *ctx, double *deff_raw);
 #define DEFF2D_PEER_HANDLE_BYTES 320
 int deff2d_slab_peer_export(deff2d_ctx *ctx, uint8_t handle[DEFF2D_PEER_HANDLE_BYTES]);
 int deff2d_slab_peer_attach(deff2d_ctx *ctx, const uint8_t *above, const uint8_t *below);
+int deff2d_slab_peer_detach(deff2d_ctx *ctx);      /* back to the NCCL exchange (every rank; needs >= pass-depth halo rows) */
 /* Another rank of the group failed: abort this context's communicator so that its pending NCCL work returns
  * instead of waiting for a peer that will never arrive.  deff2d_nccl_init is needed again afterwards. */
 int deff2d_slab_abort(deff2d_ctx *ctx);

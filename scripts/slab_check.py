@@ -42,6 +42,8 @@ def main():
     ap.add_argument("--sweeps", type=int, default=2000)
     ap.add_argument("--skip-check", action="store_true")
     ap.add_argument("--c4", action="store_true", help="strong scaling of BASELINE config 4: one 16384^2 two-phase domain over all ranks")
+    ap.add_argument("--detach", action="store_true")
+    ap.add_argument("--time-halo", type=int, default=0)
     ap.add_argument("--peer", default="1,0", help="exchange modes to check: 1 = peer-memory push fused into the kernel, 0 = NCCL deep halos")
     args = ap.parse_args()
     import faulthandler
@@ -94,7 +96,10 @@ def main():
         img = np.load(os.path.join(ROOT, "tests", "golden", "images.npz"))["img00042"]
         p = E.default_params(amp_x=4, amp_y=4)
         ctx = E.Deff2D(local)
-        dom = SlabDomain(ctx, img, p, rank, world, weak=True, peer=modes[0])
+        dom = SlabDomain(ctx, img, p, rank, world, weak=True, peer=modes[0], halo=args.time_halo or None)
+        if args.detach:
+            from effectivediffusivityfvm_b200 import _lib
+            _lib.lib().deff2d_slab_peer_detach(ctx._h)         # diagnostic: NCCL path on peer-mapped buffers
         dom.sweeps(400)                                       # warm-up incl. the CUDA-graph capture
         dom.flux()
         dist.barrier()
