@@ -28,24 +28,29 @@ void build_tables(const double Dphase[3], int64_t Nx, int64_t Ny, double CL, dou
 
 // The compact per-stage table read by the tiled sweep: four planes (wW, wE, wS, wN) of
 // DEFF2D_CLUT_ENTRIES doubles.  Slots are DENSE for the cells that matter: a cell whose four
-// neighbours are real phases gets slot p*16 + (pW | pE<<1 | pS<<2 | pN<<3) in a 2-phase domain
-// (32 slots = 256 bytes per plane: the gathers of a warp at a phase interface touch two cache
-// lines per plane) or p*81 + (pW + 3 pE + 9 pS + 27 pN) in a 3-phase domain (243 slots); cells on
-// the domain edge (a ghost neighbour) follow at base + p*256 + (pW | pE<<2 | pS<<4 | pN<<6).
+// neighbours are real phases has one of 32 (2-phase) or 243 (3-phase) interior slots; cells on the domain edge (a
+// ghost neighbour) follow at base + p*256 + (pW | pE<<2 | pS<<4 | pN<<6).  2-phase interior: p*16 + (pW | pE<<1 |
+// pS<<2 | pN<<3) -- the gathers of a warp at a phase interface touch two cache lines per plane.  3-phase interior:
+// the 243 neighbourhoods RANKED by how common they are in a microstructure (slot_perm: single-phase neighbourhoods
+// first, then one differing neighbour, then two adjacent ones, ...) instead of p*81 + base-3 digits, which spreads
+// the common ones over six cache lines per plane.
 #if defined(__CUDACC__)
 #define DEFF2D_HD __host__ __device__
 #else
 #define DEFF2D_HD
 #endif
-DEFF2D_HD inline unsigned clut_slot(unsigned p, unsigned w, unsigned e, unsigned s, unsigned n, bool pinned, int nphase)
+struct SlotPerm { uint8_t v[256]; };          // dense interior numbering -> ranked slot (a permutation of 0..31 / 0..242)
+const SlotPerm &slot_perm(int nphase);        // tables.cpp
+DEFF2D_HD inline unsigned clut_slot(unsigned p, unsigned w, unsigned e, unsigned s, unsigned n, bool pinned, int nphase,
+                                    const SlotPerm &perm)
 {
     if (pinned || p == 3u) return DEFF2D_CLUT_INERT;
     const bool edge = (w == 3u) || (e == 3u) || (s == 3u) || (n == 3u);
     if (nphase == 2) {
-        if (!edge) return p * 16u + (w | (e << 1) | (s << 2) | (n << 3));
+        if (!edge) return perm.v[p * 16u + (w | (e << 1) | (s << 2) | (n << 3))];
         return 32u + p * 256u + (w | (e << 2) | (s << 4) | (n << 6));
     }
-    if (!edge) return p * 81u + (w + 3u * e + 9u * s + 27u * n);
+    if (!edge) return perm.v[p * 81u + (w + 3u * e + 9u * s + 27u * n)];
     return 243u + p * 256u + (w | (e << 2) | (s << 4) | (n << 6));
 }
 void compact_table(const double *lut, double *clut, int nphase);

@@ -126,7 +126,7 @@ void launch_init_domain(cudaStream_t s, const uint8_t *img, int W, int Hsrc, int
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_build_idx(const uint8_t *__restrict__ code, uint16_t *__restrict__ idx16, long long Nx, long long Ny,
-            long long pitch, long long period, int nphase)
+            long long pitch, long long period, int nphase, const __grid_constant__ SlotPerm perm)
 {
     const long long groups_per_row = pitch / 8;
     const long long total = (Ny + 2) * groups_per_row;
@@ -146,7 +146,7 @@ k_build_idx(const uint8_t *__restrict__ code, uint16_t *__restrict__ idx16, long
             const unsigned next = (c + 1 < pitch) ? row[c + 1] : 3u;
             const unsigned n = up ? up[c] : 3u, s = dn ? dn[c] : 3u;
             // slot in the compact table (deff2d_internal.h: clut_slot); stage in bits 10-13
-            unsigned v = clut_slot(cur & 3u, prev & 3u, next & 3u, s & 3u, n & 3u, (cur & 4u) != 0, nphase);
+            unsigned v = clut_slot(cur & 3u, prev & 3u, next & 3u, s & 3u, n & 3u, (cur & 4u) != 0, nphase, perm);
             v |= ((cur >> 3) & 15u) << 10;
             const long long j = c - XOFF;                      // interior column
             if (j >= -1 && j <= Nx && (j + 1) % period == 0) v |= 0x8000u;
@@ -166,7 +166,7 @@ void launch_build_idx(cudaStream_t s, const uint8_t *code, uint16_t *idx16, int6
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    k_build_idx<<<blocks, 256, 0, s>>>(code, idx16, Nx, Ny, pitch, ghost_period, nphase);
+    k_build_idx<<<blocks, 256, 0, s>>>(code, idx16, Nx, Ny, pitch, ghost_period, nphase, slot_perm(nphase));
 }
 
 // calcPorosity's counting loop (cuh:399-405) as a reduction over the source image

@@ -96,15 +96,63 @@ void build_tables(const double Dphase[3], int64_t Nx, int64_t Ny, double CL, dou
     }
 }
 
+// Rank of the interior neighbourhoods of a 3-phase domain (deff2d_internal.h): by the number of neighbours in another
+// phase, two differing neighbours round a corner (W/S, W/N, E/S, E/N) before two opposite ones, then by the dense number.
+static SlotPerm make_perm(int nphase)
+{
+    SlotPerm out;
+    std::memset(out.v, 0, sizeof(out.v));
+    const unsigned np = (nphase == 2) ? 2u : 3u;
+    struct Item { unsigned key, raw; };
+    Item items[243];
+    unsigned count = 0;
+    for (unsigned p = 0; p < np; p++)
+        for (unsigned n = 0; n < np; n++)
+            for (unsigned s = 0; s < np; s++)
+                for (unsigned e = 0; e < np; e++)
+                    for (unsigned w = 0; w < np; w++) {
+                        const unsigned raw = (np == 2) ? p * 16u + (w | (e << 1) | (s << 2) | (n << 3)) : p * 81u + (w + 3u * e + 9u * s + 27u * n);
+                        const unsigned dw = w != p, de = e != p, ds = s != p, dn = n != p;
+                        const unsigned d = dw + de + ds + dn;
+                        const unsigned opposite = (d == 2 && ((dw && de) || (ds && dn))) ? 1u : 0u;
+                        // within a class: the pattern of differing neighbours, then the centre phase, then what the neighbours are
+                        const unsigned pattern = dw | (de << 1) | (ds << 2) | (dn << 3);
+                        items[count].key = (d << 24) | (opposite << 23) | (pattern << 16) | (raw & 0xffffu);
+                        if (np == 2) items[count].key = (d << 24) | (opposite << 23) | (pattern << 16) | p;
+                        items[count].raw = raw;
+                        count++;
+                    }
+    for (unsigned a = 1; a < count; a++) {                 // insertion sort: 243 items, once per process
+        const Item it = items[a];
+        unsigned b = a;
+        while (b > 0 && items[b - 1].key > it.key) { items[b] = items[b - 1]; b--; }
+        items[b] = it;
+    }
+    for (unsigned r = 0; r < count; r++) out.v[items[r].raw] = (uint8_t)r;
+    // Two phases: the dense numbering p * 16 + (pW | pE<<1 | pS<<2 | pN<<3) stays -- one cache line per centre phase.
+    // Measured on one B200 (same box, A/B): ranked against dense slots 884 / 877 GLUP/s on config 2 (3-phase), but 814 /
+    // 828 on the 2-phase 4096^2 blob medium and 686 / 705 on 64 packed config-3 images.
+    if (np == 2)
+        for (unsigned r = 0; r < count; r++) out.v[r] = (uint8_t)r;
+    return out;
+}
+
+const SlotPerm &slot_perm(int nphase)
+{
+    static const SlotPerm perm2 = make_perm(2), perm3 = make_perm(3);
+    return nphase == 2 ? perm2 : perm3;
+}
+
 void compact_table(const double *lut, double *clut, int nphase)
 {
+    const SlotPerm &perm = slot_perm(nphase);
     std::memset(clut, 0, sizeof(double) * 4 * DEFF2D_CLUT_ENTRIES);
     const unsigned np = (nphase == 2) ? 2u : 3u;
     for (unsigned p = 0; p < np; p++)
         for (unsigned n8 = 0; n8 < 256; n8++) {
             const unsigned w = n8 & 3u, e = (n8 >> 2) & 3u, s = (n8 >> 4) & 3u, n = (n8 >> 6) & 3u;
             if ((w != 3u && w >= np) || (e != 3u && e >= np) || (s != 3u && s >= np) || (n != 3u && n >= np)) continue;
-            const unsigned slot = clut_slot(p, w, e, s, n, false, nphase);
+            const unsigned slot = clut_slot(p, w, e, s, n, false, nphase, perm);
             const double *src = lut + (size_t)(p | (n8 << 2)) * 4;
             for (int f = 0; f < 4; f++) clut[(size_t)f * DEFF2D_CLUT_ENTRIES + slot] = src[f];
         }
@@ -119,5 +167,23 @@ DEFF2D_EXPORT int deff2d_build_tables(double Ds, double Df, double Dg, int64_t N
     if (!(omega > 0)) omega = 2.0 / 3.0;
     const double D[3] = {Df, Ds, Dg};
     deff2d::build_tables(D, Nx, Ny, CL, CR, omega, lut, dead);
+    return DEFF2D_OK;
+}
+
+DEFF2D_EXPORT int deff2d_compact_table(const double *lut, int nphase, double *clut, uint16_t *slot)
+{
+    if ((nphase != 2 && nphase != 3) || (clut && !lut)) return DEFF2D_ERR_ARG;
+    if (clut) deff2d::compact_table(lut, clut, nphase);
+    if (slot) {
+        const deff2d::SlotPerm &perm = deff2d::slot_perm(nphase);
+        const unsigned np = (unsigned)nphase;
+        for (unsigned idx = 0; idx < DEFF2D_LUT_ENTRIES; idx++) {
+            const unsigned p = idx & 3u, w = (idx >> 2) & 3u, e = (idx >> 4) & 3u, s = (idx >> 6) & 3u, n = (idx >> 8) & 3u;
+            const bool pinned = ((idx >> 10) & 1u) != 0;
+            auto bad = [np](unsigned q) { return q != 3u && q >= np; };
+            if (bad(p) || bad(w) || bad(e) || bad(s) || bad(n)) { slot[idx] = 0xffffu; continue; }
+            slot[idx] = (uint16_t)deff2d::clut_slot(p, w, e, s, n, pinned, nphase, perm);
+        }
+    }
     return DEFF2D_OK;
 }

@@ -259,6 +259,12 @@ double deff2d_accumulate_fraction(int64_t count, int64_t total);
  * 2 gas, 3 ghost (Dirichlet face for W/E, no-flux wall for S/N). */
 int deff2d_build_tables(double Ds, double Df, double Dg, int64_t Nx, int64_t Ny, double CL, double CR,
                         double omega, double *lut, uint8_t *dead);
+/* The compact planar form of `lut` that the tiled and the resident sweep gather from: clut is 4 * 1024 doubles
+ * (planes wW, wE, wS, wN), slot[idx] for the 2048 table indices of deff2d_build_tables is the plane position of that
+ * neighbourhood (1023: inert -- ghost or pinned cell, all weights 0; 0xffff: a neighbourhood that cannot occur with
+ * `nphase` phases).  Interior neighbourhoods are ranked: single-phase first, then one differing neighbour, ... so
+ * that the gathers of a warp touch as few cache lines as possible.  Either output may be NULL. */
+int deff2d_compact_table(const double *lut, int nphase, double *clut, uint16_t *slot);
 /* FloodFill (cuh:557-713) on a solid mask (1 = solid), incl. the y-periodic wrap and the
  * right-column seeding quirk (cuh:601).  grid: Ny*Nx bytes in/out (unreached non-solid
  * cells become 2).  Returns PathFlag (0/1) or a negative status. */

@@ -72,6 +72,46 @@ def test_lut_matches_reference_matrix(nphase, Ds, Dg, shape, CL, CR):
     assert np.array_equal(w + 0.0, exp)
 
 
+@pytest.mark.parametrize("nphase,Ds,Dg", [(2, 1e-3, 0.0), (3, 0.01, 50.0)])
+def test_compact_table_is_a_ranked_rearrangement_of_the_lut(nphase, Ds, Dg):
+    """The planar table the tiled sweep gathers from holds exactly the weights of the 2048-entry table (include/deff2d.h:
+    deff2d_compact_table): every possible neighbourhood has one slot, interior slots are a permutation of 0..31 /
+    0..242, and in a 3-phase table single-phase neighbourhoods and single differing neighbours come first."""
+    import ctypes as C
+    from effectivediffusivityfvm_b200 import _lib
+    L = _lib.lib()
+    lut, _ = E.build_tables(Ds, 1.0, Dg, 64, 48, 0.0, 1.0, 2.0 / 3.0)
+    lut = np.ascontiguousarray(lut, dtype=np.float64)
+    clut = np.zeros(4 * 1024, dtype=np.float64)
+    slot = np.zeros(2048, dtype=np.uint16)
+    rc = L.deff2d_compact_table(lut.ctypes.data_as(C.POINTER(C.c_double)), nphase, clut.ctypes.data_as(C.POINTER(C.c_double)),
+                                slot.ctypes.data_as(C.POINTER(C.c_uint16)))
+    assert rc == 0
+    clut = clut.reshape(4, 1024)
+    lut = lut.reshape(2048, 4)
+    idx = np.arange(2048)
+    ph = [(idx >> s) & 3 for s in (0, 2, 4, 6, 8)]
+    pinned = ((idx >> 10) & 1).astype(bool)
+    possible = np.all([(q == 3) | (q < nphase) for q in ph], axis=0)
+    assert np.all(slot[~possible] == 0xffff) and np.all(slot[possible] < 1024)
+    inert = possible & (pinned | (ph[0] == 3))
+    assert np.all(slot[inert] == 1023) and np.all(clut[:, 1023] == 0)
+    live = possible & ~inert
+    assert np.array_equal(clut[:, slot[live]].T, lut[live])            # same weights, bit for bit
+    assert len(np.unique(slot[live])) == live.sum()                    # one slot per neighbourhood
+    interior = live & np.all([q != 3 for q in ph[1:]], axis=0)
+    n_int = nphase ** 5
+    assert sorted(slot[interior]) == list(range(n_int))
+    if nphase == 3:                                                    # (2-phase: dense numbering, one line per centre phase)
+        ndiff = sum((q != ph[0]).astype(int) for q in ph[1:])
+        order = np.argsort(slot[interior])
+        assert np.all(np.diff(ndiff[interior][order]) >= 0)            # ranked by the number of differing neighbours
+        first_line = slot[interior] < 16
+        assert np.all(ndiff[interior][first_line] <= 1) and np.all(first_line[ndiff[interior] == 0])
+    else:
+        assert np.array_equal(slot[interior], ph[0][interior] * 16 + (ph[1] | ph[2] << 1 | ph[3] << 2 | ph[4] << 3)[interior])
+
+
 @pytest.mark.parametrize("nphase,Ds,Dg", [(2, 1e-3, 0.0), (3, 0.0, 50.0)])
 def test_matrix_free_sweeps_match_oracle(nphase, Ds, Dg):
     """The LUT formulation run in numpy tracks the oracle's A/b sweeps to rounding."""
