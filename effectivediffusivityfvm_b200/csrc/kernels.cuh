@@ -46,17 +46,19 @@ struct SolveState {
 };
 
 // PEER variant (slab.cu, peer-memory halo exchange fused into the sweep): a rank sweeps only its own rows; the tiles
-// next to a neighbouring slab come first in the tile list and, besides their local store, copy the rows the neighbour
-// needs straight into its halo rows over NVLink (peer-mapped memory).  When the last of those tiles is done the
-// neighbours' flags are raised; every pass starts by waiting for the neighbours' flags of the pass before.
+// next to a neighbouring slab come early in the tile list (behind one interior tile per CTA, which hides the flag
+// wait) and, besides their local store, copy the rows the neighbour needs straight into its halo rows over NVLink
+// (peer-mapped memory).  When the last of those tiles is counted the neighbours' flags are raised; every pass waits
+// for the neighbours' flags of the pass before ahead of its first boundary tile.
 struct PeerArgs {
     double *up[2], *down[2];          // neighbours' iterate buffers (by parity), at halo row 0 / column 0 of the interior; NULL: no neighbour
     long long *flag_up, *flag_down;   // the neighbours' flag words this rank raises (peer memory)
     const long long *flag_local;      // [0]: raised by the upper neighbour, [1]: by the lower one
-    unsigned long long *counters;     // [0]: boundary tiles finished in this pass, [1]: CTAs finished (both reset when the pass closes)
-    long long *pass_no;               // passes completed on this rank since the domain was loaded
+    unsigned long long *counters;     // boundary tiles pushed and counted in this pass (reset by the thread that counts the last one)
+    long long *pass_no;               // passes completed on this rank since the domain was loaded (advanced by the same thread)
     long long pitch;
     int above, own, H, nboundary, Nx;
+    int lead;                         // list entries in front of the boundary tiles (one interior tile per CTA, or 0)
 };
 
 struct Counts {

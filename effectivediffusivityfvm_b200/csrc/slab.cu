@@ -116,9 +116,9 @@ struct PeerState {
     long long *sync = nullptr;       // own block: [0] flag from above, [1] flag from below, [2] boundary tiles done,
                                      //            [3] CTAs done, [4] passes done
     PeerSide up, down;
-    DevBuf<uint32_t> tiles;          // per depth T: boundary tiles first, then the other tiles that touch own rows
+    DevBuf<uint32_t> tiles;          // per depth T: one interior tile per CTA, the boundary tiles, the other interior tiles
     size_t off[9] = {0};
-    int cnt[9] = {0}, nb[9] = {0};
+    int cnt[9] = {0}, nb[9] = {0}, lead[9] = {0};
     int64_t key_Nx = -1, key_Ny = -1, key_above = -1, key_own = -1;
 };
 
@@ -220,8 +220,8 @@ static int peer_open_side(deff2d_ctx *c, PeerSide &sd, const PeerHandle *h)
 }
 
 // Tile lists of the peer mode for every depth: the tile grid covers the own rows only (the neighbours write the halo
-// rows); tiles whose output box touches the first / last H own rows next to a neighbour come first (they feed the
-// neighbours), then the rest.
+// rows); tiles whose output box touches the first / last H own rows next to a neighbour (they feed the neighbours)
+// come right after one interior tile per CTA, then the rest.
 static int peer_build_lists(deff2d_ctx *c, PeerState &ps)
 {
     if (ps.key_Nx == c->Nx && ps.key_Ny == c->Ny && ps.key_above == c->halo_above && ps.key_own == c->own_rows && ps.tiles.p) return DEFF2D_OK;
@@ -238,9 +238,14 @@ static int peer_build_lists(deff2d_ctx *c, PeerState &ps)
             const bool b = (c->halo_above > 0 && r0 < H) || (c->halo_below > 0 && r1 > c->own_rows - H);
             for (int tx = 0; tx < tiles_x; tx++) (b ? bd : in).push_back(((uint32_t)ty << 16) | (uint32_t)tx);
         }
-        ps.off[T] = all.size(); ps.nb[T] = (int)bd.size(); ps.cnt[T] = (int)(bd.size() + in.size());
+        // list: one interior tile per CTA (their loads need no neighbour: the flag wait hides behind them), the boundary
+        // tiles, the other interior tiles
+        const size_t ncta = (size_t)std::min<int64_t>(c->prop.multiProcessorCount, (int64_t)(bd.size() + in.size()));
+        const size_t lead = (in.size() >= ncta) ? ncta : 0;
+        ps.off[T] = all.size(); ps.nb[T] = (int)bd.size(); ps.cnt[T] = (int)(bd.size() + in.size()); ps.lead[T] = (int)lead;
+        all.insert(all.end(), in.begin(), in.begin() + lead);
         all.insert(all.end(), bd.begin(), bd.end());
-        all.insert(all.end(), in.begin(), in.end());
+        all.insert(all.end(), in.begin() + lead, in.end());
     }
     if (ps.tiles.cap < all.size() || !ps.tiles.p) {
         if (ps.tiles.p) cudaFree(ps.tiles.p);
@@ -273,6 +278,7 @@ static int peer_pass(deff2d_ctx *c, SlabState *s, int T)
     pa.pass_no = ps.sync + 4;
     pa.pitch = c->pitch;
     pa.above = (int)c->halo_above; pa.own = (int)c->own_rows; pa.H = (int)H; pa.nboundary = ps.nb[T]; pa.Nx = (int)c->Nx;
+    pa.lead = ps.lead[T];
     c->store_row0 = c->halo_above; c->store_rows = c->own_rows;
     const int rc = tma_peer_pass(c, T, ps.tiles.p + ps.off[T], ps.cnt[T], &pa);
     c->store_row0 = 0; c->store_rows = 0;

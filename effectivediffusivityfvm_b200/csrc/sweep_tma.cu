@@ -142,7 +142,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     // omega = 1 table u; ghost columns keep their value (factor 0)
     constexpr bool CHEB = (VAR & 2) != 0;
     constexpr bool PEER = (VAR & 1) != 0;     // peer-memory halo exchange fused into the pass (needs LIST)
-    static_assert(!PEER || LIST, "the peer variant walks a tile list (boundary tiles first)");
+    static_assert(!PEER || LIST, "the peer variant walks a tile list (boundary tiles early)");
     static_assert(C::NWX == 1, "a warp spans the tile width (W / E halo by shuffles)");
 
     // No integer round trip on the base pointer: the compiler must keep seeing the shared
@@ -198,20 +198,43 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     const double *wtab = lut;
     long long pass = 0;
     int pushed = 0;                             // PEER, thread 0: boundary tiles of this CTA whose pushes are not counted yet
-    auto count_pushes = [&]() {
-        __threadfence_system();
-        const unsigned long long done = atomicAdd(peer.counters + 0, (unsigned long long)pushed) + (unsigned long long)pushed;
+    // One device-scope fence per CTA and pass (count_issue); the thread that counts the last boundary tile of the pass has then
+    // observed every other CTA's pushes (its atomic reads their counts), so its system-scope fence + release store
+    // publishes all of them: the neighbours' flags show this pass.  It also closes the pass on this rank (counter back
+    // to 0, pass number + 1) -- nobody else touches either before the next launch.  A CTA that starts so late that it
+    // already reads the new pass number has no boundary tile (they are all counted) and merely waits for flags that
+    // its neighbours raise during their current pass.
+    // The count is split: count_issue sends the atomic, count_finish -- a tile visit later -- looks at what it returned,
+    // so that its round trip to L2 is not waited for in front of a CTA-wide barrier.
+    unsigned long long counted = 0;             // what the atomic returned + this CTA's share; 0: nothing pending
+    auto count_issue = [&]() {
+        __threadfence();
+        counted = atomicAdd(peer.counters, (unsigned long long)pushed) + (unsigned long long)pushed;
         pushed = 0;
-        if (done == (unsigned long long)peer.nboundary) {          // (the counter is reset when the pass closes)
-            __threadfence_system();
-            if (peer.flag_up) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer.flag_up), "l"(pass) : "memory");
-            if (peer.flag_down) asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(peer.flag_down), "l"(pass) : "memory");
-        }
     };
-    if constexpr (PEER) {
-        if (tid == 0) {
-            // the halo rows this pass reads were written by the neighbours' previous pass; the halo rows this pass
-            // writes were read by it: both are over once their flags show that pass
+    auto count_finish = [&]() {
+        if (counted == (unsigned long long)peer.nboundary) {
+            *reinterpret_cast<volatile unsigned long long *>(peer.counters) = 0ull;
+            *reinterpret_cast<volatile long long *>(peer.pass_no) = pass + 1;
+            __threadfence_system();             // one system fence, then relaxed flag stores: a release pattern for both flags
+            if (peer.flag_up) asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(peer.flag_up), "l"(pass) : "memory");
+            if (peer.flag_down) asm volatile("st.relaxed.sys.global.s64 [%0], %1;" ::"l"(peer.flag_down), "l"(pass) : "memory");
+        }
+        counted = 0;
+    };
+    if (tid == 0) {
+        uint32_t e0 = 0, e1 = 0;
+        if constexpr (LIST) {
+            if (tile < ntiles) e0 = __ldg(tile_list + tile);
+            if (tile + (int)gridDim.x < ntiles) e1 = __ldg(tile_list + tile + gridDim.x);
+        }
+        if constexpr (PEER) {
+            // The halo rows this pass reads were written by the neighbours' previous pass; the halo rows this pass
+            // writes were read by it: both are over once their flags show that pass.  The first `lead` list entries
+            // (one per CTA) are tiles away from the neighbours -- they read and write own rows only -- so their loads
+            // go out before the flags are looked at.  (Looking at the flags only behind the first tile's prologue and
+            // issuing the second tile's load there was slower: 231.6 against 227.3 us per pass.)
+            if (peer.lead > 0 && tile < ntiles) issue_load(tile, e0, 0);
             pass = *reinterpret_cast<volatile long long *>(peer.pass_no);
             auto flag_at_least = [&](const long long *f, long long want) {
                 long long v;
@@ -220,15 +243,10 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
             if (peer.up[0]) flag_at_least(peer.flag_local + 0, pass - 1);
             if (peer.down[0]) flag_at_least(peer.flag_local + 1, pass - 1);
             fence_proxy_async();
+            if (peer.lead == 0 && tile < ntiles) issue_load(tile, e0, 0);
+        } else {
+            if (tile < ntiles) issue_load(tile, e0, 0);
         }
-    }
-    if (tid == 0) {
-        uint32_t e0 = 0, e1 = 0;
-        if constexpr (LIST) {
-            if (tile < ntiles) e0 = __ldg(tile_list + tile);
-            if (tile + (int)gridDim.x < ntiles) e1 = __ldg(tile_list + tile + gridDim.x);
-        }
-        if (tile < ntiles) issue_load(tile, e0, 0);
         if (tile + (int)gridDim.x < ntiles) issue_load(tile + gridDim.x, e1, 1);
     }
 
@@ -455,47 +473,41 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
             tma_commit();
         }
         if constexpr (PEER) {
-            if (k * (int)gridDim.x + (int)blockIdx.x < peer.nboundary) {     // boundary tiles come first in the list
-                // rows of the output box among the first / last H own rows -> the neighbour's halo rows, 16 bytes per store
-                const int dst = src ^ 1;
-                for (int e = tid; e < OH * (OW / 2); e += C::NT) {
-                    const int r = e / (OW / 2), cpair = (e - r * (OW / 2)) * 2;
-                    const int row_own = oy + r - peer.above, col = ox + cpair;
-                    if (col >= peer.Nx) continue;
-                    const double2 v = *reinterpret_cast<const double2 *>(OUT + r * OW + cpair);
-                    const bool one = (col + 1 >= peer.Nx);
-                    if (peer.up[dst] && row_own >= 0 && row_own < peer.H) {
-                        double *q = peer.up[dst] + (long long)row_own * peer.pitch + col;
-                        if (one) *q = v.x; else *reinterpret_cast<double2 *>(q) = v;
+            const int entry_no = k * (int)gridDim.x + (int)blockIdx.x;
+            if (entry_no >= peer.lead && entry_no < peer.lead + peer.nboundary) {     // the boundary tiles follow the lead tiles in the list
+                // rows of the output box among the first / last H own rows -> the neighbour's halo rows, 16 bytes per
+                // store; only those rows are walked (at most H of the OH rows of the box)
+                const int oyo = oy - peer.above;                                   // first output row, own-row coordinates
+                const int ncol2 = min(OW, peer.Nx - ox + 1) >> 1;                  // column pairs inside the domain (the last may be half)
+                double *const up = src ? peer.up[0] : peer.up[1], *const down = src ? peer.down[0] : peer.down[1];
+                auto push_rows = [&](double *dstbase, int r_lo, int r_hi, int row_shift) {
+                    // box rows [r_lo, r_hi) -> neighbour rows (oyo + r - row_shift)
+                    const int n = (r_hi - r_lo) * ncol2;
+                    for (int e = tid; e < n; e += C::NT) {
+                        const int r = r_lo + e / ncol2, cpair = (e % ncol2) * 2;
+                        const double2 v = *reinterpret_cast<const double2 *>(OUT + r * OW + cpair);
+                        double *q = dstbase + (long long)(oyo + r - row_shift) * peer.pitch + ox + cpair;
+                        if (ox + cpair + 1 >= peer.Nx) *q = v.x; else *reinterpret_cast<double2 *>(q) = v;
                     }
-                    const int rd = row_own - (peer.own - peer.H);
-                    if (peer.down[dst] && rd >= 0 && rd < peer.H && row_own < peer.own) {
-                        double *q = peer.down[dst] + (long long)rd * peer.pitch + col;
-                        if (one) *q = v.x; else *reinterpret_cast<double2 *>(q) = v;
-                    }
-                }
+                };
+                if (up) push_rows(up, max(0, -oyo), min(OH, peer.H - oyo), 0);
+                if (down) push_rows(down, max(0, peer.own - peer.H - oyo), min(OH, peer.own - oyo), peer.own - peer.H);
                 __syncthreads();               // every thread's push stores are issued (ordered before thread 0's fence below)
                 if (tid == 0) pushed++;
-            } else if (tid == 0 && pushed > 0) {
-                // One tile later the pushed rows have long landed: a single system fence per CTA and pass, not one per
-                // boundary tile on the critical path (a MEMBAR.SYS behind fresh peer stores waits an NVLink round trip).
-                count_pushes();
+            } else if (tid == 0) {
+                // a tile after the pushes the rows have long left the SM: the fence in count_issue does not wait for them
+                if (counted) count_finish();
+                if (pushed > 0) count_issue();
             }
         }
     }
-    if constexpr (PEER) { if (tid == 0 && pushed > 0) count_pushes(); }
-    if (tid == 0) tma_wait_all0();             // stores complete before the CTA's smem goes away
     if constexpr (PEER) {
-        if (tid == 0) {                         // the last CTA to leave closes the pass
-            const unsigned long long done = atomicAdd(peer.counters + 1, 1ull) + 1ull;
-            if (done == (unsigned long long)gridDim.x) {
-                peer.counters[0] = 0ull;        // every boundary tile of this pass has been counted
-                peer.counters[1] = 0ull;
-                __threadfence();
-                *reinterpret_cast<volatile long long *>(peer.pass_no) = pass + 1;
-            }
+        if (tid == 0) {
+            if (counted) count_finish();
+            if (pushed > 0) { count_issue(); count_finish(); }
         }
     }
+    if (tid == 0) tma_wait_all0();             // stores complete before the CTA's smem goes away
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -695,7 +707,7 @@ int tma_cheb_pass(deff2d_ctx *c, const double tau[8])
     return DEFF2D_OK;
 }
 
-// Slab peer mode (slab.cu): one pass of depth T over `list` (boundary tiles first, `nboundary` of them) with the halo
+// Slab peer mode (slab.cu): one pass of depth T over `list` (`lead` interior tiles, then the `nboundary` boundary tiles, then the rest) with the halo
 // push fused into the kernel; flips c->cur.  c->store_row0 / store_rows select the own rows for the local store.
 template <int T>
 static int peer_launch(deff2d_ctx *c, TmaState *ts, const uint32_t *list, int count, const PeerArgs &pa)

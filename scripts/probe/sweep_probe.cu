@@ -351,6 +351,18 @@ __global__ void __launch_bounds__(NW * 32, 1) sweep(const double *__restrict__ i
         } else if (VARIANT == 5) {
 #pragma unroll 1
             for (int s = 1; s <= T; s++) pipelined_sweep(s, std::integral_constant<int, 1>());
+        } else if (VARIANT == 10) {
+#pragma unroll 2
+            for (int s = 1; s <= T; s++) scatter_sweep(s);
+        } else if (VARIANT == 11) {
+#pragma unroll 3
+            for (int s = 1; s <= T; s++) scatter_sweep(s);
+        } else if (VARIANT == 12) {
+#pragma unroll 2
+            for (int s = 1; s <= T; s++) one_sweep(s);
+        } else if (VARIANT == 13) {
+#pragma unroll 3
+            for (int s = 1; s <= T; s++) one_sweep(s);
         } else if (VARIANT == 3) {
 #pragma unroll 1
             for (int s = 1; s <= T; s++) scatter_sweep(s);
@@ -410,6 +422,10 @@ int main()
     run<2, 8, 8, 6, 6>("2x8, all warps with 4 uniform weights", init, out, cyc, nsm);
     run<2, 8, 8, 6, 7>("2x8, odd warps with 4 uniform weights", init, out, cyc, nsm);
     run<2, 8, 8, 6, 8>("2x8, hand-scheduled scatter order", init, out, cyc, nsm);
+    run<2, 8, 8, 6, 10>("2x8, scatter order, unroll 2", init, out, cyc, nsm);
+    run<2, 8, 8, 6, 11>("2x8, scatter order, unroll 3", init, out, cyc, nsm);
+    run<2, 8, 8, 6, 12>("2x8, gather order, unroll 2", init, out, cyc, nsm);
+    run<2, 8, 8, 6, 13>("2x8, gather order, unroll 3", init, out, cyc, nsm);
     run<2, 6, 12, 6, 0>("2x6, 12 warps, unrolled", init, out, cyc, nsm);
     run<2, 4, 16, 6, 0>("2x4, 16 warps, unrolled", init, out, cyc, nsm);
     run<4, 4, 8, 6, 0>("4x4 (32 lanes: 128 columns), 8 warps", init, out, cyc, nsm);
