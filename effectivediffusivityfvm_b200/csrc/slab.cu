@@ -19,6 +19,9 @@
 // gain, the remaining scaling loss is the extra wave of tiles the halo rows add (83 instead of 82 rounds of 148 tiles on
 // config 2) -- and it did not complete on 4 GPUs.
 //
+// Alternative without NCCL in the loop (peer mode, below: deff2d_slab_peer_export / _attach): the neighbours' buffers are
+// mapped and the sweep kernel pushes the boundary rows itself; equal at 4 GPUs, 11 % faster at 8 (config 4).
+//
 // NCCL is bound at run time (dlopen of libnccl.so.2): a process that already loaded NCCL (e.g.
 // through torch) shares that copy, and single-GPU users need no NCCL at all.
 #include <dlfcn.h>
@@ -496,21 +499,28 @@ DEFF2D_EXPORT int deff2d_slab_peer_attach(deff2d_ctx *c, const uint8_t *above, c
         set_error(c, "peer attach: a handle is needed exactly where the slab has a neighbour");
         return DEFF2D_ERR_ARG;
     }
-    if (H < 1 || H > 64 || c->own_rows < 2 * H) { set_error(c, "peer mode needs 1..64 halo rows and at least twice as many own rows"); return DEFF2D_ERR_ARG; }
+    // From here on every rank reaches the all-reduce below, also one whose slab is too thin or whose mapping failed: it
+    // reports the failure through the reduced word, and all ranks return an error together (the caller then stays with
+    // the NCCL exchange) instead of the healthy ones waiting for it in the barrier.
     PeerHandle hu, hd;
-    if (above) { std::memcpy(&hu, above, sizeof(hu)); if (hu.Nx != c->Nx || hu.pitch != c->pitch || hu.below != H) { set_error(c, "peer attach: the upper neighbour's slab does not match"); return DEFF2D_ERR_ARG; } }
-    if (below) { std::memcpy(&hd, below, sizeof(hd)); if (hd.Nx != c->Nx || hd.pitch != c->pitch || hd.above != H) { set_error(c, "peer attach: the lower neighbour's slab does not match"); return DEFF2D_ERR_ARG; } }
-    int rc;
-    if ((rc = peer_open_side(c, ps.up, above ? &hu : nullptr))) return rc;
-    if ((rc = peer_open_side(c, ps.down, below ? &hd : nullptr))) return rc;
-    if ((rc = peer_build_lists(c, ps))) return rc;
-    // flags -1 ("no pass yet"), counters 0, pass 0 -- then every rank must have got here before anyone pushes a row
-    // into a neighbour (whose load may still be writing its buffers): one all-reduce as a barrier
-    const long long init[8] = {-1, -1, 0, 0, 0, 0, 0, 0};
+    int rc = DEFF2D_OK;
+    if (H < 1 || H > 64 || c->own_rows < 2 * H) { set_error(c, "peer mode needs 1..64 halo rows and at least twice as many own rows"); rc = DEFF2D_ERR_ARG; }
+    if (above && !rc) { std::memcpy(&hu, above, sizeof(hu)); if (hu.Nx != c->Nx || hu.pitch != c->pitch || hu.below != H) { set_error(c, "peer attach: the upper neighbour's slab does not match"); rc = DEFF2D_ERR_ARG; } }
+    if (below && !rc) { std::memcpy(&hd, below, sizeof(hd)); if (hd.Nx != c->Nx || hd.pitch != c->pitch || hd.above != H) { set_error(c, "peer attach: the lower neighbour's slab does not match"); rc = DEFF2D_ERR_ARG; } }
+    if (!rc) rc = peer_open_side(c, ps.up, above ? &hu : nullptr);
+    if (!rc) rc = peer_open_side(c, ps.down, below ? &hd : nullptr);
+    if (!rc) rc = peer_build_lists(c, ps);
+    // flags -1 ("no pass yet"), counters 0, pass 0, [6] = "this rank failed" -- then every rank must have got here before
+    // anyone pushes a row into a neighbour (whose load may still be writing its buffers): one all-reduce as a barrier
+    const long long init[8] = {-1, -1, 0, 0, 0, 0, rc ? 1 : 0, 0};
+    long long failed = 0;
     CUS(cudaMemcpyAsync(ps.sync, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
     NCCLCHECK(api->AllReduce(ps.sync + 6, ps.sync + 6, 1, ncclInt64, ncclSum, s->comm, c->stream));
+    CUS(cudaMemcpyAsync(&failed, ps.sync + 6, sizeof(failed), cudaMemcpyDeviceToHost, c->stream));
     CUS(cudaStreamSynchronize(c->stream));
     c->launches++;
+    if (rc) return rc;
+    if (failed) { set_error(c, "peer attach: %lld rank(s) of the group could not map their neighbours", failed); return DEFF2D_ERR_STATE; }
     ps.active = true;
     for (auto &g : s->graph) if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
     return DEFF2D_OK;

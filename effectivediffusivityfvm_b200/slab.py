@@ -81,14 +81,31 @@ class SlabDomain:
              only the slab's rows of the image and of the mask are uploaded then (deff2d_domain_load_slab).
     """
 
-    def __init__(self, ctx, img, params, rank, world, nphase=3, halo=None, pinned=None, weak=False, nccl_id=None, peer=False):
+    def __init__(self, ctx, img, params, rank, world, nphase=3, halo=None, pinned=None, weak=False, nccl_id=None, peer=None):
         img = np.ascontiguousarray(img, dtype=np.uint8)
-        Hbase, W = img.shape
         self.ctx, self.rank, self.world = ctx, int(rank), int(world)
-        # peer=False (default): NCCL send/recv of deep halos (32 rows, one exchange per 5 passes).  peer=True (ranks of
-        # one box): the sweep kernel pushes the boundary rows into the neighbours' halo rows itself (8 halo rows are
-        # enough); bit-identical, measured 1 586-1 595 GLUP/s on 2 GPUs against 1 691-1 716 for the NCCL path
-        self.peer = bool(peer) and world > 1
+        # peer=False: NCCL send/recv of deep halos (32 rows, one exchange per 5 passes).  peer=True (ranks of one box):
+        # the sweep kernel pushes the boundary rows into the neighbours' halo rows itself (8 halo rows, none
+        # recomputed); bit-identical.  Measured (B200, GLUP/s, peer / NCCL): 2 GPUs 1 686 / 1 712 (config 2 stacked) and
+        # 1 687 / 1 711 (config 4); 8 GPUs 6 730 / 6 661 and 6 426 / 5 790.  peer=None (default): peer mode from 4 ranks
+        # up, and the NCCL exchange if the ranks cannot map each other's memory (they decide together).
+        auto = peer is None
+        self.peer = (world >= 4) if auto else (bool(peer) and world > 1)
+        if nccl_id is None:
+            nccl_id = self._broadcast_id()
+        ctx.nccl_init(nccl_id, rank, world)
+        try:
+            self._setup(img, params, nphase, halo, pinned, weak)
+        except RuntimeError:
+            # the attach failed on every rank together (deff2d_slab_peer_attach reduces the failures over the group)
+            if not (auto and self.peer):
+                raise
+            self.peer = False
+            self._setup(img, params, nphase, halo, pinned, weak)
+
+    def _setup(self, img, params, nphase, halo, pinned, weak):
+        ctx, rank, world = self.ctx, self.rank, self.world
+        Hbase, W = img.shape
         if halo is None:
             halo = 8 if self.peer else 32
         H = Hbase * world if weak else Hbase
@@ -96,9 +113,6 @@ class SlabDomain:
         self.layout = L = SlabLayout(H, rank, world, params.amp_y, halo)
         self.Nx = W * params.amp_x
         self.global_cells = self.Nx * L.ny_global
-        if nccl_id is None:
-            nccl_id = self._broadcast_id()
-        ctx.nccl_init(nccl_id, rank, world)
         self.pathflag = None
         if pinned is None:
             # default: every rank uploads the WHOLE source image (1 B per pixel); FloodFill (cuh:557-713) runs on its
@@ -125,9 +139,14 @@ class SlabDomain:
         if not self.peer:
             return
         import torch.distributed as dist
-        mine = self.ctx.slab_peer_export()
+        try:
+            mine = self.ctx.slab_peer_export()
+        except RuntimeError:
+            mine = None                                    # (no IPC handle for these buffers): tell the others
         handles = [None] * self.world
         dist.all_gather_object(handles, mine)
+        if any(h is None for h in handles):
+            raise RuntimeError("peer mode: a rank of the group could not export its buffers")
         self.ctx.slab_peer_attach(handles[self.rank - 1] if self.rank > 0 else None,
                                   handles[self.rank + 1] if self.rank < self.world - 1 else None)
 
