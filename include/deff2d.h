@@ -233,12 +233,15 @@ int deff2d_slab_sweeps(deff2d_ctx *ctx, int64_t n);
 /* Global Deff: local {Q1,Q2} -> ncclAllReduce(sum) -> same value on every rank; blocks. */
 int deff2d_slab_flux(deff2d_ctx *ctx, double *deff_raw);
 /* Peer-memory halo exchange, fused into the sweep kernel (one process or thread per GPU of one box): a rank sweeps
- * only its own rows; the tiles next to a neighbour run first and copy the rows that neighbour needs straight into its
- * halo rows over NVLink; flags in peer memory order the passes of neighbouring ranks.  No NCCL call between passes,
- * no recomputed halo rows.  After every slab load: each rank exports its handle, the host layer hands every rank the
- * handles of the ranks above / below (NULL at the ends), attach (collective: it ends in a barrier).  Without it the
- * slab runs the NCCL deep-halo exchange (the default of the host layers: measured on 2 B200s the fused path gives the
- * same bits at 1 586-1 595 GLUP/s against 1 691-1 716).  Halo rows: 8 is enough (>= the pass depth). */
+ * only its own rows; the tiles next to a neighbour run early in a pass and copy the rows that neighbour needs straight
+ * into its halo rows over NVLink; flags in peer memory order the passes of neighbouring ranks.  No NCCL call between
+ * passes, no recomputed halo rows.  After every slab load: each rank exports its handle, the host layer hands every
+ * rank the handles of the ranks above / below (NULL at the ends), attach.  The attach is collective (it ends in an
+ * all-reduce that doubles as a barrier) and returns an error on EVERY rank if any rank could not map its neighbours or
+ * has a slab thinner than 2 x halo rows, so that the group can stay with the NCCL exchange together.  Same bits as the
+ * NCCL deep-halo exchange; measured on B200s (GLUP/s, fused / NCCL): 2 GPUs 1 686 / 1 712, 4 GPUs 3 341 / 3 314,
+ * 8 GPUs 6 426 / 5 790 on one 16384^2 domain -- the Python host layer uses it from 4 ranks up.  Halo rows: 8 is enough
+ * (>= the pass depth, <= 64). */
 #define DEFF2D_PEER_HANDLE_BYTES 320
 int deff2d_slab_peer_export(deff2d_ctx *ctx, uint8_t handle[DEFF2D_PEER_HANDLE_BYTES]);
 int deff2d_slab_peer_attach(deff2d_ctx *ctx, const uint8_t *above, const uint8_t *below);
