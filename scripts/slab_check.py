@@ -88,6 +88,29 @@ def main():
         report["peer%d_p%d_h%d_solve" % (peer, nphase, halo)] = {"iters": r["iters"], "iters_ref": r_ref["iters"], "deff_rel": rel}
         ref.close()
         ctx.close()
+    if not args.skip_check and world >= 2:
+        # A peer attach that fails on ONE rank (its slab is thinner than twice the halo) must fail on every rank of the
+        # group, not leave the healthy ones waiting in the barrier; afterwards the same context still runs the NCCL exchange.
+        rows = 20 * (2 * world) - 1                            # last rank gets 39 rows, the others 40: 2 x halo = 40
+        img = blobs(5, (rows, 96))
+        p = E.default_params(Ds=1e-3, Df=1.0, CL=0.25, CR=1.5, check_every=400)
+        ctx = E.Deff2D(local)
+        try:
+            SlabDomain(ctx, img, p, rank, world, nphase=2, halo=20, peer=True)
+            failed_together = False
+        except RuntimeError:
+            failed_together = True
+        dom = SlabDomain(ctx, img, p, rank, world, nphase=2, halo=20, peer=False)
+        ref = E.Deff2D(local)
+        ref.domain_load(img, 2, p)
+        ref.sweeps(50)
+        dom.sweeps(50)
+        L = dom.layout
+        same = np.array_equal(dom.own_field(), ref.get_field()[L.row0:L.row0 + L.own_rows], equal_nan=True)
+        ok = ok and failed_together and same
+        report["peer_attach_fails_on_all_ranks"] = {"failed_together": failed_together, "nccl_afterwards_equal": bool(same)}
+        ref.close()
+        ctx.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
