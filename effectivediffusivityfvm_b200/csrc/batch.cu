@@ -453,7 +453,7 @@ static int batch_stream(deff2d_ctx *c, int count, int W, int H, const deff2d_par
     // staging of one refill (at most every slot at once): source images and their FloodFill states / pinned masks
     if ((rc = grow(c->img, npix * (size_t)nslots)) || (rc = grow(c->grid, (size_t)cells * (size_t)nslots))) return rc;
     if ((rc = grow(c->lut, (size_t)nstages * DEFF2D_LUT_ENTRIES * 4)) || (rc = grow(c->dead, (size_t)nstages * DEFF2D_LUT_ENTRIES)) ||
-        (rc = grow(c->clut, (size_t)nstages * DEFF2D_CLUT_ENTRIES * 4))) return rc;
+        (rc = grow(c->clut, (size_t)nstages * DEFF2D_CLUT_ENTRIES * 4)) || (rc = grow(c->clut32, (size_t)nstages * DEFF2D_CLUT_ENTRIES * 8))) return rc;
     c->lut_stages = nstages;
     if (want_fields && (rc = grow(c->dense, (size_t)cells))) return rc;
     if ((rc = dev_ensure(c, b->slots, (size_t)nslots)) || (rc = dev_ensure(c, b->outs, (size_t)nslots)) ||
@@ -478,7 +478,10 @@ static int batch_stream(deff2d_ctx *c, int count, int W, int H, const deff2d_par
                          dead.data() + (size_t)k * DEFF2D_LUT_ENTRIES);
             compact_table(lut.data() + (size_t)k * DEFF2D_LUT_ENTRIES * 4, clut.data() + (size_t)k * DEFF2D_CLUT_ENTRIES * 4, nphase);
         }
+        std::vector<uint32_t> clut32((size_t)nstages * DEFF2D_CLUT_ENTRIES * 8);
+        split_table(clut.data(), clut32.data(), nstages);
         CUB(cudaMemcpyAsync(c->clut.p, clut.data(), clut.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        CUB(cudaMemcpyAsync(c->clut32.p, clut32.data(), clut32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
         CUB(cudaMemcpyAsync(c->lut.p, lut.data(), lut.size() * sizeof(double), cudaMemcpyHostToDevice, s));
         CUB(cudaMemcpyAsync(c->dead.p, dead.data(), dead.size(), cudaMemcpyHostToDevice, s));
         CUB(cudaStreamSynchronize(s));
@@ -494,6 +497,7 @@ static int batch_stream(deff2d_ctx *c, int count, int W, int H, const deff2d_par
         ~Restore() { c->tile_family = fam; c->tblock = tb; c->tile_list = nullptr; c->tile_count = 0; }
     } restore_guard{c, old_family, old_tblock};
     c->tile_family = 0;                                  // the default thread layout
+    c->gather32 = 0;                                     // 8-byte weight gathers (the statistic that selects the other kind is per domain load)
     // tile grids of the pass depths in use (T and the remainders 1..T-1)
     int ow[9], oh[9], tx_n[9], ty_n[9];
     size_t tiles_cap = 0;
@@ -588,7 +592,7 @@ static int batch_stream(deff2d_ctx *c, int count, int W, int H, const deff2d_par
                                                                             b->slots.p, b->outs.p);
             // the table indices of the new images (and of their neighbours' shared ghost ring); the whole stack is
             // rebuilt -- 3 B per cell, once per refill, against >= 10 000 sweeps between refills
-            launch_build_idx(s, c->code.p, c->idx16.p, c->Nx, c->Ny, c->pitch, c->ghost_period, nphase);
+            launch_build_idx(s, c->code.p, c->idx16.p, c->Nx, c->Ny, c->pitch, c->ghost_period, nphase, nullptr);
             c->launches += 3;
             CUB(cudaStreamSynchronize(s));                   // the staging buffer is free for the next refill
         }

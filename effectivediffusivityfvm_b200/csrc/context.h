@@ -44,6 +44,8 @@ struct deff2d_ctx {
     DevBuf<uint16_t> idx16;          // per-cell weight-table index derived from `code` (k_build_idx), read by the tiled sweep
     DevBuf<double> lut, dense;
     DevBuf<double> clut;             // compact per-stage weight tables of the tiled sweep (tables.cpp: compact_table), four planes
+    DevBuf<uint32_t> clut32;         // the same tables as 32-bit halves, eight planes per stage (lo W,E,S,N, hi W,E,S,N): what K2 gathers
+    int gather32 = 0;                // K2 gathers the weights as 32-bit halves (interface-rich media, set by the domain load)
     int lut_stages = 1;              // stages resident in lut / clut (packed batches: all stages of the mode)
     std::vector<uint8_t> h_grid;
 

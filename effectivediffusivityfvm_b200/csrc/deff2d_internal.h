@@ -54,6 +54,11 @@ DEFF2D_HD inline unsigned clut_slot(unsigned p, unsigned w, unsigned e, unsigned
     return 243u + p * 256u + (w | (e << 2) | (s << 4) | (n << 6));
 }
 void compact_table(const double *lut, double *clut, int nphase);
+// The compact table as 32-bit halves: per stage eight planes of DEFF2D_CLUT_ENTRIES words (low words of wW, wE, wS, wN,
+// then their high words).  A 4-byte gather of a warp is conflict-free as long as the slots differ mod 32 (32 L1 banks of
+// 4 bytes), an 8-byte gather only if they differ mod 16: on an all-interface medium (site percolation) the 8-byte
+// gather needs 3.9 LSU cycles per load, two 4-byte gathers 2.
+void split_table(const double *clut, uint32_t *clut32, int nstages);
 
 // One continuation stage of the reference drivers: the coefficients it solves with, its stop rule, and whether it is
 // a JacobiGPUPreCond stage (its Deff and time are not reported, cuh:1144-1159 vs cuh:1309-1311).

@@ -126,8 +126,9 @@ void launch_init_domain(cudaStream_t s, const uint8_t *img, int W, int Hsrc, int
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_build_idx(const uint8_t *__restrict__ code, uint16_t *__restrict__ idx16, long long Nx, long long Ny,
-            long long pitch, long long period, int nphase, const __grid_constant__ SlotPerm perm)
+            long long pitch, long long period, int nphase, const __grid_constant__ SlotPerm perm, Counts *counts)
 {
+    unsigned cells = 0, mixed = 0;
     const long long groups_per_row = pitch / 8;
     const long long total = (Ny + 2) * groups_per_row;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total;
@@ -148,6 +149,11 @@ k_build_idx(const uint8_t *__restrict__ code, uint16_t *__restrict__ idx16, long
             // slot in the compact table (deff2d_internal.h: clut_slot); stage in bits 10-13
             unsigned v = clut_slot(cur & 3u, prev & 3u, next & 3u, s & 3u, n & 3u, (cur & 4u) != 0, nphase, perm);
             v |= ((cur >> 3) & 15u) << 10;
+            if ((cur & 3u) != 3u && !(cur & 4u)) {             // live cell: how many of them sit at a phase interface
+                cells++;
+                const unsigned ph = cur & 3u;
+                mixed += ((prev & 3u) != ph) | ((next & 3u) != ph) | ((s & 3u) != ph) | ((n & 3u) != ph);
+            }
             const long long j = c - XOFF;                      // interior column
             if (j >= -1 && j <= Nx && (j + 1) % period == 0) v |= 0x8000u;
             out[k] = v;
@@ -157,16 +163,20 @@ k_build_idx(const uint8_t *__restrict__ code, uint16_t *__restrict__ idx16, long
         *reinterpret_cast<uint4 *>(idx16 + r * pitch + c0) =
             make_uint4(out[0] | (out[1] << 16), out[2] | (out[3] << 16), out[4] | (out[5] << 16), out[6] | (out[7] << 16));
     }
+    if (counts) {
+        const unsigned long long c2 = warp_sum_u64(cells), m2 = warp_sum_u64(mixed);
+        if ((threadIdx.x & 31) == 0 && c2) { atomicAdd(&counts->idx_cells, c2); atomicAdd(&counts->idx_mixed, m2); }
+    }
 }
 
 void launch_build_idx(cudaStream_t s, const uint8_t *code, uint16_t *idx16, int64_t Nx, int64_t Ny, int64_t pitch,
-                      int64_t ghost_period, int nphase)
+                      int64_t ghost_period, int nphase, Counts *counts)
 {
     const long long total = (Ny + 2) * (pitch / 8);
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
-    k_build_idx<<<blocks, 256, 0, s>>>(code, idx16, Nx, Ny, pitch, ghost_period, nphase, slot_perm(nphase));
+    k_build_idx<<<blocks, 256, 0, s>>>(code, idx16, Nx, Ny, pitch, ghost_period, nphase, slot_perm(nphase), counts);
 }
 
 // calcPorosity's counting loop (cuh:399-405) as a reduction over the source image

@@ -65,6 +65,7 @@ struct Counts {
     unsigned long long phase[4];   // cells per phase on the amplified grid (own rows only)
     unsigned long long below150;   // source pixels < 150 (calcPorosity, cuh:401)
     unsigned long long pinned;
+    unsigned long long idx_cells, idx_mixed;   // k_build_idx: live cells, and those whose four neighbours are not all of the cell's phase
 };
 
 // ---- launchers (all asynchronous on `s`) -------------------------------------------------
@@ -79,7 +80,7 @@ void launch_init_domain(cudaStream_t s, const uint8_t *img, int W, int Hsrc, int
                         Counts *counts);
 // per-cell table index of every padded cell from the codes (see idx16 above)
 void launch_build_idx(cudaStream_t s, const uint8_t *code, uint16_t *idx16, int64_t Nx, int64_t Ny, int64_t pitch,
-                      int64_t ghost_period, int nphase);
+                      int64_t ghost_period, int nphase, Counts *counts /* NULL: no statistics */);
 void launch_count_below(cudaStream_t s, const uint8_t *img, int64_t n, int thr, Counts *counts);
 
 // K3: plain streaming sweep, one sweep per HBM pass (cuh:69-92 matrix-free)

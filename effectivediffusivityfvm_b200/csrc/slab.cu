@@ -90,6 +90,7 @@ struct SlabGraph {
     int T = 0, launches = 0;
     int64_t halo_after = 0;       // c->halo_valid at the end of the captured run
     const void *x0 = nullptr, *x1 = nullptr, *idx = nullptr, *lut = nullptr;
+    int gather32 = 0;
     double omega = 0;
     int64_t Ny = 0, above = -1, below = -1;
     bool peer = false;
@@ -332,7 +333,7 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
         if (c->use_graphs && n >= (int64_t)T * SLAB_GRAPH_PASSES) {
             SlabGraph &g = s->graph[c->cur];
             const bool valid = g.exec && g.T == T && g.x0 == c->x[0].p && g.x1 == c->x[1].p && g.idx == c->idx16.p &&
-                               g.lut == c->clut.p && g.omega == c->omega && g.Ny == c->Ny && g.above == c->halo_above && g.below == c->halo_below && g.peer == s->peer.active &&
+                               g.lut == (const void *)c->clut32.p && g.gather32 == c->gather32 && g.omega == c->omega && g.Ny == c->Ny && g.above == c->halo_above && g.below == c->halo_below && g.peer == s->peer.active &&
                                g.peer_up == (const void *)s->peer.up.x[0] && g.peer_down == (const void *)s->peer.down.x[0];
             if (!valid) {
                 if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
@@ -355,7 +356,7 @@ int slab_enqueue_sweeps(deff2d_ctx *c, int64_t n)
                 e = cudaGraphInstantiate(&g.exec, graph, 0);
                 cudaGraphDestroy(graph);
                 if (e != cudaSuccess) { g.exec = nullptr; set_error(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); rc = DEFF2D_ERR_CUDA; break; }
-                g.T = T; g.x0 = c->x[0].p; g.x1 = c->x[1].p; g.idx = c->idx16.p; g.lut = c->clut.p; g.omega = c->omega;
+                g.T = T; g.x0 = c->x[0].p; g.x1 = c->x[1].p; g.idx = c->idx16.p; g.lut = c->clut32.p; g.gather32 = c->gather32; g.omega = c->omega;
                 g.Ny = c->Ny; g.above = c->halo_above; g.below = c->halo_below; g.peer = s->peer.active;
                 g.peer_up = s->peer.up.x[0]; g.peer_down = s->peer.down.x[0];
             }

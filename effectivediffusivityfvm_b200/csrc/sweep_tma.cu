@@ -133,8 +133,9 @@ struct Cfg {
 // (685 vs 828); two 128-thread CTAs per SM on 64 x 32 tiles (744 at T = 4 vs 827).
 template <class C, bool LIST, int VAR>
 __global__ void __launch_bounds__(C::NT, 1)
-k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, double om,
-            int tiles_x, int ntiles, const uint32_t *__restrict__ tile_list, const ChebTaus taus, const PeerArgs peer)
+k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restrict__ lut, const uint32_t *__restrict__ lut32,
+            double om, int tiles_x, int ntiles, const uint32_t *__restrict__ tile_list, const ChebTaus taus,
+            const PeerArgs peer)
 {
     constexpr int T = C::T, TE = C::TE, PX = C::PX, PY = C::PY, TW = C::TW, TH = C::TH, OW = C::OW, OH = C::OH;
     constexpr int PW = C::PLANE_W, IW = C::IW;
@@ -142,6 +143,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
     // omega = 1 table u; ghost columns keep their value (factor 0)
     constexpr bool CHEB = (VAR & 2) != 0;
     constexpr bool PEER = (VAR & 1) != 0;     // peer-memory halo exchange fused into the pass (needs LIST)
+    constexpr bool G32 = (VAR & 4) != 0;      // weights gathered as 32-bit halves (interface-rich media, see fetch32)
     static_assert(!PEER || LIST, "the peer variant walks a tile list (boundary tiles early)");
     static_assert(C::NWX == 1, "a warp spans the tile width (W / E halo by shuffles)");
 
@@ -327,7 +329,7 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
 #pragma unroll
             for (int py = 0; py < PY; py++)
 #pragma unroll
-                for (int px = 0; px < PX; px++)      // offset into the table: (stage * 1024 + slot) [* 4 doubles] / stage * 4096 + slot (planar)
+                for (int px = 0; px < PX; px++)      // offset into the planar table: stage * 4096 + slot
                     idx[py][px] = ((idx[py][px] & 0x3c00u) << 2) | (idx[py][px] & 0x3ffu);
             // Most patches lie inside one phase (every cell has the same neighbourhood index):
             // one LUT entry then serves all PX*PY cells -- 2 instead of 2*PX*PY 16-byte loads.
@@ -336,6 +338,17 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
                 const double *q = wtab + e;
                 w0 = __ldg(q); w1 = __ldg(q + DEFF2D_CLUT_ENTRIES); w2 = __ldg(q + 2 * DEFF2D_CLUT_ENTRIES);
                 w3 = __ldg(q + 3 * DEFF2D_CLUT_ENTRIES);
+            };
+            // Interface-rich media (G32 variant, chosen per domain load: context.cu): two 4-byte gathers per weight from the table of
+            // 32-bit halves (eight planes per stage: offset + stage * 4096).  A 4-byte gather of a warp is conflict-free
+            // when the slots differ mod 32, an 8-byte gather only when they differ mod 16 (deff2d_internal.h).
+            auto fetch32 = [&](unsigned e, double &w0, double &w1, double &w2, double &w3) {
+                const uint32_t *q = lut32 + e + (e & ~0xfffu);
+                constexpr int N = DEFF2D_CLUT_ENTRIES;
+                w0 = __hiloint2double((int)__ldg(q + 4 * N), (int)__ldg(q));
+                w1 = __hiloint2double((int)__ldg(q + 5 * N), (int)__ldg(q + N));
+                w2 = __hiloint2double((int)__ldg(q + 6 * N), (int)__ldg(q + 2 * N));
+                w3 = __hiloint2double((int)__ldg(q + 7 * N), (int)__ldg(q + 3 * N));
             };
             if (__all_sync(0xffffffffu, uniform)) {
                 double a0, a1, a2, a3;
@@ -350,8 +363,10 @@ k_sweep_tma(const __grid_constant__ TmaMaps maps, int src, const double *__restr
 #pragma unroll
                 for (int py = 0; py < PY; py++)
 #pragma unroll
-                    for (int px = 0; px < PX; px++)
-                        fetch(idx[py][px], w[py][px][0], w[py][px][1], w[py][px][2], w[py][px][3]);
+                    for (int px = 0; px < PX; px++) {
+                        if constexpr (G32) fetch32(idx[py][px], w[py][px][0], w[py][px][1], w[py][px][2], w[py][px][3]);
+                        else fetch(idx[py][px], w[py][px][0], w[py][px][1], w[py][px][2], w[py][px][3]);
+                    }
             }
         }
 
@@ -519,9 +534,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
 struct GraphEntry {
     cudaGraphExec_t exec = nullptr;
     uint64_t version = 0;        // tensor-map generation the graph was captured with
-    int T = 0, fam = 0, src = 0, count = 0, grid_limit = 0;
+    int T = 0, fam = 0, src = 0, count = 0, grid_limit = 0, gather32 = 0;
     const uint32_t *list = nullptr;
-    const double *lut = nullptr;
+    const void *lut = nullptr;
     double omega = 0;
 };
 
@@ -598,8 +613,7 @@ static int launch_T(deff2d_ctx *c, TmaState *ts, int src, const uint32_t *list, 
     int grid = c->prop.multiProcessorCount;
     if (c->grid_limit > 0 && grid > c->grid_limit) grid = c->grid_limit;
     if (grid > ntiles) grid = ntiles;
-    const double *table = c->clut.p;
-    kern<<<grid, C::NT, smem, stream>>>(ts->maps, src, table, 1.0 - c->omega, ts->tiles_x, ntiles, list, taus, peer);
+    kern<<<grid, C::NT, smem, stream>>>(ts->maps, src, c->clut.p, c->clut32.p, 1.0 - c->omega, ts->tiles_x, ntiles, list, taus, peer);
     return DEFF2D_OK;
 }
 
@@ -679,14 +693,23 @@ static int pass_from(deff2d_ctx *c, int T, int src, const uint32_t *list, int co
         rc = launch_T<TT, FF, 0>(c, ts, src, list, count, stream);                                             \
         if (rc) return rc;                                                                                     \
     }
+#define DEFF2D_VAR32(TT)                                                                                       \
+    {                                                                                                          \
+        if ((rc = prepare_T<TT, 4>(c, ts))) return rc;                                                         \
+        rc = launch_T<TT, 4, 4>(c, ts, src, nullptr, 0, stream);                                               \
+        if (rc) return rc;                                                                                     \
+    }
+    // interface-rich single domains and NCCL slabs (no tile list) in the default layout: the 32-bit gather variant
 #define DEFF2D_CASE(TT)                                                                   \
     case TT:                                                                              \
-        if (fam == 4) DEFF2D_VAR(TT, 4) else DEFF2D_VAR(TT, 3)                            \
+        if (fam == 4 && c->gather32 && !list) DEFF2D_VAR32(TT)                            \
+        else if (fam == 4) DEFF2D_VAR(TT, 4) else DEFF2D_VAR(TT, 3)                       \
         break;
     switch (T) {
         DEFF2D_CASE(1) DEFF2D_CASE(2) DEFF2D_CASE(3) DEFF2D_CASE(4) DEFF2D_CASE(5) DEFF2D_CASE(6) DEFF2D_CASE(7) DEFF2D_CASE(8)
     }
 #undef DEFF2D_CASE
+#undef DEFF2D_VAR32
 #undef DEFF2D_VAR
     return DEFF2D_OK;
 }
@@ -722,7 +745,7 @@ static int peer_launch(deff2d_ctx *c, TmaState *ts, const uint32_t *list, int co
     }
     int grid = c->prop.multiProcessorCount;
     if (grid > count) grid = count;
-    kern<<<grid, C::NT, C::SMEM, c->stream>>>(ts->maps, c->cur, c->clut.p, 1.0 - c->omega, ts->tiles_x, count, list, ChebTaus(), pa);
+    kern<<<grid, C::NT, C::SMEM, c->stream>>>(ts->maps, c->cur, c->clut.p, c->clut32.p, 1.0 - c->omega, ts->tiles_x, count, list, ChebTaus(), pa);
     return DEFF2D_OK;
 }
 
@@ -781,7 +804,7 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
         GraphEntry *g = nullptr;
         for (auto &e : ts->graphs)
             if (e.exec && e.version == ts->version && e.T == T && e.fam == k2_family(c) && e.src == c->cur && e.list == list &&
-                e.count == count && e.grid_limit == c->grid_limit && e.lut == c->clut.p && e.omega == c->omega) { g = &e; break; }
+                e.count == count && e.grid_limit == c->grid_limit && e.lut == (const void *)c->clut32.p && e.gather32 == c->gather32 && e.omega == c->omega) { g = &e; break; }
         if (!g) {
             // drop stale graphs, then capture GRAPH_PASSES passes
             for (auto &e : ts->graphs)
@@ -804,7 +827,7 @@ int tma_passes(deff2d_ctx *c, int T, int64_t npasses, const uint32_t *list, int 
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) { slot->exec = nullptr; set_error(c, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); return DEFF2D_ERR_CUDA; }
             slot->version = ts->version; slot->T = T; slot->fam = k2_family(c); slot->src = c->cur; slot->list = list;
-            slot->count = count; slot->grid_limit = c->grid_limit; slot->lut = c->clut.p; slot->omega = c->omega;
+            slot->count = count; slot->grid_limit = c->grid_limit; slot->lut = c->clut32.p; slot->gather32 = c->gather32; slot->omega = c->omega;
             g = slot;
         }
         cudaError_t e = cudaGraphLaunch(g->exec, c->stream);

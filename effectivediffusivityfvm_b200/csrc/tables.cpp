@@ -158,6 +158,18 @@ void compact_table(const double *lut, double *clut, int nphase)
         }
 }
 
+void split_table(const double *clut, uint32_t *clut32, int nstages)
+{
+    for (int k = 0; k < nstages; k++)
+        for (int f = 0; f < 4; f++)
+            for (int e = 0; e < DEFF2D_CLUT_ENTRIES; e++) {
+                uint64_t bits;
+                std::memcpy(&bits, clut + ((size_t)k * 4 + f) * DEFF2D_CLUT_ENTRIES + e, sizeof(bits));
+                clut32[((size_t)k * 8 + f) * DEFF2D_CLUT_ENTRIES + e] = (uint32_t)bits;
+                clut32[((size_t)k * 8 + 4 + f) * DEFF2D_CLUT_ENTRIES + e] = (uint32_t)(bits >> 32);
+            }
+}
+
 }  // namespace deff2d
 
 DEFF2D_EXPORT int deff2d_build_tables(double Ds, double Df, double Dg, int64_t Nx, int64_t Ny, double CL,
