@@ -117,6 +117,7 @@ def lib():
         "deff2d_accumulate_fraction": (dbl, [i64, i64]),
         "deff2d_build_tables": (i32, [dbl, dbl, dbl, i64, i64, dbl, dbl, dbl, c_double_p, c_ubyte_p]),
         "deff2d_compact_table": (i32, [c_double_p, i32, c_double_p, C.POINTER(C.c_uint16)]),
+        "deff2d_split_table": (i32, [c_double_p, i32, C.POINTER(C.c_uint32)]),
         "deff2d_floodfill": (i32, [c_ubyte_p, i64, i64]),
         "deff2d_tile_geometry": (i32, [i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
         "deff2d_batch_plan": (i32, [i64, i64, i32, i32, C.POINTER(i32), C.POINTER(i32)]),

@@ -199,3 +199,10 @@ DEFF2D_EXPORT int deff2d_compact_table(const double *lut, int nphase, double *cl
     }
     return DEFF2D_OK;
 }
+
+DEFF2D_EXPORT int deff2d_split_table(const double *clut, int nstages, uint32_t *clut32)
+{
+    if (!clut || !clut32 || nstages < 1) return DEFF2D_ERR_ARG;
+    deff2d::split_table(clut, clut32, nstages);
+    return DEFF2D_OK;
+}

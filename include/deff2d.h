@@ -268,6 +268,10 @@ int deff2d_build_tables(double Ds, double Df, double Dg, int64_t Nx, int64_t Ny,
  * `nphase` phases).  Interior neighbourhoods are ranked: single-phase first, then one differing neighbour, ... so
  * that the gathers of a warp touch as few cache lines as possible.  Either output may be NULL. */
 int deff2d_compact_table(const double *lut, int nphase, double *clut, uint16_t *slot);
+/* The compact table(s) as 32-bit halves, the form the tiled sweep gathers from on interface-rich media: per stage eight
+ * planes of 1024 words -- the low words of wW, wE, wS, wN, then their high words (clut: nstages * 4 * 1024 doubles in,
+ * clut32: nstages * 8 * 1024 words out). */
+int deff2d_split_table(const double *clut, int nstages, uint32_t *clut32);
 /* FloodFill (cuh:557-713) on a solid mask (1 = solid), incl. the y-periodic wrap and the
  * right-column seeding quirk (cuh:601).  grid: Ny*Nx bytes in/out (unreached non-solid
  * cells become 2).  Returns PathFlag (0/1) or a negative status. */

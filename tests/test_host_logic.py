@@ -102,6 +102,11 @@ def test_compact_table_is_a_ranked_rearrangement_of_the_lut(nphase, Ds, Dg):
     interior = live & np.all([q != 3 for q in ph[1:]], axis=0)
     n_int = nphase ** 5
     assert sorted(slot[interior]) == list(range(n_int))
+    # the 32-bit halves the tiled sweep gathers on interface-rich media reassemble to the same doubles
+    halves = np.zeros(8 * 1024, dtype=np.uint32)
+    assert L.deff2d_split_table(clut.ctypes.data_as(C.POINTER(C.c_double)), 1, halves.ctypes.data_as(C.POINTER(C.c_uint32))) == 0
+    halves = halves.reshape(8, 1024).astype(np.uint64)
+    assert np.array_equal((halves[4:] << np.uint64(32)) | halves[:4], np.ascontiguousarray(clut).view(np.uint64))
     if nphase == 3:                                                    # (2-phase: dense numbering, one line per centre phase)
         ndiff = sum((q != ph[0]).astype(int) for q in ph[1:])
         order = np.argsort(slot[interior])
